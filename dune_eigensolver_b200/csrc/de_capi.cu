@@ -1,0 +1,1677 @@
+// libdune_eigensolver_b200.so -- C ABI (include/dune_eigensolver_b200.h) over the sm_100a kernels.
+//
+// Host-side runtime of the block-eigensolver hot path: contexts (stream, workspaces, NCCL communicator),
+// device-resident matrices / multivectors / factor schedules, the kernel launch logic and the three
+// device-resident driver loops (reference eigensolver.hh:28-112, :116-198, :204-351).
+// No CPU fallback exists: every compute entry point needs a CUDA device and fails with DE_ERR_CUDA otherwise.
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+#include <random>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <nccl.h> // types only; the library is bound at run time with dlopen (see NcclApi)
+
+#define DE_KERNEL_MAX_M 64
+
+#include "../../include/dune_eigensolver_b200.h"
+#include "../../include/dune/eigensolver/sparse_lu.hh"
+#include "kernels_dense.cuh"
+#include "kernels_sparse.cuh"
+#include "kernels_trsv.cuh"
+
+// ====================================================================================================
+// error plumbing
+// ====================================================================================================
+namespace
+{
+  thread_local std::string g_thread_error;
+
+  constexpr int kMaxPartials = 592;               // CTAs of a reduction kernel (4 per SM on 148 SMs)
+  constexpr size_t kPartialDoubles = (size_t)2 * kMaxPartials * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M;
+  constexpr int kSmall = 4 * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M + 1024; // doubles of small device / pinned scratch
+}
+
+struct NcclApi
+{
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+static NcclApi &nccl_api()
+{
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried)
+  {
+    tried = true;
+    // a process that already loaded NCCL (torch) resolves to that copy through the soname
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (api.handle)
+    {
+      auto sym = [&](const char *n) { return dlsym(api.handle, n); };
+      api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+      api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+      api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+      api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+      api.Send = (decltype(api.Send))sym("ncclSend");
+      api.Recv = (decltype(api.Recv))sym("ncclRecv");
+      api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+      api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+      api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Send && api.Recv &&
+               api.GroupStart && api.GroupEnd && api.GetErrorString;
+    }
+  }
+  return api;
+}
+
+struct de_context
+{
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
+  int sm_count = 148;
+  int rank = 0, nranks = 1;
+  ncclComm_t comm = nullptr;
+  mutable std::string err;
+  double *partials = nullptr; // kPartialDoubles
+  double *dsmall = nullptr;   // kSmall doubles: G | Rinv | dp | info
+  int *dstatus = nullptr;     // sticky Cholesky status
+  double *hsmall = nullptr;   // pinned mirror of dsmall
+  int *hstatus = nullptr;     // pinned
+  double *stage = nullptr;    // layout-conversion staging
+  size_t stage_bytes = 0;
+  long long launches = 0;
+
+  double *dG() const { return dsmall; }
+  double *dR() const { return dsmall + DE_KERNEL_MAX_M * DE_KERNEL_MAX_M; }
+  double *dDP() const { return dsmall + 2 * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M; }
+  double *dInfo() const { return dsmall + 2 * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M + 512; }
+};
+
+struct de_mv
+{
+  de_context *ctx;
+  long long n;
+  int m;
+  double *d;
+};
+
+struct de_matrix
+{
+  de_context *ctx;
+  long long n = 0, n_halo = 0, nnz = 0;
+  int *rowptr = nullptr, *col = nullptr;
+  double *val = nullptr;
+  // distributed part
+  int npeers = 0;
+  std::vector<int> peer;
+  std::vector<long long> recv_count, recv_off, send_count, send_off;
+  long long n_send = 0;
+  int *send_rows = nullptr;
+  int *interior = nullptr, *boundary = nullptr;
+  long long n_interior = 0, n_boundary = 0;
+  double *send_buf = nullptr, *halo_buf = nullptr;
+  int buf_m = 0;
+};
+
+struct TrsvSegment
+{
+  int chain;     // 1: chain kernel over levels [a,b) ; 0: single wide level a
+  int a, b;
+};
+
+struct TrsvSchedule
+{
+  int *rows = nullptr, *rowptr = nullptr, *col = nullptr, *level_ptr = nullptr;
+  double *val = nullptr, *invdiag = nullptr;
+  std::vector<int> h_level_ptr;
+  std::vector<TrsvSegment> segments;
+  int nlevels = 0;
+  long long nnz = 0;
+};
+
+struct de_factor
+{
+  de_context *ctx;
+  long long n = 0, lnz = 0, unz = 0;
+  TrsvSchedule L, U;
+  int *P = nullptr, *Q = nullptr;
+  double *rowscale = nullptr;
+  double *W = nullptr;
+  int W_m = 0;
+};
+
+struct de_host_factor
+{
+  de_b200::FactorArrays F;
+};
+
+namespace
+{
+  int set_error(const de_context *ctx, int code, const std::string &msg)
+  {
+    g_thread_error = msg;
+    if (ctx)
+      ctx->err = msg;
+    return code;
+  }
+
+#define DE_CUDA(ctx, call)                                                                                   \
+  do                                                                                                         \
+  {                                                                                                          \
+    cudaError_t e__ = (call);                                                                                \
+    if (e__ != cudaSuccess)                                                                                  \
+      return set_error(ctx, DE_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
+  } while (0)
+
+#define DE_NCCL(ctx, call)                                                                                   \
+  do                                                                                                         \
+  {                                                                                                          \
+    ncclResult_t r__ = (call);                                                                               \
+    if (r__ != ncclSuccess)                                                                                  \
+      return set_error(ctx, DE_ERR_NCCL, std::string(#call) + ": " + nccl_api().GetErrorString(r__));        \
+  } while (0)
+
+#define DE_TRY(call)                                                                                         \
+  do                                                                                                         \
+  {                                                                                                          \
+    int s__ = (call);                                                                                        \
+    if (s__ != DE_OK)                                                                                        \
+      return s__;                                                                                            \
+  } while (0)
+
+#define DE_LAUNCH_CHECK(ctx)                                                                                 \
+  do                                                                                                         \
+  {                                                                                                          \
+    (ctx)->launches++;                                                                                       \
+    DE_CUDA(ctx, cudaGetLastError());                                                                        \
+  } while (0)
+
+  bool valid_cols(int m) { return m > 0 && m % 8 == 0 && m <= DE_MAX_COLS; }
+
+  template <class T>
+  int dev_alloc(de_context *ctx, T **p, size_t count)
+  {
+    *p = nullptr;
+    if (count == 0)
+      count = 1;
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    if (e != cudaSuccess)
+      return set_error(ctx, e == cudaErrorMemoryAllocation ? DE_ERR_ALLOC : DE_ERR_CUDA,
+                       std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return DE_OK;
+  }
+
+  template <class T, class S>
+  int upload_converted(de_context *ctx, T **dst, const S *src, size_t count)
+  {
+    std::vector<T> tmp(count);
+    for (size_t i = 0; i < count; ++i)
+      tmp[i] = (T)src[i];
+    DE_TRY(dev_alloc(ctx, dst, count));
+    DE_CUDA(ctx, cudaMemcpyAsync(*dst, tmp.data(), count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // tmp dies here
+    return DE_OK;
+  }
+
+  int bind_device(const de_context *ctx)
+  {
+    DE_CUDA(ctx, cudaSetDevice(ctx->device));
+    return DE_OK;
+  }
+
+  // ---- reductions -----------------------------------------------------------------------------------
+  int reduce_partials(de_context *ctx, const double *partials, int nparts, int len, double *out)
+  {
+    dim3 block(32, 32);
+    de::reduce_partials_kernel<<<(len + 31) / 32, block, 0, ctx->stream>>>(partials, nparts, len, out);
+    DE_LAUNCH_CHECK(ctx);
+    return DE_OK;
+  }
+
+  int allreduce_sum(de_context *ctx, double *buf, size_t count)
+  {
+    if (ctx->nranks > 1)
+      DE_NCCL(ctx, nccl_api().AllReduce(buf, buf, count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    return DE_OK;
+  }
+
+  // ---- SpMM -----------------------------------------------------------------------------------------
+  template <bool DOT>
+  int launch_spmm_rows(de_context *ctx, const de_matrix *A, const double *X, double *Y, int m, const int *rowlist,
+                       long long nrows, double *partials, int *grid_out)
+  {
+    *grid_out = 0;
+    if (nrows <= 0)
+      return DE_OK;
+    de::SpmmArgs a;
+    a.nrows = nrows;
+    a.rowlist = rowlist;
+    a.rowptr = A->rowptr;
+    a.col = A->col;
+    a.val = A->val;
+    a.X = X;
+    a.H = A->halo_buf;
+    a.n_owned = A->n;
+    a.ld = m;
+    a.m = m;
+    a.Y = Y;
+    a.partials = partials;
+    const int hp = m / 2;
+    const int tpr = hp <= 4 ? 4 : (hp <= 8 ? 8 : (hp <= 16 ? 16 : 32));
+    const int rpb = 256 / tpr;
+    const long long need = (nrows + rpb - 1) / rpb;
+    const int cap = DOT ? kMaxPartials : ctx->sm_count * 8;
+    const int grid = (int)std::min<long long>(need, cap);
+    switch (tpr)
+    {
+    case 4:
+      de::spmm_kernel<4, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+      break;
+    case 8:
+      de::spmm_kernel<8, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+      break;
+    case 16:
+      de::spmm_kernel<16, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+      break;
+    default:
+      de::spmm_kernel<32, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+      break;
+    }
+    DE_LAUNCH_CHECK(ctx);
+    *grid_out = grid;
+    return DE_OK;
+  }
+
+  int ensure_halo_buffers(de_context *ctx, de_matrix *A, int m)
+  {
+    if (A->buf_m >= m)
+      return DE_OK;
+    if (A->send_buf)
+      cudaFree(A->send_buf);
+    if (A->halo_buf)
+      cudaFree(A->halo_buf);
+    A->send_buf = A->halo_buf = nullptr;
+    DE_TRY(dev_alloc(ctx, &A->send_buf, (size_t)A->n_send * m));
+    DE_TRY(dev_alloc(ctx, &A->halo_buf, (size_t)A->n_halo * m));
+    A->buf_m = m;
+    return DE_OK;
+  }
+
+  /** Y = A X (+ dp = diag(X^T Y) into ctx->dDP when DOT). Distributed matrices first start the halo exchange
+   *  (pack -> NCCL send/recv over NVLink on the communication stream), run the interior rows meanwhile, then the
+   *  boundary rows once the halo rows have landed. */
+  template <bool DOT>
+  int spmm_device(de_context *ctx, const de_matrix *Ac, const double *X, double *Y, int m)
+  {
+    de_matrix *A = const_cast<de_matrix *>(Ac);
+    int g1 = 0, g2 = 0;
+    const bool dist = ctx->nranks > 1 && (A->n_halo > 0 || A->n_send > 0);
+    if (!dist)
+    {
+      DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, nullptr, A->n, ctx->partials, &g1));
+    }
+    else
+    {
+      DE_TRY(ensure_halo_buffers(ctx, A, m));
+      if (A->n_send > 0)
+      {
+        const long long total = A->n_send * (m / 2);
+        const int grid = (int)std::min<long long>((total + 255) / 256, ctx->sm_count * 8);
+        de::pack_rows_kernel<<<grid, 256, 0, ctx->stream>>>(A->n_send, A->send_rows, m, X, A->send_buf);
+        DE_LAUNCH_CHECK(ctx);
+      }
+      DE_CUDA(ctx, cudaEventRecord(ctx->ev_pack, ctx->stream));
+      DE_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_pack, 0));
+      NcclApi &nc = nccl_api();
+      DE_NCCL(ctx, nc.GroupStart());
+      for (int p = 0; p < A->npeers; ++p)
+      {
+        if (A->send_count[p] > 0)
+          DE_NCCL(ctx, nc.Send(A->send_buf + (size_t)A->send_off[p] * m, (size_t)A->send_count[p] * m, ncclDouble,
+                               A->peer[p], ctx->comm, ctx->comm_stream));
+        if (A->recv_count[p] > 0)
+          DE_NCCL(ctx, nc.Recv(A->halo_buf + (size_t)A->recv_off[p] * m, (size_t)A->recv_count[p] * m, ncclDouble,
+                               A->peer[p], ctx->comm, ctx->comm_stream));
+      }
+      DE_NCCL(ctx, nc.GroupEnd());
+      DE_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+      DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->interior, A->n_interior, ctx->partials, &g1));
+      DE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+      DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->boundary, A->n_boundary, ctx->partials + (size_t)g1 * m, &g2));
+    }
+    if (DOT)
+    {
+      if (g1 + g2 > 0)
+        DE_TRY(reduce_partials(ctx, ctx->partials, g1 + g2, m, ctx->dDP()));
+      else
+        DE_CUDA(ctx, cudaMemsetAsync(ctx->dDP(), 0, sizeof(double) * m, ctx->stream));
+      DE_TRY(allreduce_sum(ctx, ctx->dDP(), m));
+    }
+    return DE_OK;
+  }
+
+  // ---- diag-dot ---------------------------------------------------------------------------------------
+  int diag_dot_device(de_context *ctx, long long n, int m, const double *X, const double *Y, double *out)
+  {
+    const int hp = m / 2;
+    dim3 block(hp, 256 / hp);
+    const long long need = (n + block.y - 1) / block.y;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(need, kMaxPartials));
+    de::diag_dot_kernel<<<grid, block, 0, ctx->stream>>>(n, X, m, Y, m, m, ctx->partials);
+    DE_LAUNCH_CHECK(ctx);
+    DE_TRY(reduce_partials(ctx, ctx->partials, grid, m, out));
+    return allreduce_sum(ctx, out, m);
+  }
+
+  // ---- Gram -------------------------------------------------------------------------------------------
+  template <int M, bool UPPER, bool SAME>
+  int launch_gram_t(de_context *ctx, long long n, const double *X, int ldx, const double *Y, int ldy, double *out)
+  {
+    using C = de::GramCfg<M, UPPER, SAME>;
+    const long long ntiles = (n + C::TR - 1) / C::TR;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, kMaxPartials));
+    de::gram_kernel<M, UPPER, SAME><<<grid, C::THREADS, 0, ctx->stream>>>(n, X, ldx, Y, ldy, ctx->partials);
+    DE_LAUNCH_CHECK(ctx);
+    return reduce_partials(ctx, ctx->partials, grid, M * M, out);
+  }
+
+  template <bool UPPER, bool SAME>
+  int launch_gram_m(de_context *ctx, int w, long long n, const double *X, int ldx, const double *Y, int ldy, double *out)
+  {
+    switch (w)
+    {
+    case 8:
+      return launch_gram_t<8, UPPER, SAME>(ctx, n, X, ldx, Y, ldy, out);
+    case 16:
+      return launch_gram_t<16, UPPER, SAME>(ctx, n, X, ldx, Y, ldy, out);
+    case 24:
+      return launch_gram_t<24, UPPER, SAME>(ctx, n, X, ldx, Y, ldy, out);
+    case 32:
+      return launch_gram_t<32, UPPER, SAME>(ctx, n, X, ldx, Y, ldy, out);
+    case 40:
+      return launch_gram_t<40, UPPER, SAME>(ctx, n, X, ldx, Y, ldy, out);
+    case 48:
+      return launch_gram_t<48, UPPER, SAME>(ctx, n, X, ldx, Y, ldy, out);
+    case 56:
+      return launch_gram_t<56, UPPER, SAME>(ctx, n, X, ldx, Y, ldy, out);
+    case 64:
+      return launch_gram_t<64, UPPER, SAME>(ctx, n, X, ldx, Y, ldy, out);
+    }
+    return set_error(ctx, DE_ERR_UNSUPPORTED, "gram: column count must be a multiple of 8 in [8,64]");
+  }
+
+  /** out (device, w*w) = X^T Y over the local rows, all-reduced over the ranks.
+   *  symmetric: the result is known to be symmetric (only upper blocks are computed and mirrored). */
+  int gram_device(de_context *ctx, int w, long long n, const double *X, int ldx, const double *Y, int ldy,
+                  bool symmetric, double *out)
+  {
+    const bool same = (X == Y && ldx == ldy);
+    if (symmetric && same)
+      DE_TRY((launch_gram_m<true, true>(ctx, w, n, X, ldx, Y, ldy, out)));
+    else if (symmetric)
+      DE_TRY((launch_gram_m<true, false>(ctx, w, n, X, ldx, Y, ldy, out)));
+    else if (same)
+      DE_TRY((launch_gram_m<false, true>(ctx, w, n, X, ldx, Y, ldy, out)));
+    else
+      DE_TRY((launch_gram_m<false, false>(ctx, w, n, X, ldx, Y, ldy, out)));
+    return allreduce_sum(ctx, out, (size_t)w * w);
+  }
+
+  // ---- block update -----------------------------------------------------------------------------------
+  template <int M, int MODE>
+  int launch_update_t(de_context *ctx, long long n, const double *X, int ldx, const double *R, double *Y, int ldy,
+                      int upper)
+  {
+    using C = de::UpdCfg<M>;
+    static bool configured = false; // per instantiation; same attribute for every device of this process
+    if (!configured)
+    {
+      DE_CUDA(ctx, cudaFuncSetAttribute(de::update_kernel<M, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)C::SMEM_BYTES));
+      configured = true;
+    }
+    const long long ntiles = (n + C::TR - 1) / C::TR;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / C::SMEM_BYTES));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * per_sm));
+    de::update_kernel<M, MODE><<<grid, C::THREADS, C::SMEM_BYTES, ctx->stream>>>(n, X, ldx, R, Y, ldy, upper);
+    DE_LAUNCH_CHECK(ctx);
+    return DE_OK;
+  }
+
+  template <int MODE>
+  int update_device(de_context *ctx, int w, long long n, const double *X, int ldx, const double *R, double *Y, int ldy,
+                    int upper)
+  {
+    switch (w)
+    {
+    case 8:
+      return launch_update_t<8, MODE>(ctx, n, X, ldx, R, Y, ldy, upper);
+    case 16:
+      return launch_update_t<16, MODE>(ctx, n, X, ldx, R, Y, ldy, upper);
+    case 24:
+      return launch_update_t<24, MODE>(ctx, n, X, ldx, R, Y, ldy, upper);
+    case 32:
+      return launch_update_t<32, MODE>(ctx, n, X, ldx, R, Y, ldy, upper);
+    case 40:
+      return launch_update_t<40, MODE>(ctx, n, X, ldx, R, Y, ldy, upper);
+    case 48:
+      return launch_update_t<48, MODE>(ctx, n, X, ldx, R, Y, ldy, upper);
+    case 56:
+      return launch_update_t<56, MODE>(ctx, n, X, ldx, R, Y, ldy, upper);
+    case 64:
+      return launch_update_t<64, MODE>(ctx, n, X, ldx, R, Y, ldy, upper);
+    }
+    return set_error(ctx, DE_ERR_UNSUPPORTED, "block update: column count must be a multiple of 8 in [8,64]");
+  }
+
+  // ---- (B-)orthonormalisation: CholQR2 ------------------------------------------------------------------
+  int chol_inverse(de_context *ctx, int m, const double *G, double *Rinv, double *info)
+  {
+    de::chol_inverse_kernel<<<1, 256, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info);
+    DE_LAUNCH_CHECK(ctx);
+    return DE_OK;
+  }
+
+  /** X <- X R^-1 (thin QR with positive-diagonal triangular R; reference orthonormalize_blocked,
+   *  kernels_cpp.hh:180-351). Two CholQR sweeps over the WHOLE block: G = X^T X, R = chol(G), X <- X R^-1.
+   *  The triangular factor of a full-rank block is unique, so the result equals the reference's block
+   *  Gram-Schmidt up to round-off; the second sweep restores orthogonality to O(eps) for cond(X) < ~1e7. */
+  int orthonormalize_device(de_context *ctx, long long n, int m, double *X)
+  {
+    for (int sweep = 0; sweep < 2; ++sweep)
+    {
+      DE_TRY(gram_device(ctx, m, n, X, m, X, m, true, ctx->dG()));
+      DE_TRY(chol_inverse(ctx, m, ctx->dG(), ctx->dR(), nullptr));
+      DE_TRY(update_device<0>(ctx, m, n, X, m, ctx->dR(), X, m, 1));
+    }
+    return DE_OK;
+  }
+
+  /** X^T B X = I (reference B_orthonormalize_blocked, kernels_cpp.hh:356-591). BX = B X is formed once with the
+   *  SpMM kernel and then carried through both sweeps with the same triangular factor (the reference keeps
+   *  P = B V_k updated the same way, :527-539), so on return BX = B X for the new X. */
+  int b_orthonormalize_device(de_context *ctx, const de_matrix *B, long long n, int m, double *X, double *BX,
+                              bool want_info)
+  {
+    DE_TRY(spmm_device<false>(ctx, B, X, BX, m));
+    for (int sweep = 0; sweep < 2; ++sweep)
+    {
+      DE_TRY(gram_device(ctx, m, n, X, m, BX, m, true, ctx->dG()));
+      DE_TRY(chol_inverse(ctx, m, ctx->dG(), ctx->dR(), (want_info && sweep == 0) ? ctx->dInfo() : nullptr));
+      DE_TRY(update_device<0>(ctx, m, n, X, m, ctx->dR(), X, m, 1));
+      DE_TRY(update_device<0>(ctx, m, n, BX, m, ctx->dR(), BX, m, 1));
+    }
+    return DE_OK;
+  }
+
+  int reset_status(de_context *ctx)
+  {
+    DE_CUDA(ctx, cudaMemsetAsync(ctx->dstatus, 0, sizeof(int), ctx->stream));
+    return DE_OK;
+  }
+
+  /** copy `count` doubles of device scratch and the sticky status to the host and wait for them */
+  int fetch_small(de_context *ctx, const double *dsrc, double *hdst, size_t count)
+  {
+    if (count > 0)
+      DE_CUDA(ctx, cudaMemcpyAsync(ctx->hsmall, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaMemcpyAsync(ctx->hstatus, ctx->dstatus, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (count > 0 && hdst != ctx->hsmall)
+      std::memcpy(hdst, ctx->hsmall, count * sizeof(double));
+    if (*ctx->hstatus != 0)
+      return set_error(ctx, DE_ERR_SINGULAR,
+                       "orthonormalize: Gram matrix is not positive definite (pivot " + std::to_string(*ctx->hstatus - 1) +
+                           "); the block is numerically rank deficient");
+    return DE_OK;
+  }
+
+  // ---- triangular solves --------------------------------------------------------------------------------
+  constexpr int kChainMaxRows = 32;
+
+  /** rows sorted by level for a strictly-triangular CSR whose dependencies point to already-solved rows */
+  int build_schedule(de_context *ctx, long long n, const std::vector<int> &ptr, const std::vector<int> &col,
+                     const std::vector<double> &val, const std::vector<double> *invdiag, bool lower, TrsvSchedule &S)
+  {
+    std::vector<int> level(n, 0);
+    int nlev = 0;
+    if (lower)
+      for (long long i = 0; i < n; ++i)
+      {
+        int l = 0;
+        for (int k = ptr[i]; k < ptr[i + 1]; ++k)
+          l = std::max(l, level[col[k]] + 1);
+        level[i] = l;
+        nlev = std::max(nlev, l + 1);
+      }
+    else
+      for (long long i = n - 1; i >= 0; --i)
+      {
+        int l = 0;
+        for (int k = ptr[i]; k < ptr[i + 1]; ++k)
+          l = std::max(l, level[col[k]] + 1);
+        level[i] = l;
+        nlev = std::max(nlev, l + 1);
+      }
+    if (n == 0)
+      nlev = 0;
+    S.nlevels = nlev;
+    S.h_level_ptr.assign(nlev + 1, 0);
+    for (long long i = 0; i < n; ++i)
+      S.h_level_ptr[level[i] + 1]++;
+    for (int l = 0; l < nlev; ++l)
+      S.h_level_ptr[l + 1] += S.h_level_ptr[l];
+    std::vector<int> rows(n), fill(S.h_level_ptr.begin(), S.h_level_ptr.end() - (nlev >= 0 ? 1 : 0));
+    for (long long i = 0; i < n; ++i)
+      rows[fill[level[i]]++] = (int)i;
+    // segments: runs of narrow levels are chained in one CTA, wide levels get their own launch
+    S.segments.clear();
+    for (int l = 0; l < nlev;)
+    {
+      const int width = S.h_level_ptr[l + 1] - S.h_level_ptr[l];
+      if (width <= kChainMaxRows)
+      {
+        int e = l + 1;
+        while (e < nlev && S.h_level_ptr[e + 1] - S.h_level_ptr[e] <= kChainMaxRows)
+          ++e;
+        S.segments.push_back(TrsvSegment{1, l, e});
+        l = e;
+      }
+      else
+      {
+        S.segments.push_back(TrsvSegment{0, l, l + 1});
+        ++l;
+      }
+    }
+    S.nnz = (long long)col.size();
+    DE_TRY(upload_converted(ctx, &S.rows, rows.data(), rows.size()));
+    DE_TRY(upload_converted(ctx, &S.rowptr, ptr.data(), ptr.size()));
+    DE_TRY(upload_converted(ctx, &S.col, col.data(), col.size()));
+    DE_TRY(upload_converted(ctx, &S.val, val.data(), val.size()));
+    DE_TRY(upload_converted(ctx, &S.level_ptr, S.h_level_ptr.data(), S.h_level_ptr.size()));
+    if (invdiag)
+      DE_TRY(upload_converted(ctx, &S.invdiag, invdiag->data(), invdiag->size()));
+    return DE_OK;
+  }
+
+  void free_schedule(TrsvSchedule &S)
+  {
+    cudaFree(S.rows);
+    cudaFree(S.rowptr);
+    cudaFree(S.col);
+    cudaFree(S.val);
+    cudaFree(S.level_ptr);
+    cudaFree(S.invdiag);
+  }
+
+  template <int LC>
+  int run_schedule_t(de_context *ctx, const TrsvSchedule &S, double *W, int m)
+  {
+    de::TrsvArgs a{S.rows, S.rowptr, S.col, S.val, S.invdiag, W, m};
+    for (const TrsvSegment &seg : S.segments)
+    {
+      if (seg.chain)
+        de::trsv_chain_kernel<LC><<<1, 1024, 0, ctx->stream>>>(a, S.level_ptr, seg.a, seg.b);
+      else
+      {
+        const int first = S.h_level_ptr[seg.a], count = S.h_level_ptr[seg.a + 1] - first;
+        de::trsv_level_kernel<LC><<<(count + 7) / 8, 256, 0, ctx->stream>>>(a, first, count);
+      }
+      DE_LAUNCH_CHECK(ctx);
+    }
+    return DE_OK;
+  }
+
+  int run_schedule(de_context *ctx, const TrsvSchedule &S, double *W, int m)
+  {
+    const int hp = m / 2;
+    if (hp <= 4)
+      return run_schedule_t<4>(ctx, S, W, m);
+    if (hp <= 8)
+      return run_schedule_t<8>(ctx, S, W, m);
+    if (hp <= 16)
+      return run_schedule_t<16>(ctx, S, W, m);
+    return run_schedule_t<32>(ctx, S, W, m);
+  }
+
+  int ensure_factor_work(de_context *ctx, de_factor *F, int m)
+  {
+    if (F->W_m >= m)
+      return DE_OK;
+    if (F->W)
+      cudaFree(F->W);
+    F->W = nullptr;
+    DE_TRY(dev_alloc(ctx, &F->W, (size_t)F->n * m));
+    F->W_m = m;
+    return DE_OK;
+  }
+
+  /** Y = (factored A)^-1 X (reference matmul_inverse_tallskinny_blocked, kernels_cpp.hh:660-755) */
+  int factor_apply_device(de_context *ctx, const de_factor *Fc, const double *X, double *Y, int m)
+  {
+    de_factor *F = const_cast<de_factor *>(Fc);
+    if (ctx->nranks > 1)
+      return set_error(ctx, DE_ERR_UNSUPPORTED, "factored apply is single-GPU (triangular solves do not row-shard)");
+    DE_TRY(ensure_factor_work(ctx, F, m));
+    const long long total = F->n * (m / 2);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 8));
+    de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->P, F->rowscale, X, F->W, 0);
+    DE_LAUNCH_CHECK(ctx);
+    DE_TRY(run_schedule(ctx, F->L, F->W, m));
+    DE_TRY(run_schedule(ctx, F->U, F->W, m));
+    de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->Q, nullptr, F->W, Y, 1);
+    DE_LAUNCH_CHECK(ctx);
+    return DE_OK;
+  }
+
+  // ---- layout helpers -----------------------------------------------------------------------------------
+  int ensure_stage(de_context *ctx, size_t bytes)
+  {
+    if (ctx->stage_bytes >= bytes)
+      return DE_OK;
+    if (ctx->stage)
+      cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stage_bytes = 0;
+    DE_TRY(dev_alloc(ctx, (char **)&ctx->stage, bytes));
+    ctx->stage_bytes = bytes;
+    return DE_OK;
+  }
+
+  int convert_layout(de_context *ctx, long long n, int m, const double *src, double *dst, int to_rowmajor)
+  {
+    const long long total = n * (m / 8);
+    if (total == 0)
+      return DE_OK;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 8));
+    de::panel8_convert_kernel<<<grid, 256, 0, ctx->stream>>>(n, m, src, dst, to_rowmajor);
+    DE_LAUNCH_CHECK(ctx);
+    return DE_OK;
+  }
+
+  int upload_panel8_device(de_context *ctx, long long n, int m, const double *host, double *dst)
+  {
+    const size_t bytes = sizeof(double) * (size_t)n * m;
+    if (bytes == 0)
+      return DE_OK;
+    DE_TRY(ensure_stage(ctx, bytes));
+    DE_CUDA(ctx, cudaMemcpyAsync(ctx->stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return convert_layout(ctx, n, m, ctx->stage, dst, 1);
+  }
+
+  /** eval / evec copy-out of the drivers (eigensolver.hh:105-111, :328-341) */
+  int copy_out(de_context *ctx, long long n, int m, int nev, const double *Q, const std::vector<double> &s,
+               double *eval, double *evec)
+  {
+    for (int j = 0; j < nev; ++j)
+      eval[j] = s[j];
+    if (n == 0 || nev == 0)
+      return DE_OK;
+    const size_t bytes = sizeof(double) * (size_t)n * nev;
+    DE_TRY(ensure_stage(ctx, bytes));
+    de::extract_columns_kernel<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, m, nev, Q, ctx->stage);
+    DE_LAUNCH_CHECK(ctx);
+    DE_CUDA(ctx, cudaMemcpyAsync(evec, ctx->stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+  }
+
+  struct ScopedBlocks
+  {
+    std::vector<double *> p;
+    ~ScopedBlocks()
+    {
+      for (double *q : p)
+        cudaFree(q);
+    }
+    int alloc(de_context *ctx, double **out, size_t count)
+    {
+      DE_TRY(dev_alloc(ctx, out, count));
+      p.push_back(*out);
+      return DE_OK;
+    }
+  };
+
+  inline int padded_cols(int nev) { return (nev / 8 + std::min(nev % 8, 1)) * 8; } // eigensolver.hh:43
+
+} // namespace
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+extern "C"
+{
+
+  int de_version(void) { return 100; }
+
+  const char *de_last_error_string(const de_context *ctx) { return ctx ? ctx->err.c_str() : g_thread_error.c_str(); }
+
+  int de_context_create(int device, void *stream, de_context **out)
+  {
+    if (!out)
+      return set_error(nullptr, DE_ERR_INVALID, "de_context_create: out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      return set_error(nullptr, DE_ERR_CUDA,
+                       std::string("de_context_create: no CUDA device available (") +
+                           (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                           "); this library has no CPU fallback");
+    if (device < 0 || device >= count)
+      return set_error(nullptr, DE_ERR_INVALID, "de_context_create: device ordinal out of range");
+    de_context *ctx = new (std::nothrow) de_context();
+    if (!ctx)
+      return set_error(nullptr, DE_ERR_ALLOC, "de_context_create: out of host memory");
+    ctx->device = device;
+    auto bail = [&](int code) {
+      std::string msg = ctx->err;
+      de_context_destroy(ctx);
+      return set_error(nullptr, code, msg);
+    };
+    if (bind_device(ctx) != DE_OK)
+      return bail(DE_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+      ctx->sm_count = prop.multiProcessorCount;
+    if (stream)
+      ctx->stream = (cudaStream_t)stream;
+    else
+    {
+      if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+      {
+        ctx->err = "cudaStreamCreate failed";
+        return bail(DE_ERR_CUDA);
+      }
+      ctx->own_stream = true;
+    }
+    bool ok = cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->partials, kPartialDoubles * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->dsmall, kSmall * sizeof(double)) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->dstatus, sizeof(int)) == cudaSuccess &&
+              cudaMallocHost((void **)&ctx->hsmall, kSmall * sizeof(double)) == cudaSuccess &&
+              cudaMallocHost((void **)&ctx->hstatus, sizeof(int)) == cudaSuccess &&
+              cudaMemset(ctx->dstatus, 0, sizeof(int)) == cudaSuccess;
+    if (!ok)
+    {
+      ctx->err = std::string("de_context_create: workspace allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+      return bail(DE_ERR_ALLOC);
+    }
+    *out = ctx;
+    return DE_OK;
+  }
+
+  int de_context_destroy(de_context *ctx)
+  {
+    if (!ctx)
+      return DE_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->comm && nccl_api().ok)
+      nccl_api().CommDestroy(ctx->comm);
+    cudaFree(ctx->partials);
+    cudaFree(ctx->dsmall);
+    cudaFree(ctx->dstatus);
+    cudaFree(ctx->stage);
+    if (ctx->hsmall)
+      cudaFreeHost(ctx->hsmall);
+    if (ctx->hstatus)
+      cudaFreeHost(ctx->hstatus);
+    if (ctx->ev_pack)
+      cudaEventDestroy(ctx->ev_pack);
+    if (ctx->ev_halo)
+      cudaEventDestroy(ctx->ev_halo);
+    if (ctx->comm_stream)
+      cudaStreamDestroy(ctx->comm_stream);
+    if (ctx->own_stream && ctx->stream)
+      cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DE_OK;
+  }
+
+  int de_context_synchronize(de_context *ctx)
+  {
+    if (!ctx)
+      return set_error(nullptr, DE_ERR_INVALID, "null context");
+    DE_TRY(bind_device(ctx));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+  }
+
+  int de_context_launch_count(const de_context *ctx, int64_t *count)
+  {
+    if (!ctx || !count)
+      return set_error(ctx, DE_ERR_INVALID, "null argument");
+    *count = ctx->launches;
+    return DE_OK;
+  }
+
+  int de_comm_unique_id(void *id128)
+  {
+    if (!id128)
+      return set_error(nullptr, DE_ERR_INVALID, "null id");
+    if (!nccl_api().ok)
+      return set_error(nullptr, DE_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    ncclUniqueId id;
+    DE_NCCL(nullptr, nccl_api().GetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "unexpected ncclUniqueId size");
+    std::memcpy(id128, &id, 128);
+    return DE_OK;
+  }
+
+  int de_context_init_comm(de_context *ctx, int rank, int nranks, const void *id128)
+  {
+    if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks)
+      return set_error(ctx, DE_ERR_INVALID, "de_context_init_comm: bad arguments");
+    if (!nccl_api().ok)
+      return set_error(ctx, DE_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    DE_TRY(bind_device(ctx));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    DE_NCCL(ctx, nccl_api().CommInitRank(&ctx->comm, nranks, id, rank));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return DE_OK;
+  }
+
+  int de_context_rank(const de_context *ctx, int *rank, int *nranks)
+  {
+    if (!ctx)
+      return set_error(nullptr, DE_ERR_INVALID, "null context");
+    if (rank)
+      *rank = ctx->rank;
+    if (nranks)
+      *nranks = ctx->nranks;
+    return DE_OK;
+  }
+
+  // ---- matrices ---------------------------------------------------------------------------------------
+  static int matrix_upload(de_context *ctx, long long n, long long ncols, long long nnz, const int64_t *rowptr,
+                           const int64_t *col, const double *val, de_matrix *A)
+  {
+    if (nnz >= (1LL << 31) || n >= (1LL << 31) - 1 || ncols >= (1LL << 31) - 1)
+      return set_error(ctx, DE_ERR_UNSUPPORTED, "matrix too large for 32-bit indices on one GPU");
+    if (rowptr[0] != 0 || rowptr[n] != nnz)
+      return set_error(ctx, DE_ERR_INVALID, "de_matrix_create: rowptr does not match nnz");
+    for (long long k = 0; k < nnz; ++k)
+      if (col[k] < 0 || col[k] >= ncols)
+        return set_error(ctx, DE_ERR_INVALID, "de_matrix_create: column index out of range");
+    A->n = n;
+    A->nnz = nnz;
+    DE_TRY(upload_converted(ctx, &A->rowptr, rowptr, (size_t)n + 1));
+    DE_TRY(upload_converted(ctx, &A->col, col, (size_t)nnz));
+    DE_TRY(dev_alloc(ctx, &A->val, (size_t)nnz));
+    DE_CUDA(ctx, cudaMemcpyAsync(A->val, val, sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+  }
+
+  int de_matrix_create_csr(de_context *ctx, int64_t n, int64_t nnz, const int64_t *rowptr, const int64_t *col,
+                           const double *val, de_matrix **out)
+  {
+    if (!ctx || !out || n < 0 || nnz < 0 || !rowptr || (nnz > 0 && (!col || !val)))
+      return set_error(ctx, DE_ERR_INVALID, "de_matrix_create_csr: bad arguments");
+    *out = nullptr;
+    DE_TRY(bind_device(ctx));
+    de_matrix *A = new de_matrix();
+    A->ctx = ctx;
+    int s = matrix_upload(ctx, n, n, nnz, rowptr, col, val, A);
+    if (s != DE_OK)
+    {
+      de_matrix_destroy(A);
+      return s;
+    }
+    *out = A;
+    return DE_OK;
+  }
+
+  int de_matrix_create_distributed(de_context *ctx, int64_t n_owned, int64_t n_halo, int64_t nnz,
+                                   const int64_t *rowptr, const int64_t *col_local, const double *val, int npeers,
+                                   const int *peer_ranks, const int64_t *recv_counts, const int64_t *send_offsets,
+                                   const int64_t *send_rows, de_matrix **out)
+  {
+    if (!ctx || !out || n_owned < 0 || n_halo < 0 || nnz < 0 || !rowptr || npeers < 0 ||
+        (npeers > 0 && (!peer_ranks || !recv_counts || !send_offsets)))
+      return set_error(ctx, DE_ERR_INVALID, "de_matrix_create_distributed: bad arguments");
+    *out = nullptr;
+    DE_TRY(bind_device(ctx));
+    de_matrix *A = new de_matrix();
+    A->ctx = ctx;
+    auto fail = [&](int s) {
+      de_matrix_destroy(A);
+      return s;
+    };
+    int s = matrix_upload(ctx, n_owned, n_owned + n_halo, nnz, rowptr, col_local, val, A);
+    if (s != DE_OK)
+      return fail(s);
+    A->n_halo = n_halo;
+    A->npeers = npeers;
+    long long roff = 0;
+    for (int p = 0; p < npeers; ++p)
+    {
+      if (peer_ranks[p] < 0 || peer_ranks[p] >= ctx->nranks || peer_ranks[p] == ctx->rank ||
+          (p > 0 && peer_ranks[p] <= peer_ranks[p - 1]))
+        return fail(set_error(ctx, DE_ERR_INVALID, "de_matrix_create_distributed: peers must be ascending ranks != own"));
+      A->peer.push_back(peer_ranks[p]);
+      A->recv_count.push_back(recv_counts[p]);
+      A->recv_off.push_back(roff);
+      roff += recv_counts[p];
+      A->send_count.push_back(send_offsets[p + 1] - send_offsets[p]);
+      A->send_off.push_back(send_offsets[p]);
+    }
+    if (roff != n_halo)
+      return fail(set_error(ctx, DE_ERR_INVALID, "de_matrix_create_distributed: recv_counts do not sum to n_halo"));
+    A->n_send = npeers > 0 ? send_offsets[npeers] : 0;
+    for (long long k = 0; k < A->n_send; ++k)
+      if (send_rows[k] < 0 || send_rows[k] >= n_owned)
+        return fail(set_error(ctx, DE_ERR_INVALID, "de_matrix_create_distributed: send row out of range"));
+    if ((s = upload_converted(ctx, &A->send_rows, send_rows, (size_t)A->n_send)) != DE_OK)
+      return fail(s);
+    // interior rows touch owned columns only and can run while the halo is in flight
+    std::vector<int> in, bd;
+    for (long long i = 0; i < n_owned; ++i)
+    {
+      bool halo = false;
+      for (int64_t k = rowptr[i]; k < rowptr[i + 1] && !halo; ++k)
+        halo = col_local[k] >= n_owned;
+      (halo ? bd : in).push_back((int)i);
+    }
+    A->n_interior = (long long)in.size();
+    A->n_boundary = (long long)bd.size();
+    if ((s = upload_converted(ctx, &A->interior, in.data(), in.size())) != DE_OK)
+      return fail(s);
+    if ((s = upload_converted(ctx, &A->boundary, bd.data(), bd.size())) != DE_OK)
+      return fail(s);
+    *out = A;
+    return DE_OK;
+  }
+
+  int de_matrix_destroy(de_matrix *A)
+  {
+    if (!A)
+      return DE_OK;
+    cudaSetDevice(A->ctx->device);
+    cudaFree(A->rowptr);
+    cudaFree(A->col);
+    cudaFree(A->val);
+    cudaFree(A->send_rows);
+    cudaFree(A->interior);
+    cudaFree(A->boundary);
+    cudaFree(A->send_buf);
+    cudaFree(A->halo_buf);
+    delete A;
+    return DE_OK;
+  }
+
+  int de_matrix_rows(const de_matrix *A, int64_t *n_owned, int64_t *nnz)
+  {
+    if (!A)
+      return set_error(nullptr, DE_ERR_INVALID, "null matrix");
+    if (n_owned)
+      *n_owned = A->n;
+    if (nnz)
+      *nnz = A->nnz;
+    return DE_OK;
+  }
+
+  int de_halo_plan_local(int64_t n_owned, const int64_t *rowptr, const int64_t *col_global, int nranks, int rank,
+                         const int64_t *part, int64_t *col_local, int64_t *halo_global, int64_t *n_halo,
+                         int64_t *recv_counts)
+  {
+    if (n_owned < 0 || !rowptr || !part || nranks < 1 || rank < 0 || rank >= nranks || !n_halo || !recv_counts)
+      return set_error(nullptr, DE_ERR_INVALID, "de_halo_plan_local: bad arguments");
+    if (part[rank + 1] - part[rank] != n_owned)
+      return set_error(nullptr, DE_ERR_INVALID, "de_halo_plan_local: partition does not match n_owned");
+    const int64_t lo = part[rank], hi = part[rank + 1], nglob = part[nranks];
+    const int64_t nnz = rowptr[n_owned];
+    std::vector<int64_t> ext;
+    for (int64_t k = 0; k < nnz; ++k)
+    {
+      const int64_t g = col_global[k];
+      if (g < 0 || g >= nglob)
+        return set_error(nullptr, DE_ERR_INVALID, "de_halo_plan_local: column index out of range");
+      if (g < lo || g >= hi)
+        ext.push_back(g);
+    }
+    std::sort(ext.begin(), ext.end());
+    ext.erase(std::unique(ext.begin(), ext.end()), ext.end());
+    for (int p = 0; p < nranks; ++p)
+      recv_counts[p] = 0;
+    {
+      int p = 0;
+      for (int64_t g : ext)
+      {
+        while (g >= part[p + 1])
+          ++p;
+        recv_counts[p]++;
+      }
+    }
+    *n_halo = (int64_t)ext.size();
+    for (size_t h = 0; h < ext.size(); ++h)
+      halo_global[h] = ext[h];
+    for (int64_t k = 0; k < nnz; ++k)
+    {
+      const int64_t g = col_global[k];
+      if (g >= lo && g < hi)
+        col_local[k] = g - lo;
+      else
+        col_local[k] = n_owned + (std::lower_bound(ext.begin(), ext.end(), g) - ext.begin());
+    }
+    return DE_OK;
+  }
+
+  // ---- multivectors -------------------------------------------------------------------------------------
+  int de_mv_create(de_context *ctx, int64_t n, int m, de_mv **out)
+  {
+    if (!ctx || !out || n < 0)
+      return set_error(ctx, DE_ERR_INVALID, "de_mv_create: bad arguments");
+    *out = nullptr;
+    if (m <= 0 || m % 8 != 0)
+      return set_error(ctx, DE_ERR_INVALID, "number of cols must be a multiple of block size"); // multivector.hh:49
+    if (m > DE_MAX_COLS)
+      return set_error(ctx, DE_ERR_UNSUPPORTED, "de_mv_create: more than DE_MAX_COLS (64) columns");
+    DE_TRY(bind_device(ctx));
+    de_mv *X = new de_mv{ctx, n, m, nullptr};
+    int s = dev_alloc(ctx, &X->d, (size_t)n * m);
+    if (s != DE_OK)
+    {
+      delete X;
+      return s;
+    }
+    cudaError_t e = cudaMemsetAsync(X->d, 0, sizeof(double) * (size_t)n * m, ctx->stream);
+    if (e != cudaSuccess)
+    {
+      cudaFree(X->d);
+      delete X;
+      return set_error(ctx, DE_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = X;
+    return DE_OK;
+  }
+
+  int de_mv_destroy(de_mv *X)
+  {
+    if (!X)
+      return DE_OK;
+    cudaSetDevice(X->ctx->device);
+    cudaFree(X->d);
+    delete X;
+    return DE_OK;
+  }
+
+  int de_mv_shape(const de_mv *X, int64_t *n, int *m)
+  {
+    if (!X)
+      return set_error(nullptr, DE_ERR_INVALID, "null multivector");
+    if (n)
+      *n = X->n;
+    if (m)
+      *m = X->m;
+    return DE_OK;
+  }
+
+  int de_mv_upload_panel8(de_mv *X, const double *host)
+  {
+    if (!X || !host)
+      return set_error(X ? X->ctx : nullptr, DE_ERR_INVALID, "de_mv_upload_panel8: null argument");
+    de_context *ctx = X->ctx;
+    DE_TRY(bind_device(ctx));
+    DE_TRY(upload_panel8_device(ctx, X->n, X->m, host, X->d));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+  }
+
+  int de_mv_download_panel8(const de_mv *X, double *host)
+  {
+    if (!X || !host)
+      return set_error(X ? X->ctx : nullptr, DE_ERR_INVALID, "de_mv_download_panel8: null argument");
+    de_context *ctx = X->ctx;
+    DE_TRY(bind_device(ctx));
+    const size_t bytes = sizeof(double) * (size_t)X->n * X->m;
+    if (bytes == 0)
+      return DE_OK;
+    DE_TRY(ensure_stage(ctx, bytes));
+    DE_TRY(convert_layout(ctx, X->n, X->m, X->d, ctx->stage, 0));
+    DE_CUDA(ctx, cudaMemcpyAsync(host, ctx->stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+  }
+
+  int de_mv_upload_rowmajor(de_mv *X, const double *host)
+  {
+    if (!X || !host)
+      return set_error(X ? X->ctx : nullptr, DE_ERR_INVALID, "de_mv_upload_rowmajor: null argument");
+    de_context *ctx = X->ctx;
+    DE_TRY(bind_device(ctx));
+    DE_CUDA(ctx, cudaMemcpyAsync(X->d, host, sizeof(double) * (size_t)X->n * X->m, cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+  }
+
+  int de_mv_download_rowmajor(const de_mv *X, double *host)
+  {
+    if (!X || !host)
+      return set_error(X ? X->ctx : nullptr, DE_ERR_INVALID, "de_mv_download_rowmajor: null argument");
+    de_context *ctx = X->ctx;
+    DE_TRY(bind_device(ctx));
+    DE_CUDA(ctx, cudaMemcpyAsync(host, X->d, sizeof(double) * (size_t)X->n * X->m, cudaMemcpyDeviceToHost, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+  }
+
+  int de_mv_copy(de_mv *dst, const de_mv *src)
+  {
+    if (!dst || !src)
+      return set_error(nullptr, DE_ERR_INVALID, "de_mv_copy: null argument");
+    de_context *ctx = dst->ctx;
+    if (dst->n != src->n || dst->m != src->m)
+      return set_error(ctx, DE_ERR_INVALID, "de_mv_copy: shape mismatch");
+    DE_TRY(bind_device(ctx));
+    DE_CUDA(ctx, cudaMemcpyAsync(dst->d, src->d, sizeof(double) * (size_t)src->n * src->m, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+    return DE_OK;
+  }
+
+  int de_mv_device_ptr(de_mv *X, void **dptr)
+  {
+    if (!X || !dptr)
+      return set_error(nullptr, DE_ERR_INVALID, "null argument");
+    *dptr = X->d;
+    return DE_OK;
+  }
+
+  // ---- kernels --------------------------------------------------------------------------------------------
+  static int check_spmm_shapes(de_context *ctx, const char *who, const de_mv *Y, const de_matrix *A, const de_mv *X)
+  {
+    if (Y->n != A->n || X->n != A->n)
+      return set_error(ctx, DE_ERR_INVALID, std::string(who) + ": number of rows does not match the matrix");
+    if (Y->m != X->m)
+      return set_error(ctx, DE_ERR_INVALID, std::string(who) + ": number of columns does not match");
+    if (Y->d == X->d)
+      return set_error(ctx, DE_ERR_INVALID, std::string(who) + ": output must not alias input");
+    return DE_OK;
+  }
+
+  int de_spmm(de_mv *Y, const de_matrix *A, const de_mv *X)
+  {
+    if (!Y || !A || !X)
+      return set_error(nullptr, DE_ERR_INVALID, "de_spmm: null argument");
+    de_context *ctx = A->ctx;
+    DE_TRY(check_spmm_shapes(ctx, "matmul_sparse_tallskinny", Y, A, X));
+    DE_TRY(bind_device(ctx));
+    return spmm_device<false>(ctx, A, X->d, Y->d, X->m);
+  }
+
+  int de_spmm_diag_dot(de_mv *Y, const de_matrix *A, const de_mv *X, double *dp_host)
+  {
+    if (!Y || !A || !X || !dp_host)
+      return set_error(nullptr, DE_ERR_INVALID, "de_spmm_diag_dot: null argument");
+    de_context *ctx = A->ctx;
+    DE_TRY(check_spmm_shapes(ctx, "matmul_sparse_tallskinny", Y, A, X));
+    DE_TRY(bind_device(ctx));
+    DE_TRY(reset_status(ctx));
+    DE_TRY(spmm_device<true>(ctx, A, X->d, Y->d, X->m));
+    return fetch_small(ctx, ctx->dDP(), dp_host, X->m);
+  }
+
+  int de_diag_dot(double *dp_host, const de_mv *X, const de_mv *Y)
+  {
+    if (!dp_host || !X || !Y)
+      return set_error(nullptr, DE_ERR_INVALID, "de_diag_dot: null argument");
+    de_context *ctx = X->ctx;
+    if (X->n != Y->n)
+      return set_error(ctx, DE_ERR_INVALID, "dot_products_blocked: number of rows does not match"); // kernels_cpp.hh:30
+    if (X->m != Y->m)
+      return set_error(ctx, DE_ERR_INVALID, "dot_products_blocked: number of columns does not match"); // :32
+    DE_TRY(bind_device(ctx));
+    DE_TRY(reset_status(ctx));
+    DE_TRY(diag_dot_device(ctx, X->n, X->m, X->d, Y->d, ctx->dDP()));
+    return fetch_small(ctx, ctx->dDP(), dp_host, X->m);
+  }
+
+  int de_gram(double *G_host, const de_mv *X, const de_mv *Y)
+  {
+    if (!G_host || !X || !Y)
+      return set_error(nullptr, DE_ERR_INVALID, "de_gram: null argument");
+    de_context *ctx = X->ctx;
+    if (X->n != Y->n)
+      return set_error(ctx, DE_ERR_INVALID, "dot_products_blocked: number of rows does not match"); // kernels_cpp.hh:62
+    if (X->m != Y->m)
+      return set_error(ctx, DE_ERR_INVALID, "dot_products_blocked: number of columns does not match"); // :64
+    DE_TRY(bind_device(ctx));
+    DE_TRY(reset_status(ctx));
+    DE_TRY(gram_device(ctx, X->m, X->n, X->d, X->m, Y->d, Y->m, false, ctx->dG()));
+    return fetch_small(ctx, ctx->dG(), G_host, (size_t)X->m * X->m);
+  }
+
+  int de_block_update(de_mv *X, const double *Q_host)
+  {
+    if (!X || !Q_host)
+      return set_error(nullptr, DE_ERR_INVALID, "de_block_update: null argument");
+    de_context *ctx = X->ctx;
+    DE_TRY(bind_device(ctx));
+    const size_t cnt = (size_t)X->m * X->m;
+    std::memcpy(ctx->hsmall, Q_host, cnt * sizeof(double));
+    DE_CUDA(ctx, cudaMemcpyAsync(ctx->dR(), ctx->hsmall, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DE_TRY(update_device<0>(ctx, X->m, X->n, X->d, X->m, ctx->dR(), X->d, X->m, 0));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // hsmall may be reused by the next call
+    return DE_OK;
+  }
+
+  int de_block_project(de_mv *X, int j0, int k0, int w, const double *S_host)
+  {
+    if (!X || !S_host)
+      return set_error(nullptr, DE_ERR_INVALID, "de_block_project: null argument");
+    de_context *ctx = X->ctx;
+    if (w <= 0 || w % 8 != 0 || j0 % 8 != 0 || k0 % 8 != 0 || j0 < 0 || k0 < 0 || j0 + w > X->m || k0 + w > X->m ||
+        (j0 < k0 + w && k0 < j0 + w))
+      return set_error(ctx, DE_ERR_INVALID, "de_block_project: panels must be disjoint, 8-aligned and inside the block");
+    DE_TRY(bind_device(ctx));
+    const size_t cnt = (size_t)w * w;
+    std::memcpy(ctx->hsmall, S_host, cnt * sizeof(double));
+    DE_CUDA(ctx, cudaMemcpyAsync(ctx->dR(), ctx->hsmall, cnt * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DE_TRY(update_device<1>(ctx, w, X->n, X->d + k0, X->m, ctx->dR(), X->d + j0, X->m, 0));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+  }
+
+  int de_orthonormalize(de_mv *X)
+  {
+    if (!X)
+      return set_error(nullptr, DE_ERR_INVALID, "de_orthonormalize: null argument");
+    de_context *ctx = X->ctx;
+    DE_TRY(bind_device(ctx));
+    DE_TRY(reset_status(ctx));
+    DE_TRY(orthonormalize_device(ctx, X->n, X->m, X->d));
+    return fetch_small(ctx, nullptr, nullptr, 0);
+  }
+
+  int de_b_orthonormalize(const de_matrix *B, de_mv *X, de_mv *BX, double *norm)
+  {
+    if (!B || !X)
+      return set_error(nullptr, DE_ERR_INVALID, "de_b_orthonormalize: null argument");
+    de_context *ctx = X->ctx;
+    if (B->n != X->n || (BX && (BX->n != X->n || BX->m != X->m)))
+      return set_error(ctx, DE_ERR_INVALID, "B_orthonormalize: shape mismatch");
+    DE_TRY(bind_device(ctx));
+    DE_TRY(reset_status(ctx));
+    ScopedBlocks tmp;
+    double *bx = BX ? BX->d : nullptr;
+    if (!bx)
+      DE_TRY(tmp.alloc(ctx, &bx, (size_t)X->n * X->m));
+    DE_TRY(b_orthonormalize_device(ctx, B, X->n, X->m, X->d, bx, norm != nullptr));
+    double info = 0.0;
+    DE_TRY(fetch_small(ctx, ctx->dInfo(), &info, norm ? 1 : 0));
+    if (norm)
+      *norm = info;
+    return DE_OK;
+  }
+
+  // ---- factored apply -----------------------------------------------------------------------------------------
+  int de_factor_upload(de_context *ctx, int64_t n, const long *Lp, const long *Lj, const double *Lx, const long *Up,
+                       const long *Ui, const double *Ux, const long *P, const long *Q, const double *Rs, long do_recip,
+                       de_factor **out)
+  {
+    if (!ctx || !out || n < 0 || !Lp || !Up || !P || !Q || !Rs)
+      return set_error(ctx, DE_ERR_INVALID, "de_factor_upload: bad arguments");
+    *out = nullptr;
+    DE_TRY(bind_device(ctx));
+    const long lnz = Lp[n], unz = Up[n];
+    if (lnz >= (1L << 31) || unz >= (1L << 31) || n >= (1L << 31) - 1)
+      return set_error(ctx, DE_ERR_UNSUPPORTED, "factor too large for 32-bit indices");
+    // L: CSR with the (unit) diagonal stored last in each row -> strip it (kernels_cpp.hh:717 skips it the same way)
+    std::vector<int> lptr(n + 1, 0), lcol;
+    std::vector<double> lval;
+    lcol.reserve(lnz > n ? lnz - n : 0);
+    lval.reserve(lnz > n ? lnz - n : 0);
+    for (int64_t i = 0; i < n; ++i)
+    {
+      if (Lp[i + 1] - Lp[i] < 1 || Lj[Lp[i + 1] - 1] != i)
+        return set_error(ctx, DE_ERR_INVALID, "de_factor_upload: L rows must end with their diagonal entry");
+      for (long k = Lp[i]; k < Lp[i + 1] - 1; ++k)
+      {
+        if (Lj[k] < 0 || Lj[k] >= i)
+          return set_error(ctx, DE_ERR_INVALID, "de_factor_upload: L is not strictly lower triangular");
+        lcol.push_back((int)Lj[k]);
+        lval.push_back(Lx[k]);
+      }
+      lptr[i + 1] = (int)lcol.size();
+    }
+    // U: CSC with the diagonal last in each column -> CSR of the strictly upper part + inverse diagonal
+    std::vector<int> uptr(n + 1, 0);
+    std::vector<double> invd(n, 0.0);
+    for (int64_t j = 0; j < n; ++j)
+    {
+      if (Up[j + 1] - Up[j] < 1 || Ui[Up[j + 1] - 1] != j)
+        return set_error(ctx, DE_ERR_INVALID, "de_factor_upload: U columns must end with their diagonal entry");
+      const double d = Ux[Up[j + 1] - 1];
+      if (d == 0.0 || !std::isfinite(d))
+        return set_error(ctx, DE_ERR_SINGULAR, "UMFPackFactorizedMatrix: input matrix is singular"); // umfpacktools.hh:163
+      invd[j] = 1.0 / d;
+      for (long k = Up[j]; k < Up[j + 1] - 1; ++k)
+      {
+        if (Ui[k] < 0 || Ui[k] >= j)
+          return set_error(ctx, DE_ERR_INVALID, "de_factor_upload: U is not strictly upper triangular");
+        uptr[Ui[k] + 1]++;
+      }
+    }
+    for (int64_t i = 0; i < n; ++i)
+      uptr[i + 1] += uptr[i];
+    std::vector<int> ucol(uptr[n]);
+    std::vector<double> uval(uptr[n]);
+    {
+      std::vector<int> w(uptr.begin(), uptr.end() - 1);
+      for (int64_t j = 0; j < n; ++j) // ascending j => ascending columns inside every row
+        for (long k = Up[j]; k < Up[j + 1] - 1; ++k)
+        {
+          const int dst = w[Ui[k]]++;
+          ucol[dst] = (int)j;
+          uval[dst] = Ux[k];
+        }
+    }
+    std::vector<double> rowscale(n);
+    std::vector<char> seenp(n, 0), seenq(n, 0);
+    for (int64_t k = 0; k < n; ++k)
+    {
+      if (P[k] < 0 || P[k] >= n || Q[k] < 0 || Q[k] >= n || seenp[P[k]] || seenq[Q[k]])
+        return set_error(ctx, DE_ERR_INVALID, "de_factor_upload: P / Q are not permutations");
+      seenp[P[k]] = seenq[Q[k]] = 1;
+      rowscale[k] = do_recip ? Rs[P[k]] : 1.0 / Rs[P[k]]; // kernels_cpp.hh:687, :699
+    }
+    de_factor *F = new de_factor();
+    F->ctx = ctx;
+    F->n = n;
+    F->lnz = lnz;
+    F->unz = unz;
+    auto fail = [&](int s) {
+      de_factor_destroy(F);
+      return s;
+    };
+    int s;
+    if ((s = build_schedule(ctx, n, lptr, lcol, lval, nullptr, true, F->L)) != DE_OK)
+      return fail(s);
+    if ((s = build_schedule(ctx, n, uptr, ucol, uval, &invd, false, F->U)) != DE_OK)
+      return fail(s);
+    if ((s = upload_converted(ctx, &F->P, P, (size_t)n)) != DE_OK)
+      return fail(s);
+    if ((s = upload_converted(ctx, &F->Q, Q, (size_t)n)) != DE_OK)
+      return fail(s);
+    if ((s = upload_converted(ctx, &F->rowscale, rowscale.data(), (size_t)n)) != DE_OK)
+      return fail(s);
+    *out = F;
+    return DE_OK;
+  }
+
+  int de_factor_destroy(de_factor *F)
+  {
+    if (!F)
+      return DE_OK;
+    cudaSetDevice(F->ctx->device);
+    free_schedule(F->L);
+    free_schedule(F->U);
+    cudaFree(F->P);
+    cudaFree(F->Q);
+    cudaFree(F->rowscale);
+    cudaFree(F->W);
+    delete F;
+    return DE_OK;
+  }
+
+  int de_factor_apply(de_mv *Y, const de_factor *F, de_mv *X)
+  {
+    if (!Y || !F || !X)
+      return set_error(nullptr, DE_ERR_INVALID, "de_factor_apply: null argument");
+    de_context *ctx = F->ctx;
+    if (Y->n != X->n || Y->m != X->m)
+      return set_error(ctx, DE_ERR_INVALID, "matmul_inverse_tallskinny_blocked: Qout/Qin size mismatch"); // kernels_cpp.hh:665
+    if (F->n != X->n)
+      return set_error(ctx, DE_ERR_INVALID,
+                       "matmul_inverse_tallskinny_blocked: Factorization does not match size of Qout/Qin"); // :667
+    DE_TRY(bind_device(ctx));
+    return factor_apply_device(ctx, F, X->d, Y->d, X->m);
+  }
+
+  int de_factor_info(const de_factor *F, int64_t *n, int64_t *lnz, int64_t *unz, int *levels_L, int *levels_U)
+  {
+    if (!F)
+      return set_error(nullptr, DE_ERR_INVALID, "null factor");
+    if (n)
+      *n = F->n;
+    if (lnz)
+      *lnz = F->lnz;
+    if (unz)
+      *unz = F->unz;
+    if (levels_L)
+      *levels_L = F->L.nlevels;
+    if (levels_U)
+      *levels_U = F->U.nlevels;
+    return DE_OK;
+  }
+
+  // ---- drivers --------------------------------------------------------------------------------------------------
+  /** shared skeleton of StandardLargest (eigensolver.hh:28-112) and StandardInverse (:116-198).
+   *  Qa holds the orthonormal iterate (reference Q1 after the swap), Qb the block it is mapped to (reference Q2).
+   *  For the largest-eigenvalue variant the product A*Qa that the reference recomputes at the top of the loop
+   *  (:78) is the one it already formed for the Rayleigh quotients (:84) -- it is reused, bit-identically. */
+  static int standard_driver(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
+                             int maxiter, int nev, const double *start_panel8, double *eval, double *evec, int verbose,
+                             int *iterations)
+  {
+    if (!ctx || !A || !start_panel8 || !eval || !evec || nev <= 0)
+      return set_error(ctx, DE_ERR_INVALID, "standard eigensolver driver: bad arguments");
+    const int m = padded_cols(nev);
+    if (!valid_cols(m))
+      return set_error(ctx, DE_ERR_UNSUPPORTED, "standard eigensolver driver: nev exceeds DE_MAX_COLS (64)");
+    if (F && F->n != A->n)
+      return set_error(ctx, DE_ERR_INVALID, "standard eigensolver driver: factorisation does not match the matrix");
+    DE_TRY(bind_device(ctx));
+    const long long n = A->n;
+    ScopedBlocks blk;
+    double *Qa, *Qb;
+    DE_TRY(blk.alloc(ctx, &Qa, (size_t)n * m));
+    DE_TRY(blk.alloc(ctx, &Qb, (size_t)n * m));
+    DE_TRY(reset_status(ctx));
+    DE_TRY(upload_panel8_device(ctx, n, m, start_panel8, Qa));
+    DE_TRY(orthonormalize_device(ctx, n, m, Qa));
+    std::vector<double> s1(m, 0.0), s2(m, 0.0);
+    int k_exit = std::min(1, maxiter - 1);
+    bool have_product = false; // Qb == A*Qa already?
+    for (int k = 1; k < maxiter; ++k)
+    {
+      k_exit = k;
+      if (F)
+        DE_TRY(factor_apply_device(ctx, F, Qa, Qb, m)); // Qb = A^-1 Qa (:168)
+      else if (!have_product)
+        DE_TRY(spmm_device<false>(ctx, A, Qa, Qb, m)); // Qb = A Qa (:78)
+      DE_TRY(orthonormalize_device(ctx, n, m, Qb));    // (:81, :171)
+      DE_TRY(spmm_device<true>(ctx, A, Qb, Qa, m));    // Qa = A Qb and s1 = diag(Qb^T Qa) (:84-85, :174-175)
+      DE_TRY(fetch_small(ctx, ctx->dDP(), s1.data(), m));
+      double distance = 0.0;
+      for (int i = 0; i < m; ++i)
+      {
+        s1[i] -= shift;
+        distance = std::max(distance, std::abs(s1[i] - s2[i]));
+      }
+      if (verbose > 0 && k > 1)
+        std::printf("%s=%d %g\n", F ? "iter" : "Iter", k, distance);
+      std::swap(s1, s2);
+      std::swap(Qa, Qb); // now Qa orthonormal, Qb = A*Qa
+      have_product = true;
+      if (k > 1 && distance < tol)
+        break;
+    }
+    if (iterations)
+      *iterations = k_exit;
+    return copy_out(ctx, n, m, nev, Qa, s2, eval, evec);
+  }
+
+  int de_standard_largest(de_context *ctx, const de_matrix *A, double shift, double tol, int maxiter, int nev,
+                          const double *start_panel8, double *eval, double *evec, int verbose, int *iterations)
+  {
+    return standard_driver(ctx, A, nullptr, shift, tol, maxiter, nev, start_panel8, eval, evec, verbose, iterations);
+  }
+
+  int de_standard_inverse(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
+                          int maxiter, int nev, const double *start_panel8, double *eval, double *evec, int verbose,
+                          int *iterations)
+  {
+    if (!F)
+      return set_error(ctx, DE_ERR_INVALID, "de_standard_inverse: factorisation is null");
+    return standard_driver(ctx, A, F, shift, tol, maxiter, nev, start_panel8, eval, evec, verbose, iterations);
+  }
+
+  int de_generalized_inverse(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *F, double shift,
+                             double tol, int maxiter, int nev, const double *start_panel8, double *eval, double *evec,
+                             int verbose, int *iterations, double *relerror_out)
+  {
+    if (!ctx || !A || !B || !F || !start_panel8 || !eval || !evec || nev <= 0)
+      return set_error(ctx, DE_ERR_INVALID, "de_generalized_inverse: bad arguments");
+    const int m = padded_cols(nev);
+    if (!valid_cols(m))
+      return set_error(ctx, DE_ERR_UNSUPPORTED, "de_generalized_inverse: nev exceeds DE_MAX_COLS (64)");
+    if (A->n != B->n || F->n != A->n)
+      return set_error(ctx, DE_ERR_INVALID, "de_generalized_inverse: A, B and the factorisation must have the same size");
+    DE_TRY(bind_device(ctx));
+    const long long n = A->n;
+    ScopedBlocks blk;
+    double *Q1, *Q2, *BQ;
+    DE_TRY(blk.alloc(ctx, &Q1, (size_t)n * m));
+    DE_TRY(blk.alloc(ctx, &Q2, (size_t)n * m));
+    DE_TRY(blk.alloc(ctx, &BQ, (size_t)n * m));
+    DE_TRY(reset_status(ctx));
+    DE_TRY(upload_panel8_device(ctx, n, m, start_panel8, Q1));
+    std::vector<double> ra1(m, 0.0), ra2(m, 0.0), sA(m, 0.0);
+    DE_TRY(b_orthonormalize_device(ctx, B, n, m, Q1, BQ, false)); // (:270) ; BQ = B*Q1
+    DE_TRY(spmm_device<true>(ctx, A, Q1, Q2, m));                 // (:271-272)
+    DE_TRY(fetch_small(ctx, ctx->dDP(), sA.data(), m));
+    for (int i = 0; i < m; ++i)
+      ra2[i] = sA[i] - shift;
+    int iter = 0;
+    double relerror = 0.0;
+    while (iter < maxiter)
+    {
+      // Q2 = B*Q1 (:295) is the product BQ that B-orthonormalisation carried along; Q1 = A^-1 * (B*Q1) (:296)
+      DE_TRY(factor_apply_device(ctx, F, BQ, Q1, m));
+      DE_TRY(b_orthonormalize_device(ctx, B, n, m, Q1, BQ, false)); // (:297)
+      iter += 1;
+      DE_TRY(spmm_device<true>(ctx, A, Q1, Q2, m)); // (:308-309)
+      DE_TRY(fetch_small(ctx, ctx->dDP(), sA.data(), m));
+      relerror = 0.0;
+      for (int i = 0; i < m; ++i)
+      {
+        ra1[i] = sA[i] - shift;
+        relerror = std::max(relerror, std::abs(ra1[i] - ra2[i]));
+      }
+      relerror /= *std::max_element(ra1.begin(), ra1.end());
+      if (verbose > 2)
+        std::printf("iter=%d relerror=%g\n", iter, relerror);
+      std::swap(ra1, ra2);
+      if (iter > 10 && relerror < tol) // (:323)
+        break;
+    }
+    if (iterations)
+      *iterations = iter;
+    if (relerror_out)
+      *relerror_out = relerror;
+    return copy_out(ctx, n, m, nev, Q1, ra2, eval, evec);
+  }
+
+  // ---- host-side helpers ---------------------------------------------------------------------------------------
+  int de_start_block(int64_t n, int m, unsigned seed, double *out)
+  {
+    if (n < 0 || m <= 0 || m % 8 != 0 || !out)
+      return set_error(nullptr, DE_ERR_INVALID, "de_start_block: bad arguments");
+    std::mt19937 urbg{seed};
+    std::normal_distribution<double> gen{0.0, 1.0};
+    for (int64_t bj = 0; bj < m; bj += 8)
+      for (int64_t i = 0; i < n; ++i)
+        for (int j = 0; j < 8; ++j)
+          out[(bj / 8 * n + i) * 8 + j] = gen(urbg);
+    return DE_OK;
+  }
+
+  int de_host_factorize(int64_t n, const int64_t *rowptr, const int64_t *col, const double *val, int ordering,
+                        int scale_rows, de_host_factor **out)
+  {
+    if (!out || n < 0 || !rowptr)
+      return set_error(nullptr, DE_ERR_INVALID, "de_host_factorize: bad arguments");
+    *out = nullptr;
+    de_host_factor *F = new de_host_factor();
+    try
+    {
+      de_b200::factorize_csr((long)n, rowptr, col, val, F->F, (de_b200::Ordering)ordering, scale_rows != 0);
+    }
+    catch (const std::exception &e)
+    {
+      delete F;
+      const std::string msg = e.what();
+      return set_error(nullptr, msg.find("singular") != std::string::npos ? DE_ERR_SINGULAR : DE_ERR_INVALID, msg);
+    }
+    *out = F;
+    return DE_OK;
+  }
+
+  int de_host_factor_arrays(const de_host_factor *F, int64_t *n, int64_t *lnz, int64_t *unz, const long **Lp,
+                            const long **Lj, const double **Lx, const long **Up, const long **Ui, const double **Ux,
+                            const long **P, const long **Q, const double **Rs, long *do_recip)
+  {
+    if (!F)
+      return set_error(nullptr, DE_ERR_INVALID, "null host factor");
+    const de_b200::FactorArrays &A = F->F;
+    if (n)
+      *n = A.n;
+    if (lnz)
+      *lnz = A.lnz;
+    if (unz)
+      *unz = A.unz;
+    if (Lp)
+      *Lp = A.Lp.data();
+    if (Lj)
+      *Lj = A.Lj.data();
+    if (Lx)
+      *Lx = A.Lx.data();
+    if (Up)
+      *Up = A.Up.data();
+    if (Ui)
+      *Ui = A.Ui.data();
+    if (Ux)
+      *Ux = A.Ux.data();
+    if (P)
+      *P = A.P.data();
+    if (Q)
+      *Q = A.Q.data();
+    if (Rs)
+      *Rs = A.Rs.data();
+    if (do_recip)
+      *do_recip = A.do_recip;
+    return DE_OK;
+  }
+
+  int de_host_factor_destroy(de_host_factor *F)
+  {
+    delete F;
+    return DE_OK;
+  }
+
+} // extern "C"

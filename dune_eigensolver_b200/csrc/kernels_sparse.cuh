@@ -1,0 +1,284 @@
+// SpMM (K1 / K1'), diag-dot (K2), partial-sum reduction and small data-movement kernels for sm_100a.
+//
+// Data layout in HBM: a multivector is a dense row-major n x m fp64 array (leading dimension ld = m doubles,
+// rows 64-byte aligned because m % 8 == 0). One matrix row touches one contiguous 8*m-byte row of X per
+// nonzero, so the gather is made of full 32-byte sectors and 128-bit loads; A is CSR with int32 indices.
+//
+// Roofline: all kernels here are HBM-bound. Algorithmic bytes per call:
+//   SpMM      12*nnz + 4*(n+1) + 16*n*m        diag-dot  16*n*m
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace de
+{
+
+  __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+  __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+  __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+  __device__ __forceinline__ void fma2(double2 &acc, double a, double2 x)
+  {
+    acc.x = fma(a, x.x, acc.x);
+    acc.y = fma(a, x.y, acc.y);
+  }
+
+  struct SpmmArgs
+  {
+    long long nrows;     // rows to process (length of rowlist if given, else rows 0..nrows-1)
+    const int *rowlist;  // optional list of local row indices (interior / boundary split of a distributed matrix)
+    const int *rowptr;   // CSR row pointer (int32: nnz < 2^31 per GPU)
+    const int *col;      // local column indices: [0,n_owned) -> X, [n_owned, n_owned+n_halo) -> H
+    const double *val;
+    const double *X;     // owned rows of the input block
+    const double *H;     // halo rows received from peers (may be null when n_halo == 0)
+    long long n_owned;
+    int ld;              // leading dimension (doubles) of X, H and Y
+    int m;               // columns
+    double *Y;
+    double *partials;    // DOT only: [gridDim.x][m] per-CTA partial dot products
+  };
+
+  /** Y = A X for all m columns in ONE pass over A (the reference re-streams A once per 8-column panel,
+   *  kernels_cpp.hh:640-656). TPR threads cooperate on a row, each owning VPT double2 column pairs
+   *  (columns 2*(t + v*TPR)); a row's nonzeros are accumulated in CSR order with FMA, like the CPU loop
+   *  kernels_cpp.hh:644-655. The (val,col) loads of a row are warp-broadcast; the X-row gather is a coalesced
+   *  8*m-byte segment. Consecutive CTAs walk consecutive row blocks so X rows shared by neighbouring matrix
+   *  rows (stencil reuse distance = one grid plane) stay in the 126 MB L2.
+   *  DOT additionally accumulates dp[j] += X(i,j) * Y(i,j) while the Y row is still in registers (K1':
+   *  eigensolver.hh:84-85) and leaves one partial vector per CTA (reduced in fixed order afterwards).
+   */
+  template <int TPR, int VPT, bool DOT>
+  __global__ void __launch_bounds__(256) spmm_kernel(const SpmmArgs a)
+  {
+    constexpr int RPB = 256 / TPR; // rows per CTA per step
+    const int t = threadIdx.x % TPR;
+    const int rslot = threadIdx.x / TPR;
+    int cidx[VPT];
+    bool act[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v)
+    {
+      cidx[v] = 2 * (t + v * TPR);
+      act[v] = cidx[v] < a.m;
+    }
+    double2 dacc[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v)
+      dacc[v] = make_double2(0.0, 0.0);
+
+    for (long long r = (long long)blockIdx.x * RPB + rslot; r < a.nrows; r += (long long)gridDim.x * RPB)
+    {
+      const long long row = a.rowlist ? (long long)a.rowlist[r] : r;
+      int k = __ldg(a.rowptr + row);
+      const int kend = __ldg(a.rowptr + row + 1);
+      double2 acc[VPT];
+#pragma unroll
+      for (int v = 0; v < VPT; ++v)
+        acc[v] = make_double2(0.0, 0.0);
+
+      for (; k + 4 <= kend; k += 4)
+      {
+        int j[4];
+        double av[4];
+        const double *xr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+          j[u] = __ldg(a.col + k + u);
+          av[u] = __ldg(a.val + k + u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          xr[u] = (j[u] < a.n_owned) ? a.X + (size_t)j[u] * a.ld : a.H + (size_t)(j[u] - a.n_owned) * a.ld;
+        double2 xv[4][VPT];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < VPT; ++v)
+            xv[u][v] = act[v] ? ldg2(xr[u] + cidx[v]) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < VPT; ++v)
+            fma2(acc[v], av[u], xv[u][v]);
+      }
+      for (; k < kend; ++k)
+      {
+        const int j = __ldg(a.col + k);
+        const double av = __ldg(a.val + k);
+        const double *xr = (j < a.n_owned) ? a.X + (size_t)j * a.ld : a.H + (size_t)(j - a.n_owned) * a.ld;
+#pragma unroll
+        for (int v = 0; v < VPT; ++v)
+          if (act[v])
+            fma2(acc[v], av, ldg2(xr + cidx[v]));
+      }
+#pragma unroll
+      for (int v = 0; v < VPT; ++v)
+        if (act[v])
+        {
+          st2(a.Y + (size_t)row * a.ld + cidx[v], acc[v]);
+          if (DOT)
+          {
+            const double2 z = ldg2(a.X + (size_t)row * a.ld + cidx[v]);
+            dacc[v].x = fma(z.x, acc[v].x, dacc[v].x);
+            dacc[v].y = fma(z.y, acc[v].y, dacc[v].y);
+          }
+        }
+    }
+
+    if (DOT)
+    {
+      __shared__ double2 red[VPT][256];
+#pragma unroll
+      for (int v = 0; v < VPT; ++v)
+        red[v][threadIdx.x] = dacc[v];
+      __syncthreads();
+      if (rslot == 0)
+      {
+#pragma unroll
+        for (int v = 0; v < VPT; ++v)
+          if (act[v])
+          {
+            double2 s = make_double2(0.0, 0.0);
+            for (int q = 0; q < RPB; ++q) // fixed order: deterministic
+            {
+              s.x += red[v][q * TPR + t].x;
+              s.y += red[v][q * TPR + t].y;
+            }
+            st2(a.partials + (size_t)blockIdx.x * a.m + cidx[v], s);
+          }
+      }
+    }
+  }
+
+  /** dp[j] = sum_i X(i,j) Y(i,j) (reference dot_products_diagonal_blocked, kernels_cpp.hh:24-55).
+   *  blockDim = (m/2, 256/(m/2)): x indexes a column pair, y a row lane; rows are strided over the grid.
+   *  Leaves one partial vector per CTA. */
+  __global__ void __launch_bounds__(256) diag_dot_kernel(long long n, const double *__restrict__ X, int ldx,
+                                                         const double *__restrict__ Y, int ldy, int m,
+                                                         double *__restrict__ partials)
+  {
+    const int c = 2 * threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.y;
+    double2 acc = make_double2(0.0, 0.0);
+    long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y;
+    for (; r + 3 * step < n; r += 4 * step)
+    {
+      double2 xv[4], yv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        xv[u] = ldg2(X + (size_t)(r + u * step) * ldx + c);
+        yv[u] = ldg2(Y + (size_t)(r + u * step) * ldy + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        acc.x = fma(xv[u].x, yv[u].x, acc.x);
+        acc.y = fma(xv[u].y, yv[u].y, acc.y);
+      }
+    }
+    for (; r < n; r += step)
+    {
+      const double2 xv = ldg2(X + (size_t)r * ldx + c), yv = ldg2(Y + (size_t)r * ldy + c);
+      acc.x = fma(xv.x, yv.x, acc.x);
+      acc.y = fma(xv.y, yv.y, acc.y);
+    }
+    __shared__ double2 red[256];
+    red[threadIdx.y * blockDim.x + threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0)
+    {
+      double2 s = make_double2(0.0, 0.0);
+      for (int q = 0; q < (int)blockDim.y; ++q)
+      {
+        s.x += red[q * blockDim.x + threadIdx.x].x;
+        s.y += red[q * blockDim.x + threadIdx.x].y;
+      }
+      st2(partials + (size_t)blockIdx.x * m + c, s);
+    }
+  }
+
+  /** out[e] = sum_p partials[p*len + e], p ascending: the fixed-order (deterministic) second stage of every
+   *  reduction. blockDim = (32,32); each CTA owns 32 consecutive outputs. */
+  __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__restrict__ partials, int nparts,
+                                                                 int len, double *__restrict__ out)
+  {
+    __shared__ double red[32][33];
+    const int e = blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    if (e < len)
+      for (int p = threadIdx.y; p < nparts; p += 32)
+        s += partials[(size_t)p * len + e];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < len)
+    {
+      double tot = 0.0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        tot += red[q][threadIdx.x];
+      out[e] = tot;
+    }
+  }
+
+  // ---- layout conversion at the boundary (reference MultiVector layout <-> row-major) ------------------
+  /** to_rowmajor: dst[i*m + j] = src[((j/8)*n + i)*8 + j%8]; else the inverse. One thread per (row, 8-col panel). */
+  __global__ void __launch_bounds__(256) panel8_convert_kernel(long long n, int m, const double *__restrict__ src,
+                                                               double *__restrict__ dst, int to_rowmajor)
+  {
+    const int np = m / 8;
+    const long long total = n * np;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x)
+    {
+      const long long i = e / np;
+      const int p = (int)(e % np);
+      const size_t pan = ((size_t)p * n + i) * 8, row = (size_t)i * m + 8 * p;
+      const double *s = to_rowmajor ? src + pan : src + row;
+      double *d = to_rowmajor ? dst + row : dst + pan;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        st2(d + 2 * q, ldg2(s + 2 * q));
+    }
+  }
+
+  /** evec[j*n + i] = X(i,j), j < nev (copy-out of eigensolver.hh:109-111): tiled transpose through smem. */
+  __global__ void __launch_bounds__(256) extract_columns_kernel(long long n, int m, int nev,
+                                                                const double *__restrict__ X,
+                                                                double *__restrict__ out)
+  {
+    __shared__ double tile[32][65];
+    const long long i0 = (long long)blockIdx.x * 32;
+    // load 32 rows x m columns (m <= 64), coalesced along columns
+    for (int e = threadIdx.x; e < 32 * m; e += blockDim.x)
+    {
+      const int r = e / m, c = e % m;
+      tile[r][c] = (i0 + r < n) ? X[(size_t)(i0 + r) * m + c] : 0.0;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * nev; e += blockDim.x)
+    {
+      const int c = e / 32, r = e % 32;
+      if (i0 + r < n)
+        out[(size_t)c * n + i0 + r] = tile[r][c];
+    }
+  }
+
+  /** halo pack: buf[s*m + c] = X[rows[s]*m + c] */
+  __global__ void __launch_bounds__(256) pack_rows_kernel(long long count, const int *__restrict__ rows, int m,
+                                                          const double *__restrict__ X, double *__restrict__ buf)
+  {
+    const int hp = m / 2;
+    const long long total = count * hp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x)
+    {
+      const long long s = e / hp;
+      const int c = 2 * (int)(e % hp);
+      st2(buf + (size_t)s * m + c, ldg2(X + (size_t)rows[s] * m + c));
+    }
+  }
+
+} // namespace de

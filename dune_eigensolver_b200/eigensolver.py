@@ -1,0 +1,427 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference's free functions
+(reference dune/eigensolver/eigensolver.hh, kernels_cpp.hh, multivector.hh); the C++ drop-in headers in
+include/dune/eigensolver/ are the primary host side, this module is what the Python parity tests and
+bench.py drive. Matrices are CSR triples `(rowptr, col, val)` (what the C++ header extracts from a
+BCRSMatrix through its iterators); all compute runs on the GPU through libdune_eigensolver_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import DeError, check, dptr, f64, i64, i64ptr, lptr
+
+
+def padded_cols(nev, b=8):
+    """m = smallest multiple of the block size >= nev (reference eigensolver.hh:43)."""
+    return (nev // b + min(nev % b, 1)) * b
+
+
+def to_panels(X):
+    """(n, m) row-major -> reference MultiVector<double,8> storage order (multivector.hh:130-133)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    n, m = X.shape
+    if m % 8 != 0:
+        raise DeError(capi.DE_ERR_INVALID, "number of cols must be a multiple of block size")
+    return np.ascontiguousarray(X.reshape(n, m // 8, 8).transpose(1, 0, 2)).reshape(-1)
+
+
+def from_panels(p, n, m):
+    return np.ascontiguousarray(np.asarray(p).reshape(m // 8, n, 8).transpose(1, 0, 2)).reshape(n, m)
+
+
+def start_block(n, m, seed=123):
+    """The reference's random start block (eigensolver.hh:50-55) in panel8 storage order."""
+    out = np.empty(n * m)
+    check(capi.lib().de_start_block(n, m, seed, dptr(out)))
+    return out
+
+
+class Context:
+    """One GPU + stream + workspaces (+ NCCL communicator once init_comm was called)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        check(capi.lib().de_context_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            capi.lib().de_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(capi.lib().de_context_synchronize(self._h), self._h)
+
+    def launch_count(self):
+        c = C.c_int64(0)
+        check(capi.lib().de_context_launch_count(self._h, C.byref(c)), self._h)
+        return c.value
+
+    def init_comm(self, rank, nranks, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        check(capi.lib().de_context_init_comm(self._h, rank, nranks, buf), self._h)
+
+    def rank(self):
+        r, n = C.c_int(0), C.c_int(1)
+        check(capi.lib().de_context_rank(self._h, C.byref(r), C.byref(n)), self._h)
+        return r.value, n.value
+
+
+def comm_unique_id():
+    buf = (C.c_char * 128)()
+    check(capi.lib().de_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def _csr(A):
+    if hasattr(A, "indptr"):
+        A = (A.indptr, A.indices, A.data)
+    rp, ci, v = A
+    return i64(rp), i64(ci), f64(v)
+
+
+class Matrix:
+    """Device CSR matrix (what the drop-in header builds from a BCRSMatrix<FieldMatrix<double,1,1>>)."""
+
+    def __init__(self, ctx, A=None, _handle=None):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            rp, ci, v = _csr(A)
+            n = len(rp) - 1
+            check(capi.lib().de_matrix_create_csr(ctx._h, n, len(ci), i64ptr(rp), i64ptr(ci), dptr(v),
+                                                  C.byref(self._h)), ctx._h)
+        n, nnz = C.c_int64(0), C.c_int64(0)
+        check(capi.lib().de_matrix_rows(self._h, C.byref(n), C.byref(nnz)))
+        self.n, self.nnz = n.value, nnz.value
+
+    @classmethod
+    def distributed(cls, ctx, n_owned, n_halo, rowptr, col_local, val, peers, recv_counts, send_offsets, send_rows):
+        rp, ci, v = i64(rowptr), i64(col_local), f64(val)
+        peers = capi.i32(peers)
+        rc, so, sr = i64(recv_counts), i64(send_offsets), i64(send_rows)
+        h = C.c_void_p()
+        check(capi.lib().de_matrix_create_distributed(ctx._h, n_owned, n_halo, len(ci), i64ptr(rp), i64ptr(ci), dptr(v),
+                                                      len(peers), capi.i32ptr(peers), i64ptr(rc), i64ptr(so),
+                                                      i64ptr(sr), C.byref(h)), ctx._h)
+        return cls(ctx, _handle=h)
+
+    def close(self):
+        if self._h:
+            capi.lib().de_matrix_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiVector:
+    """Device-resident n x m block; mirrors MultiVector<double,8> (multivector.hh:17-146): zero-initialised,
+    m % 8 == 0 enforced with the reference's message."""
+
+    blocksize = 8
+
+    def __init__(self, ctx, n, m):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        check(capi.lib().de_mv_create(ctx._h, n, m, C.byref(self._h)), ctx._h)
+        self.n, self.m = n, m
+
+    @classmethod
+    def from_array(cls, ctx, X):
+        X = f64(X)
+        mv = cls(ctx, X.shape[0], X.shape[1])
+        mv.upload(X)
+        return mv
+
+    def rows(self):
+        return self.n
+
+    def cols(self):
+        return self.m
+
+    def upload(self, X):
+        """(n, m) array -> device, going through the reference storage order like the C++ boundary does."""
+        p = to_panels(X)
+        check(capi.lib().de_mv_upload_panel8(self._h, dptr(p)), self.ctx._h)
+
+    def upload_panels(self, p):
+        p = f64(p)
+        check(capi.lib().de_mv_upload_panel8(self._h, dptr(p)), self.ctx._h)
+
+    def upload_rowmajor(self, X):
+        X = f64(X)
+        check(capi.lib().de_mv_upload_rowmajor(self._h, dptr(X)), self.ctx._h)
+
+    def download(self):
+        p = np.empty(self.n * self.m)
+        check(capi.lib().de_mv_download_panel8(self._h, dptr(p)), self.ctx._h)
+        return from_panels(p, self.n, self.m)
+
+    def download_rowmajor(self):
+        X = np.empty((self.n, self.m))
+        check(capi.lib().de_mv_download_rowmajor(self._h, dptr(X)), self.ctx._h)
+        return X
+
+    def copy_from(self, other):
+        check(capi.lib().de_mv_copy(self._h, other._h), self.ctx._h)
+
+    def device_ptr(self):
+        p = C.c_void_p()
+        check(capi.lib().de_mv_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def close(self):
+        if self._h:
+            capi.lib().de_mv_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostFactorization:
+    """One-time host factorisation filling the UMFPACK field contract (reference umfpacktools.hh:26-44):
+    stand-in for UMFPackFactorizedMatrix's constructor where UMFPACK is not installed."""
+
+    def __init__(self, A, ordering=1, scale_rows=False):
+        rp, ci, v = _csr(A)
+        self._h = C.c_void_p()
+        check(capi.lib().de_host_factorize(len(rp) - 1, i64ptr(rp), i64ptr(ci), dptr(v), ordering, int(scale_rows),
+                                           C.byref(self._h)))
+        n, lnz, unz, rec = C.c_int64(), C.c_int64(), C.c_int64(), C.c_long()
+        ptrs = [C.POINTER(C.c_long)(), C.POINTER(C.c_long)(), C.POINTER(C.c_double)(), C.POINTER(C.c_long)(),
+                C.POINTER(C.c_long)(), C.POINTER(C.c_double)(), C.POINTER(C.c_long)(), C.POINTER(C.c_long)(),
+                C.POINTER(C.c_double)()]
+        check(capi.lib().de_host_factor_arrays(self._h, C.byref(n), C.byref(lnz), C.byref(unz),
+                                               *[C.byref(p) for p in ptrs], C.byref(rec)))
+        self.n, self.lnz, self.unz, self.do_recip = n.value, lnz.value, unz.value, rec.value
+        sizes = [self.n + 1, self.lnz, self.lnz, self.n + 1, self.unz, self.unz, self.n, self.n, self.n]
+        names = ["Lp", "Lj", "Lx", "Up", "Ui", "Ux", "P", "Q", "Rs"]
+        for name, p, s in zip(names, ptrs, sizes):
+            setattr(self, name, np.ctypeslib.as_array(p, shape=(s,)).copy() if s > 0 else
+                    np.zeros(0, dtype=np.float64 if name in ("Lx", "Ux", "Rs") else np.int64))
+
+    def arrays(self):
+        return {k: getattr(self, k) for k in ("Lp", "Lj", "Lx", "Up", "Ui", "Ux", "P", "Q", "Rs", "do_recip")}
+
+    def close(self):
+        if self._h:
+            capi.lib().de_host_factor_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Factor:
+    """Device copy of a factorisation in the UMFPACK field contract, with its level schedules."""
+
+    def __init__(self, ctx, F):
+        """F: HostFactorization or dict with Lp,Lj,Lx,Up,Ui,Ux,P,Q,Rs,do_recip."""
+        if isinstance(F, HostFactorization):
+            F = F.arrays()
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        ia = {k: np.ascontiguousarray(F[k], dtype=np.int64) for k in ("Lp", "Lj", "Up", "Ui", "P", "Q")}
+        da = {k: f64(F[k]) for k in ("Lx", "Ux", "Rs")}
+        n = len(ia["Lp"]) - 1
+        check(capi.lib().de_factor_upload(ctx._h, n, lptr(ia["Lp"]), lptr(ia["Lj"]), dptr(da["Lx"]), lptr(ia["Up"]),
+                                          lptr(ia["Ui"]), dptr(da["Ux"]), lptr(ia["P"]), lptr(ia["Q"]), dptr(da["Rs"]),
+                                          int(F["do_recip"]), C.byref(self._h)), ctx._h)
+        self.n = n
+
+    def info(self):
+        n, lnz, unz, ll, lu = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int(), C.c_int()
+        check(capi.lib().de_factor_info(self._h, C.byref(n), C.byref(lnz), C.byref(unz), C.byref(ll), C.byref(lu)))
+        return {"n": n.value, "lnz": lnz.value, "unz": unz.value, "levels_L": ll.value, "levels_U": lu.value}
+
+    def close(self):
+        if self._h:
+            capi.lib().de_factor_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- kernels: reference names (kernels_cpp.hh) --------------------------------------------------------------
+def matmul_sparse_tallskinny_blocked(Qout, A, Qin):
+    """Qout = A * Qin (kernels_cpp.hh:626-657)."""
+    check(capi.lib().de_spmm(Qout._h, A._h, Qin._h), A.ctx._h)
+
+
+def matmul_sparse_tallskinny_with_dots(Qout, A, Qin):
+    """Qout = A * Qin and the column-wise dot products diag(Qin^T Qout) from the same pass."""
+    dp = np.empty(Qin.m)
+    check(capi.lib().de_spmm_diag_dot(Qout._h, A._h, Qin._h, dptr(dp)), A.ctx._h)
+    return dp
+
+
+def dot_products_diagonal_blocked(Q1, Q2):
+    """dp[j] = <Q1[:,j], Q2[:,j]> (kernels_cpp.hh:24-55); returns dp (the reference resizes its out-argument)."""
+    dp = np.empty(Q1.m)
+    check(capi.lib().de_diag_dot(dptr(dp), Q1._h, Q2._h), Q1.ctx._h)
+    return dp
+
+
+def dot_products_all_blocked(Q1, Q2):
+    """Full Gram matrix Q1^T Q2 (kernels_cpp.hh:58-96)."""
+    G = np.empty((Q1.m, Q1.m))
+    check(capi.lib().de_gram(dptr(G), Q1._h, Q2._h), Q1.ctx._h)
+    return G
+
+
+def block_update(Q, R):
+    """Q <- Q R (kernels_cpp.hh:293-305, :514-539)."""
+    R = f64(R)
+    if R.shape != (Q.m, Q.m):
+        raise DeError(capi.DE_ERR_INVALID, "block_update: factor must be m x m")
+    check(capi.lib().de_block_update(Q._h, dptr(R)), Q.ctx._h)
+
+
+def block_project(Q, j0, k0, S):
+    """Q[:, j0:j0+w] -= Q[:, k0:k0+w] S (kernels_cpp.hh:335-348)."""
+    S = f64(S)
+    check(capi.lib().de_block_project(Q._h, j0, k0, S.shape[0], dptr(S)), Q.ctx._h)
+
+
+def orthonormalize_blocked(Q):
+    """In-place thin QR with positive-diagonal triangular factor (kernels_cpp.hh:180-351)."""
+    check(capi.lib().de_orthonormalize(Q._h), Q.ctx._h)
+
+
+def B_orthonormalize_blocked(B, Q, BQ=None):
+    """In-place B-orthonormalisation (kernels_cpp.hh:356-591); returns the `norm` diagnostic."""
+    nrm = C.c_double(0.0)
+    check(capi.lib().de_b_orthonormalize(B._h, Q._h, BQ._h if BQ is not None else None, C.byref(nrm)), Q.ctx._h)
+    return nrm.value
+
+
+def matmul_inverse_tallskinny_blocked(Qout, F, Qin):
+    """Qout = A^-1 Qin through the factors; Qin is scratch (kernels_cpp.hh:660-755)."""
+    check(capi.lib().de_factor_apply(Qout._h, F._h, Qin._h), F.ctx._h)
+
+
+# ---- drivers: reference names (eigensolver.hh) ---------------------------------------------------------------
+def _add_to_diagonal(rp, ci, v, s):
+    n = len(rp) - 1
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+    v[rows == ci] += s
+
+
+class Result:
+    def __init__(self, eval_, evec, iterations, relerror=None, time_factorization=None):
+        self.eval, self.evec, self.iterations = eval_, evec, iterations
+        self.relerror, self.time_factorization = relerror, time_factorization
+
+
+def StandardLargest(ctx, A, shift, tol, maxiter, nev, verbose=0, seed=123, start=None):
+    """reference StandardLargest (eigensolver.hh:28-112). `A = (rowptr, col, val)`; like the reference the
+    caller's values are shifted in place when shift != 0."""
+    rp, ci, v = A if isinstance(A, tuple) else (A.indptr, A.indices, A.data)
+    n = len(rp) - 1
+    m = padded_cols(nev)
+    if start is None:
+        start = start_block(n, m, seed)
+    if shift != 0.0:
+        _add_to_diagonal(np.asarray(rp), np.asarray(ci), v, shift)
+    dA = Matrix(ctx, (rp, ci, v))
+    try:
+        ev, V, it = np.zeros(nev), np.zeros((nev, n)), C.c_int(0)
+        check(capi.lib().de_standard_largest(ctx._h, dA._h, shift, tol, maxiter, nev, dptr(f64(start)), dptr(ev),
+                                             dptr(V), verbose, C.byref(it)), ctx._h)
+    finally:
+        dA.close()
+    return Result(ev, V, it.value)
+
+
+def StandardInverse(ctx, A, shift, tol, maxiter, nev, verbose=0, seed=123, start=None, ordering=1):
+    """reference StandardInverse (eigensolver.hh:116-198)."""
+    rp, ci, v = A if isinstance(A, tuple) else (A.indptr, A.indices, A.data)
+    n = len(rp) - 1
+    m = padded_cols(nev)
+    if start is None:
+        start = start_block(n, m, seed)
+    if shift != 0.0:
+        _add_to_diagonal(np.asarray(rp), np.asarray(ci), v, shift)
+    hF = HostFactorization((rp, ci, v), ordering)
+    dA = Matrix(ctx, (rp, ci, v))
+    dF = Factor(ctx, hF)
+    try:
+        ev, V, it = np.zeros(nev), np.zeros((nev, n)), C.c_int(0)
+        check(capi.lib().de_standard_inverse(ctx._h, dA._h, dF._h, shift, tol, maxiter, nev, dptr(f64(start)),
+                                             dptr(ev), dptr(V), verbose, C.byref(it)), ctx._h)
+    finally:
+        dA.close()
+        dF.close()
+        hF.close()
+    return Result(ev, V, it.value)
+
+
+def GeneralizedInverse(ctx, inA, B, shift, reg, tol, maxiter, nev, verbose=0, seed=123, start=None, ordering=1):
+    """reference GeneralizedInverse (eigensolver.hh:204-351): A x = lambda B x by shift-invert subspace iteration.
+    The input matrix is copied (eigensolver.hh:208); pattern(B) must be contained in pattern(A)."""
+    import time
+
+    rpa, cia, va = inA if isinstance(inA, tuple) else (inA.indptr, inA.indices, inA.data)
+    rpb, cib, vb = B if isinstance(B, tuple) else (B.indptr, B.indices, B.data)
+    rpa, cia, va = i64(rpa), i64(cia), f64(va).copy()
+    rpb, cib, vb = i64(rpb), i64(cib), f64(vb)
+    n = len(rpa) - 1
+    m = padded_cols(nev)
+    if start is None:
+        start = start_block(n, m, seed)
+    if shift != 0.0:  # A.axpy(shift, B) (eigensolver.hh:241-242)
+        if len(cia) == len(cib) and np.array_equal(rpa, rpb) and np.array_equal(cia, cib):
+            va += shift * vb
+        else:
+            rows_b = np.repeat(np.arange(n, dtype=np.int64), np.diff(rpb))
+            keys_a = np.repeat(np.arange(n, dtype=np.int64), np.diff(rpa)) * n + cia
+            pos = np.searchsorted(keys_a, rows_b * n + cib)
+            if np.any(pos >= len(keys_a)) or np.any(keys_a[np.minimum(pos, len(keys_a) - 1)] != rows_b * n + cib):
+                raise DeError(capi.DE_ERR_INVALID, "GeneralizedInverse: pattern of B not contained in pattern of A")
+            np.add.at(va, pos, shift * vb)
+    if reg != 0.0:
+        _add_to_diagonal(rpa, cia, va, reg)
+    t0 = time.perf_counter()
+    hF = HostFactorization((rpa, cia, va), ordering)
+    t_fact = time.perf_counter() - t0
+    dA, dB = Matrix(ctx, (rpa, cia, va)), Matrix(ctx, (rpb, cib, vb))
+    dF = Factor(ctx, hF)
+    try:
+        ev, V, it, rel = np.zeros(nev), np.zeros((nev, n)), C.c_int(0), C.c_double(0.0)
+        check(capi.lib().de_generalized_inverse(ctx._h, dA._h, dB._h, dF._h, shift, tol, maxiter, nev,
+                                                dptr(f64(start)), dptr(ev), dptr(V), verbose, C.byref(it),
+                                                C.byref(rel)), ctx._h)
+    finally:
+        dA.close()
+        dB.close()
+        dF.close()
+        hF.close()
+    if verbose > 0:  # the reference's summary line (eigensolver.hh:344-350)
+        print("GeneralizedInverse:  time_factorization=%g iterations=%d relerror=%g" % (t_fact, it.value, rel.value))
+    return Result(ev, V, it.value, rel.value, t_fact)

@@ -335,8 +335,9 @@ namespace de_b200
         Urx[t] = x[Urj[t]];
         x[Urj[t]] = 0.0;
       }
+      // a pivot that is zero up to round-off of the elimination counts as structurally singular
       const double piv = Urx[Urp[k]];
-      if (piv != 0.0 && std::abs(piv) > 1e-300 && std::isfinite(piv))
+      if (std::isfinite(piv) && std::abs(piv) > 64.0 * 2.220446049250313e-16 * amax)
         ++nz_udiag;
     }
 
@@ -385,7 +386,6 @@ namespace de_b200
     }
     F.P.assign(perm.begin(), perm.end());
     F.Q.assign(perm.begin(), perm.end());
-    (void)amax;
   }
 
   //! convenience: ordering + factorisation

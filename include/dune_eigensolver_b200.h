@@ -1,0 +1,186 @@
+/* dune_eigensolver_b200.h -- C ABI of the B200-native block-eigensolver hot path.
+ *
+ * The reference (normallytangent/dune-eigensolver) has no FFI: its API is header-only C++ templates.
+ * The drop-in boundary is therefore (1) the source-level signatures of the reference headers, re-created
+ * in include/dune/eigensolver/{multivector,kernels_b200,eigensolver}.hh, and (2) this C ABI directly beneath
+ * them. Every entry point below names the reference function or type it replaces (file:line relative to
+ * the reference root). Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns a de_status (0 = ok); de_last_error_string() gives the message
+ *   - host pointers are borrowed for the duration of the call only; the library never frees caller memory
+ *   - a de_context is used by one host thread at a time; several contexts may coexist
+ *   - all arithmetic is IEEE fp64; there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with DE_ERR_CUDA
+ *   - "panel8" = the reference MultiVector<double,8> layout (multivector.hh:130-133):
+ *       element (i,j) at ((j/8)*n + i)*8 + j%8 ; the number of columns must be a multiple of 8
+ */
+#ifndef DUNE_EIGENSOLVER_B200_H
+#define DUNE_EIGENSOLVER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct de_context de_context;
+typedef struct de_matrix de_matrix;
+typedef struct de_mv de_mv;
+typedef struct de_factor de_factor;
+typedef struct de_host_factor de_host_factor;
+
+typedef enum de_status
+{
+  DE_OK = 0,
+  DE_ERR_INVALID = 1,     /* shape / block-size / argument violation (reference: std::invalid_argument) */
+  DE_ERR_ALLOC = 2,
+  DE_ERR_CUDA = 3,
+  DE_ERR_NCCL = 4,
+  DE_ERR_SINGULAR = 5,    /* factorisation singular (umfpacktools.hh:160-164) or Gram matrix not positive definite */
+  DE_ERR_UNSUPPORTED = 6
+} de_status;
+
+#define DE_MAX_COLS 64 /* widest column block the fused kernels handle (north_star: p = 8..64) */
+
+int de_version(void);
+/* message of the last failure on this context (ctx may be NULL: last failure of the calling thread) */
+const char *de_last_error_string(const de_context *ctx);
+
+/* ---- context ------------------------------------------------------------------------------------
+ * device: CUDA ordinal. stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to let
+ * the context create its own. */
+int de_context_create(int device, void *stream, de_context **out);
+int de_context_destroy(de_context *ctx);
+int de_context_synchronize(de_context *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int de_context_launch_count(const de_context *ctx, int64_t *count);
+
+/* Multi-GPU (new; the reference is single-threaded): one process per GPU. Rank 0 obtains an
+ * id with de_comm_unique_id (128 bytes), the host distributes it (torch.distributed / MPI), every rank calls
+ * de_context_init_comm. Reductions of diag-dot / Gram results are then all-reduced over NCCL and distributed
+ * matrices exchange their halo rows over NVLink. */
+int de_comm_unique_id(void *id128);
+int de_context_init_comm(de_context *ctx, int rank, int nranks, const void *id128);
+int de_context_rank(const de_context *ctx, int *rank, int *nranks);
+
+/* ---- sparse matrix: replaces BCRSMatrix<FieldMatrix<double,1,1>> traversal ------------------------
+ * (eigensolver.hh:32-66,208-252; kernels_cpp.hh:383-392,644-653). Header code flattens BCRS -> CSR once
+ * per solve, AFTER applying shift / axpy / regularisation on the host exactly as the reference does. */
+int de_matrix_create_csr(de_context *ctx, int64_t n, int64_t nnz, const int64_t *rowptr, const int64_t *col,
+                         const double *val, de_matrix **out);
+/* Row-partitioned matrix: this rank owns `n_owned` consecutive rows. Columns are already renumbered to
+ * [0,n_owned) = owned rows of the vector block, [n_owned, n_owned+n_halo) = halo rows received from peers.
+ * Peers are listed in ascending rank order; recv_counts[p] halo rows arrive from peer p (they occupy the
+ * halo range in peer order), and the owned rows send_rows[send_offsets[p] .. send_offsets[p+1]) are sent
+ * to peer p. Build these with de_halo_plan_* below. */
+int de_matrix_create_distributed(de_context *ctx, int64_t n_owned, int64_t n_halo, int64_t nnz,
+                                 const int64_t *rowptr, const int64_t *col_local, const double *val, int npeers,
+                                 const int *peer_ranks, const int64_t *recv_counts, const int64_t *send_offsets,
+                                 const int64_t *send_rows, de_matrix **out);
+int de_matrix_destroy(de_matrix *A);
+int de_matrix_rows(const de_matrix *A, int64_t *n_owned, int64_t *nnz);
+
+/* Host-only halo planning for a 1-D row partition (no GPU needed; exercised by the gloo CPU tests).
+ * Input: this rank's rows [row_begin,row_end) of the global CSR with GLOBAL column indices and the partition
+ * offsets part[0..nranks]. Output (caller-allocated): col_local[nnz]; halo_global[] (capacity nnz) = global
+ * index of every halo row in halo order (sorted by owner then index); recv_counts[nranks] per owner. */
+int de_halo_plan_local(int64_t n_owned, const int64_t *rowptr, const int64_t *col_global, int nranks, int rank,
+                       const int64_t *part, int64_t *col_local, int64_t *halo_global, int64_t *n_halo,
+                       int64_t *recv_counts);
+
+/* ---- multivector: replaces MultiVector<double,8> (multivector.hh:17-146) ---------------------------
+ * Device-resident n x m block (row-major inside the library; the layout is opaque). m % 8 == 0 is enforced
+ * like multivector.hh:48-49; storage is zero-initialised like multivector.hh:52. For a distributed run n is
+ * the number of OWNED rows. */
+int de_mv_create(de_context *ctx, int64_t n, int m, de_mv **out);
+int de_mv_destroy(de_mv *X);
+int de_mv_shape(const de_mv *X, int64_t *n, int *m);
+int de_mv_upload_panel8(de_mv *X, const double *host_panel8);
+int de_mv_download_panel8(const de_mv *X, double *host_panel8);
+int de_mv_upload_rowmajor(de_mv *X, const double *host_rowmajor);
+int de_mv_download_rowmajor(const de_mv *X, double *host_rowmajor);
+int de_mv_copy(de_mv *dst, const de_mv *src);
+/* raw device pointer (row-major, leading dimension m) for zero-copy interop */
+int de_mv_device_ptr(de_mv *X, void **dptr);
+
+/* ---- kernels --------------------------------------------------------------------------------------*/
+/* Y = A X.  replaces matmul_sparse_tallskinny_{naive,blocked,avx2_b8,neon_b8}
+ * (kernels_cpp.hh:596-657, kernels_avx2.hh:1021-1059, kernels_neon.hh:1314-1361). All m columns in one pass
+ * over A. */
+int de_spmm(de_mv *Y, const de_matrix *A, const de_mv *X);
+/* Y = A X and dp[j] = sum_i X(i,j) Y(i,j) in the same pass (the SpMM + dot_products_diagonal_blocked pair of
+ * eigensolver.hh:84-85, :174-175, :308-309). dp_host has m entries. */
+int de_spmm_diag_dot(de_mv *Y, const de_matrix *A, const de_mv *X, double *dp_host);
+/* dp[j] = sum_i X(i,j) Y(i,j).  replaces dot_products_diagonal_{blocked,avx2_b8,neon_b8} (kernels_cpp.hh:24-55) */
+int de_diag_dot(double *dp_host, const de_mv *X, const de_mv *Y);
+/* G = X^T Y, row-major m x m on the host. replaces dot_products_all_blocked (kernels_cpp.hh:58-96) and the naive
+ * dot_products_diagonal(Q) full Gram (kernels_cpp.hh:7-21) */
+int de_gram(double *G_host, const de_mv *X, const de_mv *Y);
+/* X <- X Q with Q a row-major m x m host matrix: the block update of kernels_cpp.hh:293-305, :514-539 (Q upper
+ * triangular there) written for a general Q */
+int de_block_update(de_mv *X, const double *Q_host);
+/* X[:, j0:j0+w) -= X[:, k0:k0+w) S with S a row-major w x w host matrix: the projection of
+ * kernels_cpp.hh:335-348, :570-583 (w = 8 there) */
+int de_block_project(de_mv *X, int j0, int k0, int w, const double *S_host);
+/* In-place thin QR, X <- X R^-1 with R upper triangular, positive diagonal (so the column order of Gram-Schmidt
+ * is preserved). replaces orthonormalize_{naive,blocked,avx2_b8,avx2_b8_v2,neon_b8,neon_b8_v2}
+ * (kernels_cpp.hh:121-155, :180-351). Algorithm: CholQR2 over the whole block. */
+int de_orthonormalize(de_mv *X);
+/* Same in the B inner product, X^T B X = I. replaces B_orthonormalize_{blocked,avx2_b8,neon_b8}
+ * (kernels_cpp.hh:356-591). If BX is not NULL it receives B*X for the orthonormalised X (the reference keeps
+ * that product in its scratch panel `p`, kernels_cpp.hh:372,527-539). *norm (may be NULL) receives the largest
+ * strict-upper entry of the first Gram matrix X^T B X (diagnostic; unused by the reference's callers). */
+int de_b_orthonormalize(const de_matrix *B, de_mv *X, de_mv *BX, double *norm);
+
+/* ---- factored inverse apply -----------------------------------------------------------------------
+ * replaces UMFPackFactorizedMatrix's field contract (umfpacktools.hh:26-44) and
+ * matmul_inverse_tallskinny_{blocked,avx2_b8,neon_b8} (kernels_cpp.hh:660-755). L: CSR, unit diagonal stored
+ * last in each row; U: CSC, diagonal last in each column; P, Q, Rs, do_recip as UMFPACK defines them. The upload
+ * builds the level schedules once; single-GPU only (triangular solves do not row-shard). */
+int de_factor_upload(de_context *ctx, int64_t n, const long *Lp, const long *Lj, const double *Lx, const long *Up,
+                     const long *Ui, const double *Ux, const long *P, const long *Q, const double *Rs, long do_recip,
+                     de_factor **out);
+int de_factor_destroy(de_factor *F);
+/* Y = A^-1 X ; X is used as scratch and is clobbered, as in the reference (kernels_cpp.hh:659) */
+int de_factor_apply(de_mv *Y, const de_factor *F, de_mv *X);
+int de_factor_info(const de_factor *F, int64_t *n, int64_t *lnz, int64_t *unz, int *levels_L, int *levels_U);
+
+/* ---- whole-driver entry points: the iteration loop never leaves the device ------------------------
+ * start_panel8: the n x m start block (m = nev rounded up to a multiple of 8) filled by the caller exactly as
+ * eigensolver.hh:50-55 does (de_start_block reproduces that stream). eval: nev values; evec: nev vectors of
+ * length n, vector j at evec + j*n (both caller-allocated, as eigensolver.hh:105-111 assumes). *iterations
+ * receives the reference's loop counter at exit. The shift must already be part of A (the header applies it
+ * on the host like eigensolver.hh:57-66); it is passed only to be subtracted from the Rayleigh quotients. */
+/* replaces StandardLargest (eigensolver.hh:28-112) */
+int de_standard_largest(de_context *ctx, const de_matrix *A, double shift, double tol, int maxiter, int nev,
+                        const double *start_panel8, double *eval, double *evec, int verbose, int *iterations);
+/* replaces StandardInverse (eigensolver.hh:116-198); F = factorisation of the shifted A */
+int de_standard_inverse(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
+                        int maxiter, int nev, const double *start_panel8, double *eval, double *evec, int verbose,
+                        int *iterations);
+/* replaces GeneralizedInverse (eigensolver.hh:204-351); A = inA + shift*B + reg*I (built on the host like
+ * eigensolver.hh:241-252), F its factorisation */
+int de_generalized_inverse(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *F, double shift,
+                           double tol, int maxiter, int nev, const double *start_panel8, double *eval, double *evec,
+                           int verbose, int *iterations, double *relerror);
+
+/* ---- host-side helpers (no GPU) -------------------------------------------------------------------*/
+/* the reference's start block: std::mt19937{seed} + std::normal_distribution<double>{0,1}, filled
+ * panel -> row -> column-in-panel (eigensolver.hh:50-55, :138-143, :232-237) */
+int de_start_block(int64_t n, int m, unsigned seed, double *out_panel8);
+/* one-time host factorisation filling the UMFPACK field contract (stand-in for umfpacktools.hh:46-199 where
+ * UMFPACK is unavailable): ordering 0 = natural, 1 = nested dissection (METIS), 2 = RCM */
+int de_host_factorize(int64_t n, const int64_t *rowptr, const int64_t *col, const double *val, int ordering,
+                      int scale_rows, de_host_factor **out);
+int de_host_factor_arrays(const de_host_factor *F, int64_t *n, int64_t *lnz, int64_t *unz, const long **Lp,
+                          const long **Lj, const double **Lx, const long **Up, const long **Ui, const double **Ux,
+                          const long **P, const long **Q, const double **Rs, long *do_recip);
+int de_host_factor_destroy(de_host_factor *F);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DUNE_EIGENSOLVER_B200_H */

@@ -1,0 +1,108 @@
+"""Driver-level parity on the GPU (north_star): eigenvalues within 1e-10 relative, eigenvector residuals
+||A x - lambda B x|| under the same tolerance as the reference's, iteration counts within +-1."""
+import numpy as np
+import pytest
+
+from dune_eigensolver_b200 import eigensolver as E, matrices as M
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-10
+
+
+def rel_err(a, b):
+    return np.abs(a - b).max() / max(1e-300, np.abs(b).max())
+
+
+def residuals(A, B, lam, V):
+    A = M.to_scipy(A)
+    out = []
+    for j in range(len(lam)):
+        x = V[j]
+        bx = x if B is None else M.to_scipy(B) @ x
+        out.append(np.linalg.norm(A @ x - lam[j] * bx))
+    return np.array(out)
+
+
+def copy(A):
+    return (A[0].copy(), A[1].copy(), A[2].copy())
+
+
+def test_standard_largest_golden(ctx, golden):
+    """N = 20, nev = 8, tol = 1e-10 -> 1456 iterations in the reference."""
+    A = M.laplacian_dirichlet_2d(20)
+    r = E.StandardLargest(ctx, copy(A), 0.0, 1e-10, 4000, 8)
+    assert abs(r.iterations - int(golden["d_largest_iter"])) <= 1
+    assert rel_err(r.eval, golden["d_largest_eval"]) <= REL
+    an = M.eigenvalues_laplace_dirichlet_2d(20)[::-1][:8]
+    assert np.abs(r.eval - an).max() < 2e-8
+
+
+@pytest.mark.parametrize("N,nev,shift,tol", [(12, 8, 0.0, 1e-12), (30, 16, 0.0, 1e-8), (24, 5, 0.25, 1e-10), (40, 16, 0.0, 2e-3)])
+def test_standard_largest_matches_oracle(ctx, oracle, N, nev, shift, tol):
+    A = M.laplacian_dirichlet_2d(N)
+    ev, V, k = oracle.standard_largest(copy(A), shift, tol, 4000, nev)
+    Ain = copy(A)
+    r = E.StandardLargest(ctx, Ain, shift, tol, 4000, nev)
+    assert abs(r.iterations - k) <= 1
+    # eigenvalue parity at the reference's own convergence level: both stop when successive Rayleigh quotients
+    # differ by < tol, so they agree to ~tol (and to 1e-10 relative once tol is that tight)
+    assert rel_err(r.eval, ev) <= max(REL, 10 * tol / 8.0)
+    if shift != 0.0:  # the reference shifts the caller's matrix in place (eigensolver.hh:57-66)
+        assert np.allclose(Ain[2][Ain[1] == np.repeat(np.arange(N * N), np.diff(Ain[0]))], 4.0 + shift)
+    res_ref = residuals(A, None, ev + 0 * shift, V) if shift == 0.0 else None
+    if res_ref is not None:
+        res = residuals(A, None, r.eval, r.evec)
+        assert np.all(res <= 2.0 * res_ref + 1e-9)
+
+
+def test_standard_inverse_matches_oracle(ctx, oracle, golden):
+    A = M.laplacian_dirichlet_2d(20)
+    r = E.StandardInverse(ctx, copy(A), 1e-3, 1e-10, 4000, 8)
+    assert abs(r.iterations - int(golden["d_inverse_iter"])) <= 1
+    assert rel_err(r.eval, golden["d_inverse_eval"]) <= REL
+    an = M.eigenvalues_laplace_dirichlet_2d(20)[:8]
+    assert np.abs(r.eval - an).max() < 1e-9
+    ev, V, k = oracle.standard_inverse(copy(A), 1e-3, 1e-10, 4000, 8)
+    res_ref, res = residuals(A, None, ev, V), residuals(A, None, r.eval, r.evec)
+    assert np.all(res <= 2.0 * res_ref + 1e-9)
+
+
+def test_generalized_inverse_golden(ctx, golden):
+    """N = 16, overlap 3, shift 1e-3, nev 8, tol 1e-12 -> iterations = 121."""
+    A, B = M.laplacian_neumann_2d(16), M.laplacian_B_2d(16, 3)
+    r = E.GeneralizedInverse(ctx, A, B, 1e-3, 0.0, 1e-12, 4000, 8)
+    assert abs(r.iterations - 121) <= 1
+    assert np.abs(r.eval - golden["d_geninv_eval"]).max() <= REL * np.abs(golden["d_geninv_eval"]).max()
+    res = residuals(A, B, r.eval, r.evec)
+    assert np.all(res < 1e-5)
+
+
+@pytest.mark.parametrize("N,nev,tol,reg", [(40, 16, 2e-3, 0.0), (24, 12, 1e-10, 0.0), (20, 8, 1e-9, 1e-4)])
+def test_generalized_inverse_matches_oracle(ctx, oracle, golden, N, nev, tol, reg):
+    """includes the shipped ini configuration (tol 2e-3, shift 1e-3, overlap 3, ev.m = 16) at N = 40."""
+    A, B = M.laplacian_neumann_2d(N), M.laplacian_B_2d(N, 3)
+    ev, V, it = oracle.generalized_inverse(A, B, 1e-3, reg, tol, 4000, nev)
+    r = E.GeneralizedInverse(ctx, A, B, 1e-3, reg, tol, 4000, nev)
+    assert abs(r.iterations - it) <= 1
+    assert np.abs(r.eval - ev).max() <= max(REL, 10 * tol) * np.abs(ev).max()
+    res_ref, res = residuals(A, B, ev, V), residuals(A, B, r.eval, r.evec)
+    assert np.all(res <= 2.0 * res_ref + 1e-8)
+
+
+def test_q1_pencil_3d_against_analytic(ctx):
+    """new generators: 3D Q1 stiffness + mass (BASELINE config 3 in small): smallest eigenvalues of K x = lambda M x."""
+    shape = (9, 8, 7)
+    K, Mm = M.q1_stiffness(shape), M.q1_mass(shape)
+    r = E.GeneralizedInverse(ctx, K, Mm, 1e-3, 0.0, 1e-13, 4000, 8)
+    an = M.eigenvalues_q1_pencil(shape)[:8]
+    assert np.abs(np.sort(r.eval) - an).max() <= 1e-8 * an.max()
+
+
+def test_nev_not_multiple_of_eight_and_maxiter(ctx, oracle):
+    A = M.laplacian_dirichlet_2d(10)
+    ev, V, k = oracle.standard_largest(copy(A), 0.0, 1e-30, 7, 5)  # never converges: runs to maxiter - 1
+    r = E.StandardLargest(ctx, copy(A), 0.0, 1e-30, 7, 5)
+    assert k == 6 and r.iterations == 6
+    assert r.eval.shape == (5,) and r.evec.shape == (5, 100)
+    assert rel_err(r.eval, ev) <= 1e-9
