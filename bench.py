@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- time-to-m-eigenpairs of the block eigensolver hot path on B200, next to the reference CPU path.
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on at 1 GPU): 3D Q1 (27-point
+trilinear finite-element) Laplace stiffness matrix on 100^3 interior nodes, 32 eigenpairs. configs[1] names a
+LOBPCG driver that the reference does not contain; the driver timed here is the reference's own
+StandardLargest (reference dune/eigensolver/eigensolver.hh:28-112) with the parameters of the shipped ini
+(reference src/dune-eigensolver.ini: tol = 2e-3, maxiter = 4000, seed = 123), shift = 0.
+
+A "step" is ONE complete solve (start block already orthonormalisation-ready on the device -> converged
+eigenpairs): every iteration is one pass of the hot path (SpMM + fused Rayleigh quotients, CholQR2
+orthonormalisation, convergence test on m values copied to the host).
+
+  value : seconds per solve with matrix and start block resident in HBM (device-resident driver entry point)
+  e2e   : the same solve through the reference-facing call with HOST buffers (CSR arrays in, eigenvectors out):
+          host->device copies of matrix and start block and the device->host copy of the eigenvectors are inside
+          the timed region
+  --impl reference : the reference's own CPU implementation (oracle/_ref = its headers compiled verbatim, else the
+          oracle port), single-threaded as the reference is, on a bounded sample of iterations of the same solve,
+          extrapolated to the iteration count of the full solve (stated in `sample`)
+
+N > 1 GPUs: the same global problem row-partitioned into z-slabs (strong scaling), halo rows over NCCL/NVLink.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Iterations StandardLargest needs on this workload (N = 100, 27-point Q1, m = 32, tol = 2e-3, seed = 123).
+# Measured by this script's own arm on B200 (asserted there to +-1 on every run); the CPU arms need it only to
+# extrapolate their bounded sample to a full solve.
+ITERATIONS_TO_CONVERGENCE = {(100, "q1", 32, 2e-3): None}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--grid", type=int, default=100, help="interior nodes per dimension")
+    ap.add_argument("--stencil", default="q1", choices=["q1", "fd"])
+    ap.add_argument("--nev", type=int, default=32)
+    ap.add_argument("--tol", type=float, default=2e-3)
+    ap.add_argument("--maxiter", type=int, default=4000)
+    ap.add_argument("--cpu-sample-iters", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def generator(args):
+    from dune_eigensolver_b200 import matrices as M
+
+    shape = (args.grid,) * 3
+    return (lambda rows=None: M.q1_stiffness(shape, rows=rows)) if args.stencil == "q1" else \
+           (lambda rows=None: M.laplacian_fd(shape, rows=rows))
+
+
+def workload_name(args):
+    st = "Q1 27-point FE stiffness" if args.stencil == "q1" else "7-point FD"
+    return ("3D %s Laplace %d^3 (n=%d), %d eigenpairs, StandardLargest (reference eigensolver.hh:28-112), "
+            "tol=%g maxiter=%d seed=123 (reference ini), shift=0" %
+            (st, args.grid, args.grid ** 3, args.nev, args.tol, args.maxiter))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_sample(args, sample_iters, iterations_full):
+    """Time `sample_iters` iterations of the reference's StandardLargest on the host (1 thread, as the reference
+    runs) and extrapolate to `iterations_full`. Returns (seconds_extrapolated, seconds_per_iteration, kind)."""
+    from oracle import oracle as O
+
+    orc = O.load_best()
+    if orc is None:
+        raise RuntimeError("no oracle library (run __graft_entry__.build())")
+    A = generator(args)()
+    rp, ci, v = (np.ascontiguousarray(A[0], dtype=np.int64), np.ascontiguousarray(A[1], dtype=np.int64),
+                 np.ascontiguousarray(A[2]))
+
+    def run(iters):  # tol < 0 never converges: exactly maxiter-1 = iters iterations of the reference loop
+        t0 = time.perf_counter()
+        ev, V, k = orc.standard_largest((rp, ci, v), 0.0, -1.0, iters + 1, args.nev)
+        dt = time.perf_counter() - t0
+        assert k == max(iters, 1), (k, iters)
+        return dt
+
+    # two run lengths separate the per-iteration cost from the fixed cost (start block, first orthonormalisation)
+    t_short = run(1)
+    t_long = run(1 + sample_iters)
+    per_iter = (t_long - t_short) / sample_iters
+    fixed = max(t_short - per_iter, 0.0)
+    return fixed + per_iter * iterations_full, per_iter, orc.kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    key = (args.grid, args.stencil, args.nev, args.tol)
+    iters = ITERATIONS_TO_CONVERGENCE.get(key)
+    note = "iterations-to-convergence %s from the B200 arm of this script (parity +-1 tested)" % iters
+    if iters is None:
+        iters = 100
+        note = "iterations-to-convergence unknown for this configuration: assumed 100"
+    vals, per = [], []
+    kind = "port"
+    for s in range(args.warmup + args.steps):
+        tot, per_iter, kind = cpu_reference_sample(args, args.cpu_sample_iters, iters)
+        if s >= args.warmup:
+            vals.append(tot)
+            per.append(per_iter)
+        if s == 0 and per_iter * args.cpu_sample_iters * (args.warmup + args.steps) > 240:
+            # keep the whole run within a few minutes: one measured step stands for all
+            vals, per = [tot], [per_iter]
+            break
+    value = float(np.mean(vals))
+    sample = ("%d iterations of the reference loop timed on the host (1 thread; the reference solve is "
+              "single-threaded), per-iteration %.3f s, extrapolated to %d iterations; %s" %
+              (args.cpu_sample_iters, float(np.mean(per)), iters, note))
+    line = {
+        "impl": "reference", "metric": "time-to-m-eigenpairs", "value": value, "unit": "s", "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args)},
+        "cpu_baseline": {"value": value, "unit": "s", "cores": 1,
+                         "kind": "reference" if kind == "reference" else "port", "sample": sample},
+        "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+
+    from dune_eigensolver_b200 import eigensolver as E, parallel as P
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # one torch stream carries everything: the library launches on it and torch.cuda.Event times it
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    ctx = E.Context(local, stream=tstream.cuda_stream)
+    if world > 1:
+        P.init_comm(ctx, dist)
+
+    gen = generator(args)
+    n = args.grid ** 3
+    m = E.padded_cols(args.nev)
+    plane = args.grid ** 2
+    part = P.partition_rows(n, world, align=plane)
+    r0, r1 = int(part[rank]), int(part[rank + 1])
+    rp, ci, v = gen(rows=(r0, r1)) if world > 1 else gen()
+    nnz_local = len(ci)
+    if world > 1:
+        dA = P.build_distributed_matrix(ctx, rp, ci, v, part, rank, dist)
+    else:
+        dA = E.Matrix(ctx, (rp, ci, v))
+    # the reference's start block for the GLOBAL problem; every rank keeps its own rows
+    start_full = E.from_panels(E.start_block(n, m, 123), n, m)
+    start_local = np.ascontiguousarray(start_full[r0:r1])
+    del start_full
+    Q0 = E.MultiVector(ctx, r1 - r0, m)
+    Q0.upload_rowmajor(start_local)
+    Q = E.MultiVector(ctx, r1 - r0, m)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    iters_seen = []
+
+    def step():
+        Q.copy_from(Q0)  # restore the start block (device-to-device, 8*n*m bytes, part of the step)
+        ev, it = E.standard_largest_mv(ctx, dA, 0.0, args.tol, args.maxiter, Q)
+        iters_seen.append(it)
+        return ev
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.profile(reset=True)
+    ctx.set_profiling(True)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        ev = step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile(reset=True)
+    ctx.set_profiling(False)
+    launches = ctx.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms_per_step = ms / args.steps
+    iterations = iters_seen[-1]
+
+    # ---- end to end through the reference-facing call with host buffers ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        start_panels = E.to_panels(start_local)
+        e2e_steps = max(1, min(args.steps, 3))
+
+        def e2e_step():
+            if world > 1:
+                mat = P.build_distributed_matrix(ctx, rp, ci, v, part, rank, dist)
+            else:
+                mat = E.Matrix(ctx, (rp, ci, v))
+            evl, V, it = np.zeros(args.nev), np.zeros((args.nev, r1 - r0)), E.C.c_int(0)
+            E.check(E.capi.lib().de_standard_largest(ctx._h, mat._h, 0.0, args.tol, args.maxiter, args.nev,
+                                                     E.dptr(start_panels), E.dptr(evl), E.dptr(V), 0, E.C.byref(it)),
+                    ctx._h)
+            mat.close()
+            return evl, V
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            evl, V = e2e_step()
+        barrier()
+        t_e2e = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        h2d = 8 * (len(rp) + len(ci)) + 8 * len(v) + 8 * (r1 - r0) * m  # int64 CSR + values + start block
+        d2h = 8 * (r1 - r0) * args.nev + 8 * m * iterations           # eigenvectors + m quotients per iteration
+        e2e = {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": e2e_steps, "api": "de_matrix_create_csr + de_standard_largest (host CSR in, host eigenvectors out)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: SpMM (+ fused Rayleigh-quotient dots) ----------------------------
+    peak, peak_src = peaks()
+    spmm_ms, spmm_cnt = prof["spmm"]
+    # per-launch algorithmic bytes: 12*nnz + 4*(n+1) + 16*n*m on this rank's rows
+    n_loc = r1 - r0
+    spmm_bytes = 12.0 * nnz_local + 4.0 * (n_loc + 1) + 16.0 * n_loc * m
+    launches_per_spmm = 1 if world == 1 else 2  # interior + boundary launches of a distributed SpMM
+    achieved = (spmm_bytes * (spmm_cnt / launches_per_spmm)) / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
+    total_kernel_ms = sum(val[0] for val in prof.values())
+    shares = {k: (val[0] / total_kernel_ms if total_kernel_ms > 0 else 0.0) for k, val in prof.items()}
+    gram_ms, gram_cnt = prof["gram"]
+    upd_ms, upd_cnt = prof["update"]
+    other = {
+        "gram": {"GBps": (8.0 * n_loc * m * gram_cnt) / (gram_ms * 1e-3) / 1e9 if gram_ms > 0 else 0.0,
+                 "avg_ms": gram_ms / max(gram_cnt, 1), "algorithmic_bytes": 8.0 * n_loc * m},
+        "update": {"GBps": (16.0 * n_loc * m * upd_cnt) / (upd_ms * 1e-3) / 1e9 if upd_ms > 0 else 0.0,
+                   "avg_ms": upd_ms / max(upd_cnt, 1), "algorithmic_bytes": 16.0 * n_loc * m},
+    }
+    roofline = {"bound": "hbm", "kernel": "spmm_kernel (SpMM + fused Rayleigh-quotient dots)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "avg_launch_ms": spmm_ms / max(spmm_cnt, 1),
+                "algorithmic_bytes_per_launch": spmm_bytes, "kernel_time_shares": shares, "other_kernels": other}
+
+    key = (args.grid, args.stencil, args.nev, args.tol)
+    known = ITERATIONS_TO_CONVERGENCE.get(key)
+    if known is not None and world == 1:
+        assert abs(iterations - known) <= 1, "iteration count %d drifted from the recorded %d" % (iterations, known)
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        tot, per_iter, kind = cpu_reference_sample(args, args.cpu_sample_iters, iterations)
+        cpu = {"value": tot, "unit": "s", "cores": 1, "kind": "reference" if kind == "reference" else "port",
+               "sample": "%d iterations of the reference StandardLargest loop on the host (1 thread; the reference "
+                         "solve is single-threaded), %.3f s per iteration, extrapolated to the %d iterations the "
+                         "solve needs" % (args.cpu_sample_iters, per_iter, iterations)}
+
+    line = {
+        "metric": "time-to-m-eigenpairs", "value": ms_per_step * 1e-3, "unit": "s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "iterations": iterations, "m": m,
+                   "l2": "inputs larger than L2 (matrix %.0f MB + vector blocks 2 x %.0f MB per GPU); no flush" %
+                         ((12.0 * nnz_local + 4 * n_loc) / 1e6, 8.0 * n_loc * m / 1e6),
+                   "parallelism": "row-partitioned z-slabs x%d" % world if world > 1 else "single GPU"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "eigenvalues_head": [float(x) for x in ev[:4]],
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,6 +28,8 @@ SIGNATURES = {
     "de_context_destroy": [_vp],
     "de_context_synchronize": [_vp],
     "de_context_launch_count": [_vp, _i64p],
+    "de_context_set_profiling": [_vp, C.c_int],
+    "de_context_profile": [_vp, C.c_int, _dp, _i64p, C.c_int],
     "de_comm_unique_id": [_vp],
     "de_context_init_comm": [_vp, C.c_int, C.c_int, _vp],
     "de_context_rank": [_vp, _ip, _ip],
@@ -59,6 +61,8 @@ SIGNATURES = {
     "de_factor_apply": [_vp, _vp, _vp],
     "de_factor_info": [_vp, _i64p, _i64p, _i64p, _ip, _ip],
     "de_standard_largest": [_vp, _vp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip],
+    "de_standard_largest_mv": [_vp, _vp, C.c_double, C.c_double, C.c_int, _vp, _dp, C.c_int, _ip],
+    "de_standard_inverse_mv": [_vp, _vp, _vp, C.c_double, C.c_double, C.c_int, _vp, _dp, C.c_int, _ip],
     "de_standard_inverse": [_vp, _vp, _vp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip],
     "de_generalized_inverse": [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int,
                                _ip, _dp],

@@ -100,6 +100,17 @@ struct de_context
   double *stage = nullptr;    // layout-conversion staging
   size_t stage_bytes = 0;
   long long launches = 0;
+  // optional per-kernel CUDA-event timing (bench.py's roofline numbers)
+  bool profiling = false;
+  struct ProfRecord
+  {
+    int cat;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<ProfRecord> prof_records;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[DE_PROF_CATEGORIES] = {0};
+  long long prof_count[DE_PROF_CATEGORIES] = {0};
 
   double *dG() const { return dsmall; }
   double *dR() const { return dsmall + DE_KERNEL_MAX_M * DE_KERNEL_MAX_M; }
@@ -175,6 +186,43 @@ namespace
     return code;
   }
 
+  /** brackets one kernel launch with CUDA events on the launching stream when profiling is on */
+  struct ProfScope
+  {
+    de_context *c;
+    int cat;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    static cudaEvent_t take(de_context *c)
+    {
+      cudaEvent_t e = nullptr;
+      if (!c->prof_pool.empty())
+      {
+        e = c->prof_pool.back();
+        c->prof_pool.pop_back();
+      }
+      else
+        cudaEventCreate(&e);
+      return e;
+    }
+    ProfScope(de_context *ctx, int category) : c(ctx), cat(category)
+    {
+      if (c->profiling)
+      {
+        e0 = take(c);
+        e1 = take(c);
+        cudaEventRecord(e0, c->stream);
+      }
+    }
+    ~ProfScope()
+    {
+      if (e0)
+      {
+        cudaEventRecord(e1, c->stream);
+        c->prof_records.push_back(de_context::ProfRecord{cat, e0, e1});
+      }
+    }
+  };
+
 #define DE_CUDA(ctx, call)                                                                                   \
   do                                                                                                         \
   {                                                                                                          \
@@ -243,6 +291,7 @@ namespace
   int reduce_partials(de_context *ctx, const double *partials, int nparts, int len, double *out)
   {
     dim3 block(32, 32);
+    ProfScope prof(ctx, DE_PROF_SMALL);
     de::reduce_partials_kernel<<<(len + 31) / 32, block, 0, ctx->stream>>>(partials, nparts, len, out);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
@@ -282,6 +331,7 @@ namespace
     const long long need = (nrows + rpb - 1) / rpb;
     const int cap = DOT ? kMaxPartials : ctx->sm_count * 8;
     const int grid = (int)std::min<long long>(need, cap);
+    ProfScope prof(ctx, DE_PROF_SPMM);
     switch (tpr)
     {
     case 4:
@@ -337,6 +387,7 @@ namespace
       {
         const long long total = A->n_send * (m / 2);
         const int grid = (int)std::min<long long>((total + 255) / 256, ctx->sm_count * 8);
+        ProfScope prof(ctx, DE_PROF_MISC);
         de::pack_rows_kernel<<<grid, 256, 0, ctx->stream>>>(A->n_send, A->send_rows, m, X, A->send_buf);
         DE_LAUNCH_CHECK(ctx);
       }
@@ -377,7 +428,10 @@ namespace
     dim3 block(hp, 256 / hp);
     const long long need = (n + block.y - 1) / block.y;
     const int grid = (int)std::max<long long>(1, std::min<long long>(need, kMaxPartials));
-    de::diag_dot_kernel<<<grid, block, 0, ctx->stream>>>(n, X, m, Y, m, m, ctx->partials);
+    {
+      ProfScope prof(ctx, DE_PROF_DOT);
+      de::diag_dot_kernel<<<grid, block, 0, ctx->stream>>>(n, X, m, Y, m, m, ctx->partials);
+    }
     DE_LAUNCH_CHECK(ctx);
     DE_TRY(reduce_partials(ctx, ctx->partials, grid, m, out));
     return allreduce_sum(ctx, out, m);
@@ -390,7 +444,10 @@ namespace
     using C = de::GramCfg<M, UPPER, SAME>;
     const long long ntiles = (n + C::TR - 1) / C::TR;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, kMaxPartials));
-    de::gram_kernel<M, UPPER, SAME><<<grid, C::THREADS, 0, ctx->stream>>>(n, X, ldx, Y, ldy, ctx->partials);
+    {
+      ProfScope prof(ctx, DE_PROF_GRAM);
+      de::gram_kernel<M, UPPER, SAME><<<grid, C::THREADS, 0, ctx->stream>>>(n, X, ldx, Y, ldy, ctx->partials);
+    }
     DE_LAUNCH_CHECK(ctx);
     return reduce_partials(ctx, ctx->partials, grid, M * M, out);
   }
@@ -453,6 +510,7 @@ namespace
     const long long ntiles = (n + C::TR - 1) / C::TR;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / C::SMEM_BYTES));
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * per_sm));
+    ProfScope prof(ctx, DE_PROF_UPDATE);
     de::update_kernel<M, MODE><<<grid, C::THREADS, C::SMEM_BYTES, ctx->stream>>>(n, X, ldx, R, Y, ldy, upper);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
@@ -487,6 +545,7 @@ namespace
   // ---- (B-)orthonormalisation: CholQR2 ------------------------------------------------------------------
   int chol_inverse(de_context *ctx, int m, const double *G, double *Rinv, double *info)
   {
+    ProfScope prof(ctx, DE_PROF_SMALL);
     de::chol_inverse_kernel<<<1, 256, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
@@ -630,6 +689,7 @@ namespace
     de::TrsvArgs a{S.rows, S.rowptr, S.col, S.val, S.invdiag, W, m};
     for (const TrsvSegment &seg : S.segments)
     {
+      ProfScope prof(ctx, DE_PROF_TRSV);
       if (seg.chain)
         de::trsv_chain_kernel<LC><<<1, 1024, 0, ctx->stream>>>(a, S.level_ptr, seg.a, seg.b);
       else
@@ -675,11 +735,17 @@ namespace
     DE_TRY(ensure_factor_work(ctx, F, m));
     const long long total = F->n * (m / 2);
     const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 8));
-    de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->P, F->rowscale, X, F->W, 0);
+    {
+      ProfScope prof(ctx, DE_PROF_TRSV);
+      de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->P, F->rowscale, X, F->W, 0);
+    }
     DE_LAUNCH_CHECK(ctx);
     DE_TRY(run_schedule(ctx, F->L, F->W, m));
     DE_TRY(run_schedule(ctx, F->U, F->W, m));
-    de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->Q, nullptr, F->W, Y, 1);
+    {
+      ProfScope prof(ctx, DE_PROF_TRSV);
+      de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->Q, nullptr, F->W, Y, 1);
+    }
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -704,6 +770,7 @@ namespace
     if (total == 0)
       return DE_OK;
     const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 8));
+    ProfScope prof(ctx, DE_PROF_MISC);
     de::panel8_convert_kernel<<<grid, 256, 0, ctx->stream>>>(n, m, src, dst, to_rowmajor);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
@@ -729,7 +796,10 @@ namespace
       return DE_OK;
     const size_t bytes = sizeof(double) * (size_t)n * nev;
     DE_TRY(ensure_stage(ctx, bytes));
-    de::extract_columns_kernel<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, m, nev, Q, ctx->stage);
+    {
+      ProfScope prof(ctx, DE_PROF_MISC);
+      de::extract_columns_kernel<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, m, nev, Q, ctx->stage);
+    }
     DE_LAUNCH_CHECK(ctx);
     DE_CUDA(ctx, cudaMemcpyAsync(evec, ctx->stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -830,6 +900,13 @@ extern "C"
     cudaSetDevice(ctx->device);
     if (ctx->comm && nccl_api().ok)
       nccl_api().CommDestroy(ctx->comm);
+    for (const de_context::ProfRecord &r : ctx->prof_records)
+    {
+      cudaEventDestroy(r.e0);
+      cudaEventDestroy(r.e1);
+    }
+    for (cudaEvent_t e : ctx->prof_pool)
+      cudaEventDestroy(e);
     cudaFree(ctx->partials);
     cudaFree(ctx->dsmall);
     cudaFree(ctx->dstatus);
@@ -856,6 +933,45 @@ extern "C"
       return set_error(nullptr, DE_ERR_INVALID, "null context");
     DE_TRY(bind_device(ctx));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+  }
+
+  int de_context_set_profiling(de_context *ctx, int enable)
+  {
+    if (!ctx)
+      return set_error(nullptr, DE_ERR_INVALID, "null context");
+    ctx->profiling = enable != 0;
+    return DE_OK;
+  }
+
+  int de_context_profile(de_context *ctx, int category, double *total_ms, int64_t *launches, int reset)
+  {
+    if (!ctx || category < 0 || category >= DE_PROF_CATEGORIES)
+      return set_error(ctx, DE_ERR_INVALID, "de_context_profile: bad arguments");
+    DE_TRY(bind_device(ctx));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (const de_context::ProfRecord &r : ctx->prof_records)
+    {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess)
+      {
+        ctx->prof_ms[r.cat] += ms;
+        ctx->prof_count[r.cat] += 1;
+      }
+      ctx->prof_pool.push_back(r.e0);
+      ctx->prof_pool.push_back(r.e1);
+    }
+    ctx->prof_records.clear();
+    if (total_ms)
+      *total_ms = ctx->prof_ms[category];
+    if (launches)
+      *launches = ctx->prof_count[category];
+    if (reset)
+      for (int c = 0; c < DE_PROF_CATEGORIES; ++c)
+      {
+        ctx->prof_ms[c] = 0.0;
+        ctx->prof_count[c] = 0;
+      }
     return DE_OK;
   }
 
@@ -1470,31 +1586,20 @@ extern "C"
   }
 
   // ---- drivers --------------------------------------------------------------------------------------------------
-  /** shared skeleton of StandardLargest (eigensolver.hh:28-112) and StandardInverse (:116-198).
-   *  Qa holds the orthonormal iterate (reference Q1 after the swap), Qb the block it is mapped to (reference Q2).
-   *  For the largest-eigenvalue variant the product A*Qa that the reference recomputes at the top of the loop
-   *  (:78) is the one it already formed for the Rayleigh quotients (:84) -- it is reused, bit-identically. */
-  static int standard_driver(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
-                             int maxiter, int nev, const double *start_panel8, double *eval, double *evec, int verbose,
-                             int *iterations)
+  /** shared skeleton of StandardLargest (eigensolver.hh:28-112) and StandardInverse (:116-198) on device blocks.
+   *  On entry Qa holds the start block; on exit Qa holds the orthonormal iterate (reference Q1 after the swap)
+   *  and Qb the block it was mapped to (reference Q2). For the largest-eigenvalue variant the product A*Qa that
+   *  the reference recomputes at the top of the loop (:78) is the one it already formed for the Rayleigh
+   *  quotients (:84) -- it is reused, bit-identically. */
+  static int standard_core(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
+                           int maxiter, int m, double *&Qa, double *&Qb, std::vector<double> &s2, int verbose,
+                           int *k_exit_out)
   {
-    if (!ctx || !A || !start_panel8 || !eval || !evec || nev <= 0)
-      return set_error(ctx, DE_ERR_INVALID, "standard eigensolver driver: bad arguments");
-    const int m = padded_cols(nev);
-    if (!valid_cols(m))
-      return set_error(ctx, DE_ERR_UNSUPPORTED, "standard eigensolver driver: nev exceeds DE_MAX_COLS (64)");
-    if (F && F->n != A->n)
-      return set_error(ctx, DE_ERR_INVALID, "standard eigensolver driver: factorisation does not match the matrix");
-    DE_TRY(bind_device(ctx));
     const long long n = A->n;
-    ScopedBlocks blk;
-    double *Qa, *Qb;
-    DE_TRY(blk.alloc(ctx, &Qa, (size_t)n * m));
-    DE_TRY(blk.alloc(ctx, &Qb, (size_t)n * m));
     DE_TRY(reset_status(ctx));
-    DE_TRY(upload_panel8_device(ctx, n, m, start_panel8, Qa));
-    DE_TRY(orthonormalize_device(ctx, n, m, Qa));
-    std::vector<double> s1(m, 0.0), s2(m, 0.0);
+    DE_TRY(orthonormalize_device(ctx, n, m, Qa)); // (:69, :159)
+    std::vector<double> s1(m, 0.0);
+    s2.assign(m, 0.0);
     int k_exit = std::min(1, maxiter - 1);
     bool have_product = false; // Qb == A*Qa already?
     for (int k = 1; k < maxiter; ++k)
@@ -1518,12 +1623,71 @@ extern "C"
       std::swap(s1, s2);
       std::swap(Qa, Qb); // now Qa orthonormal, Qb = A*Qa
       have_product = true;
-      if (k > 1 && distance < tol)
+      if (k > 1 && distance < tol) // absolute change of the Rayleigh quotients (:101-102, :188-189)
         break;
     }
-    if (iterations)
-      *iterations = k_exit;
+    if (k_exit_out)
+      *k_exit_out = k_exit;
+    return DE_OK;
+  }
+
+  static int standard_driver(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
+                             int maxiter, int nev, const double *start_panel8, double *eval, double *evec, int verbose,
+                             int *iterations)
+  {
+    if (!ctx || !A || !start_panel8 || !eval || !evec || nev <= 0)
+      return set_error(ctx, DE_ERR_INVALID, "standard eigensolver driver: bad arguments");
+    const int m = padded_cols(nev);
+    if (!valid_cols(m))
+      return set_error(ctx, DE_ERR_UNSUPPORTED, "standard eigensolver driver: nev exceeds DE_MAX_COLS (64)");
+    if (F && F->n != A->n)
+      return set_error(ctx, DE_ERR_INVALID, "standard eigensolver driver: factorisation does not match the matrix");
+    DE_TRY(bind_device(ctx));
+    const long long n = A->n;
+    ScopedBlocks blk;
+    double *Qa, *Qb;
+    DE_TRY(blk.alloc(ctx, &Qa, (size_t)n * m));
+    DE_TRY(blk.alloc(ctx, &Qb, (size_t)n * m));
+    DE_TRY(upload_panel8_device(ctx, n, m, start_panel8, Qa));
+    std::vector<double> s2;
+    DE_TRY(standard_core(ctx, A, F, shift, tol, maxiter, m, Qa, Qb, s2, verbose, iterations));
     return copy_out(ctx, n, m, nev, Qa, s2, eval, evec);
+  }
+
+  /** device-resident variant: Q holds the start block on entry and the eigenvector block on return */
+  static int standard_driver_mv(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
+                                int maxiter, de_mv *Q, double *eval_m, int verbose, int *iterations)
+  {
+    if (!ctx || !A || !Q || !eval_m)
+      return set_error(ctx, DE_ERR_INVALID, "standard eigensolver driver: bad arguments");
+    if (Q->n != A->n || (F && F->n != A->n))
+      return set_error(ctx, DE_ERR_INVALID, "standard eigensolver driver: block / factorisation do not match the matrix");
+    DE_TRY(bind_device(ctx));
+    double *Qa = Q->d, *Qb = nullptr;
+    DE_TRY(dev_alloc(ctx, &Qb, (size_t)Q->n * Q->m));
+    std::vector<double> s2;
+    int s = standard_core(ctx, A, F, shift, tol, maxiter, Q->m, Qa, Qb, s2, verbose, iterations);
+    Q->d = Qa; // the buffers may have swapped roles; Q keeps the one with the result
+    cudaFree(Qb);
+    if (s != DE_OK)
+      return s;
+    for (int j = 0; j < Q->m; ++j)
+      eval_m[j] = s2[j];
+    return DE_OK;
+  }
+
+  int de_standard_largest_mv(de_context *ctx, const de_matrix *A, double shift, double tol, int maxiter, de_mv *Q,
+                             double *eval_m, int verbose, int *iterations)
+  {
+    return standard_driver_mv(ctx, A, nullptr, shift, tol, maxiter, Q, eval_m, verbose, iterations);
+  }
+
+  int de_standard_inverse_mv(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
+                             int maxiter, de_mv *Q, double *eval_m, int verbose, int *iterations)
+  {
+    if (!F)
+      return set_error(ctx, DE_ERR_INVALID, "de_standard_inverse_mv: factorisation is null");
+    return standard_driver_mv(ctx, A, F, shift, tol, maxiter, Q, eval_m, verbose, iterations);
   }
 
   int de_standard_largest(de_context *ctx, const de_matrix *A, double shift, double tol, int maxiter, int nev,

@@ -66,6 +66,20 @@ class Context:
         check(capi.lib().de_context_launch_count(self._h, C.byref(c)), self._h)
         return c.value
 
+    def set_profiling(self, on=True):
+        check(capi.lib().de_context_set_profiling(self._h, int(on)), self._h)
+
+    def profile(self, reset=False):
+        """{category: (total_ms, launches)} of the per-kernel CUDA-event timers (synchronises the stream)."""
+        names = ["spmm", "gram", "update", "small", "dot", "trsv", "misc"]
+        out = {}
+        for c, name in enumerate(names):
+            ms, cnt = C.c_double(0.0), C.c_int64(0)
+            last = c == len(names) - 1
+            check(capi.lib().de_context_profile(self._h, c, C.byref(ms), C.byref(cnt), int(reset and last)), self._h)
+            out[name] = (ms.value, cnt.value)
+        return out
+
     def init_comm(self, rank, nranks, unique_id):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
         check(capi.lib().de_context_init_comm(self._h, rank, nranks, buf), self._h)
@@ -357,6 +371,22 @@ def StandardLargest(ctx, A, shift, tol, maxiter, nev, verbose=0, seed=123, start
     finally:
         dA.close()
     return Result(ev, V, it.value)
+
+
+def standard_largest_mv(ctx, dA, shift, tol, maxiter, Q, verbose=0):
+    """Device-resident StandardLargest: Q (MultiVector) holds the start block on entry, the eigenvector block on
+    return. Returns (eval[m], iterations)."""
+    ev, it = np.zeros(Q.m), C.c_int(0)
+    check(capi.lib().de_standard_largest_mv(ctx._h, dA._h, shift, tol, maxiter, Q._h, dptr(ev), verbose, C.byref(it)),
+          ctx._h)
+    return ev, it.value
+
+
+def standard_inverse_mv(ctx, dA, dF, shift, tol, maxiter, Q, verbose=0):
+    ev, it = np.zeros(Q.m), C.c_int(0)
+    check(capi.lib().de_standard_inverse_mv(ctx._h, dA._h, dF._h, shift, tol, maxiter, Q._h, dptr(ev), verbose,
+                                            C.byref(it)), ctx._h)
+    return ev, it.value
 
 
 def StandardInverse(ctx, A, shift, tol, maxiter, nev, verbose=0, seed=123, start=None, ordering=1):

@@ -56,6 +56,19 @@ int de_context_destroy(de_context *ctx);
 int de_context_synchronize(de_context *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int de_context_launch_count(const de_context *ctx, int64_t *count);
+/* Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
+ * de_context_profile synchronises, folds the pending events into per-category totals and returns one category;
+ * reset != 0 clears all categories afterwards. */
+#define DE_PROF_SPMM 0    /* spmm_kernel (with or without the fused diag-dot) */
+#define DE_PROF_GRAM 1    /* gram_kernel */
+#define DE_PROF_UPDATE 2  /* update_kernel */
+#define DE_PROF_SMALL 3   /* reduce_partials_kernel, chol_inverse_kernel */
+#define DE_PROF_DOT 4     /* diag_dot_kernel */
+#define DE_PROF_TRSV 5    /* permute / level / chain kernels of the factored apply */
+#define DE_PROF_MISC 6    /* layout conversion, halo pack, eigenvector extraction */
+#define DE_PROF_CATEGORIES 7
+int de_context_set_profiling(de_context *ctx, int enable);
+int de_context_profile(de_context *ctx, int category, double *total_ms, int64_t *launches, int reset);
 
 /* Multi-GPU (new; the reference is single-threaded): one process per GPU. Rank 0 obtains an
  * id with de_comm_unique_id (128 bytes), the host distributes it (torch.distributed / MPI), every rank calls
@@ -156,6 +169,13 @@ int de_factor_info(const de_factor *F, int64_t *n, int64_t *lnz, int64_t *unz, i
 /* replaces StandardLargest (eigensolver.hh:28-112) */
 int de_standard_largest(de_context *ctx, const de_matrix *A, double shift, double tol, int maxiter, int nev,
                         const double *start_panel8, double *eval, double *evec, int verbose, int *iterations);
+/* device-resident variants of the two drivers above: Q holds the n x m start block on entry and the eigenvector
+ * block on return (all m columns), eval_m receives m Rayleigh quotients; nothing but the m convergence values
+ * per iteration crosses PCIe. Used when the caller keeps its blocks on the GPU (and by bench.py's `value`). */
+int de_standard_largest_mv(de_context *ctx, const de_matrix *A, double shift, double tol, int maxiter, de_mv *Q,
+                           double *eval_m, int verbose, int *iterations);
+int de_standard_inverse_mv(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
+                           int maxiter, de_mv *Q, double *eval_m, int verbose, int *iterations);
 /* replaces StandardInverse (eigensolver.hh:116-198); F = factorisation of the shifted A */
 int de_standard_inverse(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
                         int maxiter, int nev, const double *start_panel8, double *eval, double *evec, int verbose,

@@ -28,7 +28,8 @@ def to_panels(X):
     X = np.ascontiguousarray(X, dtype=np.float64)
     n, m = X.shape
     assert m % 8 == 0
-    return np.ascontiguousarray(X.reshape(n, m // 8, 8).transpose(1, 0, 2)).reshape(-1)
+    # always a fresh buffer: for m == 8 the two layouts coincide and the reference clobbers some inputs
+    return np.array(X.reshape(n, m // 8, 8).transpose(1, 0, 2), order="C", copy=True).reshape(-1)
 
 
 def from_panels(p, n, m):
