@@ -1,0 +1,180 @@
+#ifndef DUNE_EIGENSOLVER_B200_EIGENSOLVER_HH
+#define DUNE_EIGENSOLVER_B200_EIGENSOLVER_HH
+
+/** \file
+ *  Drop-in for the reference's dune/eigensolver/eigensolver.hh: the three block-eigensolver drivers keep their
+ *  signatures, parameter meaning, side effects and exceptions, and run their iteration loop on a B200 through the
+ *  C ABI (dune_eigensolver_b200.h). What stays on the host is exactly what the reference does outside its kernels:
+ *
+ *    - the random start block: std::mt19937{seed} + std::normal_distribution, filled panel -> row -> column
+ *      (reference eigensolver.hh:50-55, :138-143, :232-237) -- generated HERE, in the caller's translation unit,
+ *      so it is the same libstdc++ stream the caller's reference build would produce
+ *    - the shift A += shift*I applied IN PLACE to the caller's matrix for the Standard* drivers (:57-66, :145-153),
+ *      and A = inA + shift*B + reg*I on a COPY for GeneralizedInverse (:208, :241-252)
+ *    - the one-time sparse factorisation (UMFPackFactorizedMatrix)
+ *    - the convergence decision on the m Rayleigh quotients each iteration (inside the library, on the host)
+ *
+ *  Differences from the reference, all deliberate: no address printing from MultiVector; the duplicate SpMM at
+ *  the top of the StandardLargest loop (:78 recomputes what :84 produced) is elided; orthonormalisation is
+ *  CholQR2 over the whole block instead of panel-wise Gram-Schmidt (same unique triangular factor).
+ */
+
+#include <algorithm>
+#include <cmath>
+#include <iostream>
+#include <random>
+#include <stdexcept>
+#include <vector>
+
+#include "b200_runtime.hh"
+#include "kernels_b200.hh"
+#include "multivector.hh"
+#include "umfpacktools.hh"
+
+namespace de_b200
+{
+  inline std::size_t padded_columns(int nev, int b) { return (nev / b + std::min(nev % b, 1)) * b; }
+
+  //! the reference's start block, in MultiVector storage order
+  inline MultiVector<double, 8> random_start_block(std::size_t n, std::size_t m, unsigned int seed)
+  {
+    MultiVector<double, 8> Q1{n, m};
+    std::mt19937 urbg{seed};
+    std::normal_distribution<double> generator{0.0, 1.0};
+    for (std::size_t bj = 0; bj < Q1.cols(); bj += 8)
+      for (std::size_t i = 0; i < Q1.rows(); ++i)
+        for (std::size_t j = 0; j < 8; ++j)
+          Q1(i, bj + j) = generator(urbg);
+    return Q1;
+  }
+
+  template <class ISTLM>
+  inline void add_to_diagonal(ISTLM &A, double value)
+  {
+    using block_type = typename ISTLM::block_type;
+    for (auto row = A.begin(); row != A.end(); ++row)
+      for (auto entry = row->begin(); entry != row->end(); ++entry)
+        if (row.index() == entry.index())
+          for (int i = 0; i < block_type::rows; ++i)
+            (*entry)[i][i] += value;
+  }
+
+  template <class ISTLM>
+  inline void require_square_blocks(const char *who)
+  {
+    using block_type = typename ISTLM::block_type;
+    if (block_type::rows != block_type::cols)
+      throw std::invalid_argument(std::string(who) + ": blocks of input matrix must be square");
+  }
+
+  template <class VEC>
+  inline void scatter_results(int nev, std::size_t n, const std::vector<double> &values,
+                              const std::vector<double> &vectors, std::vector<double> &eval, std::vector<VEC> &evec)
+  {
+    for (int j = 0; j < nev; ++j)
+      eval[j] = values[j];
+    for (int j = 0; j < nev; ++j)
+      for (std::size_t i = 0; i < n; ++i)
+        evec[j][i] = vectors[(std::size_t)j * n + i];
+  }
+} // namespace de_b200
+
+/** \brief largest eigenvalues of a standard eigenproblem by orthogonal (subspace) iteration
+ *  (reference StandardLargest, eigensolver.hh:28-112). eval / evec must be pre-sized by the caller. */
+template <typename ISTLM, typename VEC>
+void StandardLargest(ISTLM &A, double shift, double tol, int maxiter, int nev, std::vector<double> &eval,
+                     std::vector<VEC> &evec, int verbose = 0, unsigned int seed = 123)
+{
+  de_b200::require_square_blocks<ISTLM>("StandardLargest");
+  de_b200::require_scalar_blocks<ISTLM>("matmul_sparse_tallskinny_blocked");
+  const std::size_t n = A.N();
+  const std::size_t m = de_b200::padded_columns(nev, 8);
+  MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
+  if (shift != 0.0)
+    de_b200::add_to_diagonal(A, shift); // overwrites the caller's matrix, like the reference
+
+  auto &ctx = de_b200::Context::thread_default();
+  de_b200::DeviceMatrix dA(ctx, A);
+  std::vector<double> values(nev), vectors((std::size_t)nev * n);
+  int iterations = 0;
+  de_b200::check(de_standard_largest(ctx.get(), dA.get(), shift, tol, maxiter, nev, start.data(), values.data(),
+                                     vectors.data(), verbose, &iterations),
+                 ctx.get());
+  de_b200::scatter_results(nev, n, values, vectors, eval, evec);
+}
+
+/** \brief smallest eigenvalues of a standard eigenproblem by shift-invert subspace iteration
+ *  (reference StandardInverse, eigensolver.hh:116-198). */
+template <typename ISTLM, typename VEC>
+void StandardInverse(ISTLM &A, double shift, double tol, int maxiter, int nev, std::vector<double> &eval,
+                     std::vector<VEC> &evec, int verbose = 0, unsigned int seed = 123)
+{
+  de_b200::require_square_blocks<ISTLM>("StandardInverse");
+  de_b200::require_scalar_blocks<ISTLM>("matmul_sparse_tallskinny_blocked");
+  const std::size_t n = A.N();
+  const std::size_t m = de_b200::padded_columns(nev, 8);
+  MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
+  if (shift != 0.0)
+    de_b200::add_to_diagonal(A, shift);
+  UMFPackFactorizedMatrix<ISTLM> F(A, 1);
+
+  auto &ctx = de_b200::Context::thread_default();
+  de_b200::DeviceMatrix dA(ctx, A);
+  de_factor *dF = nullptr;
+  de_b200::check(de_factor_upload(ctx.get(), F.n, F.Lp, F.Lj, F.Lx, F.Up, F.Ui, F.Ux, F.P, F.Q, F.Rs, F.do_recip, &dF),
+                 ctx.get());
+  std::vector<double> values(nev), vectors((std::size_t)nev * n);
+  int iterations = 0;
+  const int status = de_standard_inverse(ctx.get(), dA.get(), dF, shift, tol, maxiter, nev, start.data(),
+                                         values.data(), vectors.data(), verbose, &iterations);
+  de_factor_destroy(dF);
+  de_b200::check(status, ctx.get());
+  de_b200::scatter_results(nev, n, values, vectors, eval, evec);
+}
+
+/** \brief smallest eigenvalues of A x = lambda B x by shift-invert subspace iteration with B-orthonormalisation
+ *  (reference GeneralizedInverse, eigensolver.hh:204-351). pattern(B) must be contained in pattern(A).
+ *  eval / evec are resized like the reference does (:328-341). */
+template <typename ISTLM, typename VEC>
+void GeneralizedInverse(const ISTLM &inA, const ISTLM &B, double shift, double reg, double tol, int maxiter, int nev,
+                        std::vector<double> &eval, std::vector<VEC> &evec, int verbose = 0, unsigned int seed = 123)
+{
+  ISTLM A(inA); // the driver works on a copy
+  de_b200::require_square_blocks<ISTLM>("StandardInverse"); // sic: the reference reuses this text (:218)
+  de_b200::require_scalar_blocks<ISTLM>("B_orthonormalize_blocked");
+  const std::size_t n = A.N();
+  const std::size_t m = de_b200::padded_columns(nev, 8);
+  MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
+  if (shift != 0.0)
+    A.axpy(shift, B);
+  if (reg != 0.0)
+    de_b200::add_to_diagonal(A, reg);
+  UMFPackFactorizedMatrix<ISTLM> F(A, std::max(0, verbose - 1));
+
+  auto &ctx = de_b200::Context::thread_default();
+  de_b200::DeviceMatrix dA(ctx, A), dB(ctx, B);
+  de_factor *dF = nullptr;
+  de_b200::check(de_factor_upload(ctx.get(), F.n, F.Lp, F.Lj, F.Lx, F.Up, F.Ui, F.Ux, F.P, F.Q, F.Rs, F.do_recip, &dF),
+                 ctx.get());
+  std::vector<double> values(nev), vectors((std::size_t)nev * n);
+  int iterations = 0;
+  double relerror = 0.0;
+  const int status = de_generalized_inverse(ctx.get(), dA.get(), dB.get(), dF, shift, tol, maxiter, nev, start.data(),
+                                            values.data(), vectors.data(), verbose, &iterations, &relerror);
+  de_factor_destroy(dF);
+  de_b200::check(status, ctx.get());
+
+  if (eval.size() != (std::size_t)nev)
+    eval.resize(nev);
+  if (evec.size() != (std::size_t)nev)
+    evec.resize(nev);
+  for (int j = 0; j < nev; ++j)
+    if (evec[j].size() != n)
+      evec[j].resize(n);
+  de_b200::scatter_results(nev, n, values, vectors, eval, evec);
+  if (verbose > 0) // the reference's machine-greppable summary line (:344-350)
+    std::cout << "GeneralizedInverse: "
+              << " iterations=" << iterations << " relerror=" << relerror << std::endl;
+}
+
+#endif

@@ -1,0 +1,124 @@
+// Test program for the C++ drop-in headers (include/dune/eigensolver/*.hh): the same source a DUNE user would
+// write against the reference's eigensolver.hh, compiled against this repo's headers + libdune_eigensolver_b200.so.
+// The matrix type is the minimal BCRSMatrix stand-in from oracle/shim (test infrastructure; real dune-istl at a
+// user's site). Prints results as "key value..." lines that tests/test_cpp_dropin.py compares with the oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include <dune/common/fmatrix.hh>
+#include <dune/istl/bcrsmatrix.hh>
+
+#include <dune/eigensolver/eigensolver.hh>
+
+using Block = Dune::FieldMatrix<double, 1, 1>;
+using Matrix = Dune::BCRSMatrix<Block>;
+
+// 2D 5-point matrices of the reference's driver (reference src/dune-eigensolver.cc:98-143)
+static Matrix laplacian(int N, const char *kind, int overlap)
+{
+  std::vector<long> ptr(1, 0), col;
+  std::vector<double> val;
+  auto pu = [&](int x, int y) { return (x < overlap || x > N - 1 - overlap || y < overlap || y > N - 1 - overlap) ? 0.0 : 1.0; };
+  for (int y = 0; y < N; ++y)
+    for (int x = 0; x < N; ++x)
+    {
+      const int nb = (y > 0) + (x > 0) + (x < N - 1) + (y < N - 1);
+      auto put = [&](int xx, int yy, double v) {
+        if (!std::strcmp(kind, "B"))
+          v *= pu(x, y) * pu(xx, yy);
+        col.push_back(yy * N + xx);
+        val.push_back(v);
+      };
+      const double diag = !std::strcmp(kind, "neumann") ? (double)nb : 4.0;
+      if (y > 0) put(x, y - 1, -1.0);
+      if (x > 0) put(x - 1, y, -1.0);
+      put(x, y, diag);
+      if (x < N - 1) put(x + 1, y, -1.0);
+      if (y < N - 1) put(x, y + 1, -1.0);
+      ptr.push_back((long)col.size());
+    }
+  return Matrix((std::size_t)N * N, (std::size_t)N * N, ptr.data(), col.data(), val.data());
+}
+
+static void print(const char *key, const std::vector<double> &v)
+{
+  std::printf("%s", key);
+  for (double x : v)
+    std::printf(" %.17g", x);
+  std::printf("\n");
+}
+
+int main(int argc, char **argv)
+{
+  const std::string mode = argc > 1 ? argv[1] : "largest";
+  const int N = argc > 2 ? std::atoi(argv[2]) : 12;
+  const int nev = argc > 3 ? std::atoi(argv[3]) : 8;
+  const double tol = argc > 4 ? std::atof(argv[4]) : 1e-10;
+  const std::size_t n = (std::size_t)N * N;
+  try
+  {
+    std::vector<double> eval(nev);
+    std::vector<std::vector<double>> evec(nev, std::vector<double>(n));
+    if (mode == "largest")
+    {
+      Matrix A = laplacian(N, "dirichlet", 0);
+      StandardLargest(A, 0.0, tol, 4000, nev, eval, evec, 0, 123);
+    }
+    else if (mode == "inverse")
+    {
+      Matrix A = laplacian(N, "dirichlet", 0);
+      StandardInverse(A, 1e-3, tol, 4000, nev, eval, evec, 0, 123);
+      // the caller's matrix was shifted in place (reference eigensolver.hh:145-153)
+      std::printf("diag0 %.17g\n", (double)(*(A.begin()->begin())));
+    }
+    else if (mode == "generalized")
+    {
+      Matrix A = laplacian(N, "neumann", 0), B = laplacian(N, "B", 3);
+      std::vector<double> ev;
+      std::vector<std::vector<double>> V;
+      GeneralizedInverse(A, B, 1e-3, 0.0, tol, 4000, nev, ev, V, 1, 123);
+      eval = ev;
+      evec = V;
+    }
+    else if (mode == "kernels")
+    {
+      Matrix A = laplacian(N, "dirichlet", 0);
+      MultiVector<double, 8> X = de_b200::random_start_block(n, 16, 123), Y{n, 16};
+      matmul_sparse_tallskinny_blocked(Y, A, X);
+      std::vector<double> dp;
+      dot_products_diagonal_blocked(dp, X, Y);
+      print("diagdot", dp);
+      orthonormalize_blocked(X);
+      std::vector<std::vector<double>> G = dot_products_diagonal(X);
+      double off = 0.0;
+      for (std::size_t i = 0; i < 16; ++i)
+        for (std::size_t j = 0; j < 16; ++j)
+          off = std::max(off, std::abs(G[i][j] - (i == j ? 1.0 : 0.0)));
+      std::printf("ortho_defect %.3e\n", off);
+      try
+      {
+        MultiVector<double, 8> bad{n, 12};
+      }
+      catch (const std::invalid_argument &e)
+      {
+        std::printf("caught %s\n", e.what());
+      }
+      return 0;
+    }
+    print("eval", eval);
+    std::vector<double> head;
+    for (int j = 0; j < nev; ++j)
+      head.push_back(evec[j][0]);
+    print("evec_row0", head);
+  }
+  catch (const std::exception &e)
+  {
+    std::printf("exception %s\n", e.what());
+    return 3;
+  }
+  return 0;
+}

@@ -1,0 +1,86 @@
+"""The C++ drop-in headers (include/dune/eigensolver/*.hh) compile as a user's translation unit against a
+BCRSMatrix-like type, and (on the GPU) reproduce the oracle's eigenvalues through the reference's own signatures."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from dune_eigensolver_b200 import build as B, matrices as M
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "dropin_test")
+
+
+def build_exe():
+    lib = B.build_library()
+    src = os.path.join(ROOT, "tests", "cpp", "dropin_main.cc")
+    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(lib)):
+        return EXE
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++17", "-O2", "-march=x86-64-v3", "-I", os.path.join(ROOT, "include"), "-I",
+           os.path.join(ROOT, "oracle", "shim"), src, "-o", EXE, lib, "-Wl,-rpath," + os.path.dirname(lib)]
+    metis = B.METIS
+    if os.path.exists(metis):
+        cmd += ["-DDE_B200_HAVE_METIS", metis]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return EXE
+
+
+def run(*args):
+    out = subprocess.run([build_exe(), *[str(a) for a in args]], capture_output=True, text=True, timeout=300)
+    vals = {}
+    for line in out.stdout.splitlines():
+        k, _, rest = line.partition(" ")
+        vals.setdefault(k, rest)
+    return out.returncode, vals, out.stdout
+
+
+def test_dropin_headers_compile_and_fail_loudly_without_gpu():
+    exe = build_exe()
+    assert os.path.exists(exe)
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        rc, vals, text = run("largest", 8, 8)
+        assert rc == 3 and "no CPU fallback" in text
+
+
+@pytest.mark.gpu
+def test_dropin_drivers_match_oracle(oracle):
+    rc, vals, text = run("largest", 20, 8, 1e-10)
+    assert rc == 0, text
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    ref, V, k = oracle.standard_largest(M.laplacian_dirichlet_2d(20), 0.0, 1e-10, 4000, 8)
+    assert np.abs(ev - ref).max() <= 1e-10 * np.abs(ref).max()
+
+    rc, vals, text = run("inverse", 20, 8, 1e-10)
+    assert rc == 0, text
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    ref, V, k = oracle.standard_inverse(M.laplacian_dirichlet_2d(20), 1e-3, 1e-10, 4000, 8)
+    assert np.abs(ev - ref).max() <= 1e-10 * np.abs(ref).max()
+    assert abs(float(vals["diag0"]) - 4.001) < 1e-15  # caller's matrix shifted in place
+
+    rc, vals, text = run("generalized", 16, 8, 1e-12)
+    assert rc == 0, text
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    ref, V, it = oracle.generalized_inverse(M.laplacian_neumann_2d(16), M.laplacian_B_2d(16, 3), 1e-3, 0.0, 1e-12, 4000, 8)
+    assert np.abs(ev - ref).max() <= 1e-10 * np.abs(ref).max()
+    assert "iterations=%d" % it in text or "iterations=%d" % (it + 1) in text or "iterations=%d" % (it - 1) in text
+
+
+@pytest.mark.gpu
+def test_dropin_kernels(oracle):
+    rc, vals, text = run("kernels", 12, 8)
+    assert rc == 0, text
+    A = M.laplacian_dirichlet_2d(12)
+    X = oracle.start_block(144, 16, 123)
+    ref = oracle.diag_dot(X, oracle.spmm(A, X))
+    dp = np.array([float(x) for x in vals["diagdot"].split()])
+    assert np.abs(dp - ref).max() <= 1e-12 * np.abs(ref).max()
+    assert float(vals["ortho_defect"]) < 1e-13
+    assert "number of cols must be a multiple of block size" in vals["caught"]

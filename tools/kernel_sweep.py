@@ -43,7 +43,7 @@ def main():
     for m in [int(c) for c in args.cols.split(",")]:
         rng = np.random.default_rng(m)
         X = E.MultiVector(ctx, n, m)
-        X.upload_rowmajor(np.tile(rng.standard_normal((n, 8)), (1, m // 8)) + 0.01 * np.arange(m))
+        X.upload_rowmajor(rng.standard_normal((n, m)))
         Y = E.MultiVector(ctx, n, m)
         R = np.triu(rng.standard_normal((m, m))) / m + np.eye(m)
         bytes_ = {
