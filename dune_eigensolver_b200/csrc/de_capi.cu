@@ -24,6 +24,7 @@
 #include "../../include/dune/eigensolver/sparse_lu.hh"
 #include "kernels_dense.cuh"
 #include "kernels_sparse.cuh"
+#include "kernels_tallskinny.cuh"
 #include "kernels_trsv.cuh"
 
 // ====================================================================================================
@@ -95,6 +96,7 @@ struct de_context
   double *partials = nullptr; // kPartialDoubles
   double *dsmall = nullptr;   // kSmall doubles: G | Rinv | dp | info
   int *dstatus = nullptr;     // sticky Cholesky status
+  int *dflags = nullptr;      // device flag: second CholQR sweep not needed
   double *hsmall = nullptr;   // pinned mirror of dsmall
   int *hstatus = nullptr;     // pinned
   double *stage = nullptr;    // layout-conversion staging
@@ -332,21 +334,48 @@ namespace
     const int cap = DOT ? kMaxPartials : ctx->sm_count * 8;
     const int grid = (int)std::min<long long>(need, cap);
     ProfScope prof(ctx, DE_PROF_SPMM);
-    switch (tpr)
+    const bool exact = (m == 2 * tpr) && ((A->n + A->n_halo) * (long long)(m / 2) < (1LL << 31));
+    const bool halo = A->n_halo > 0;
+    if (exact)
     {
-    case 4:
-      de::spmm_kernel<4, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
-      break;
-    case 8:
-      de::spmm_kernel<8, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
-      break;
-    case 16:
-      de::spmm_kernel<16, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
-      break;
-    default:
-      de::spmm_kernel<32, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
-      break;
+#define DE_SPMM_V2(T)                                                                                        \
+  if (halo)                                                                                                  \
+    de::spmm_kernel_v2<T, DOT, true><<<grid, 256, 0, ctx->stream>>>(a);                                      \
+  else                                                                                                       \
+    de::spmm_kernel_v2<T, DOT, false><<<grid, 256, 0, ctx->stream>>>(a);
+      switch (tpr)
+      {
+      case 4:
+        DE_SPMM_V2(4)
+        break;
+      case 8:
+        DE_SPMM_V2(8)
+        break;
+      case 16:
+        DE_SPMM_V2(16)
+        break;
+      default:
+        DE_SPMM_V2(32)
+        break;
+      }
+#undef DE_SPMM_V2
     }
+    else
+      switch (tpr)
+      {
+      case 4:
+        de::spmm_kernel<4, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+        break;
+      case 8:
+        de::spmm_kernel<8, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+        break;
+      case 16:
+        de::spmm_kernel<16, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+        break;
+      default:
+        de::spmm_kernel<32, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+        break;
+      }
     DE_LAUNCH_CHECK(ctx);
     *grid_out = grid;
     return DE_OK;
@@ -437,6 +466,52 @@ namespace
     return allreduce_sum(ctx, out, m);
   }
 
+  // ---- pipelined tall-skinny kernel (m = 8/16/32/64) -------------------------------------------------------
+  inline bool ts_supported(int w) { return w == 8 || w == 16 || w == 32 || w == 64; }
+
+  template <int M, bool DO_UPDATE, bool DO_GRAM, bool UPPER, bool SAME>
+  int launch_ts_t(de_context *ctx, de::TsArgs a, double *gram_out)
+  {
+    constexpr int NOPS = (DO_GRAM && !SAME) ? 2 : 1;
+    using C = de::TsCfg<M, UPPER, NOPS>;
+    constexpr size_t smem = de::tall_skinny_smem_bytes<M, DO_UPDATE, DO_GRAM, UPPER, SAME>();
+    static bool configured = false;
+    if (!configured)
+    {
+      DE_CUDA(ctx, cudaFuncSetAttribute(de::tall_skinny_kernel<M, DO_UPDATE, DO_GRAM, UPPER, SAME>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    const long long ntiles = (a.n + C::TR - 1) / C::TR;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, ctx->sm_count));
+    a.partials = ctx->partials;
+    {
+      ProfScope prof(ctx, DO_UPDATE ? DE_PROF_UPDATE : DE_PROF_GRAM);
+      de::tall_skinny_kernel<M, DO_UPDATE, DO_GRAM, UPPER, SAME><<<grid, C::THREADS, smem, ctx->stream>>>(a);
+    }
+    DE_LAUNCH_CHECK(ctx);
+    if (DO_GRAM)
+      DE_TRY(reduce_partials(ctx, ctx->partials, grid, M * M, gram_out));
+    return DE_OK;
+  }
+
+  template <bool DO_UPDATE, bool DO_GRAM, bool UPPER, bool SAME>
+  int launch_ts(de_context *ctx, int w, const de::TsArgs &a, double *gram_out)
+  {
+    switch (w)
+    {
+    case 8:
+      return launch_ts_t<8, DO_UPDATE, DO_GRAM, UPPER, SAME>(ctx, a, gram_out);
+    case 16:
+      return launch_ts_t<16, DO_UPDATE, DO_GRAM, UPPER, SAME>(ctx, a, gram_out);
+    case 32:
+      return launch_ts_t<32, DO_UPDATE, DO_GRAM, UPPER, SAME>(ctx, a, gram_out);
+    case 64:
+      return launch_ts_t<64, DO_UPDATE, DO_GRAM, UPPER, SAME>(ctx, a, gram_out);
+    }
+    return set_error(ctx, DE_ERR_UNSUPPORTED, "pipelined tall-skinny kernel: unsupported width");
+  }
+
   // ---- Gram -------------------------------------------------------------------------------------------
   template <int M, bool UPPER, bool SAME>
   int launch_gram_t(de_context *ctx, long long n, const double *X, int ldx, const double *Y, int ldy, double *out)
@@ -483,6 +558,24 @@ namespace
                   bool symmetric, double *out)
   {
     const bool same = (X == Y && ldx == ldy);
+    if (ts_supported(w))
+    {
+      de::TsArgs a{};
+      a.n = n;
+      a.X = X;
+      a.ldx = ldx;
+      a.Y = Y;
+      a.ldy = ldy;
+      if (symmetric && same)
+        DE_TRY((launch_ts<false, true, true, true>(ctx, w, a, out)));
+      else if (symmetric)
+        DE_TRY((launch_ts<false, true, true, false>(ctx, w, a, out)));
+      else if (same)
+        DE_TRY((launch_ts<false, true, false, true>(ctx, w, a, out)));
+      else
+        DE_TRY((launch_ts<false, true, false, false>(ctx, w, a, out)));
+      return allreduce_sum(ctx, out, (size_t)w * w);
+    }
     if (symmetric && same)
       DE_TRY((launch_gram_m<true, true>(ctx, w, n, X, ldx, Y, ldy, out)));
     else if (symmetric)
@@ -518,8 +611,21 @@ namespace
 
   template <int MODE>
   int update_device(de_context *ctx, int w, long long n, const double *X, int ldx, const double *R, double *Y, int ldy,
-                    int upper)
+                    int upper, const int *skip_flag = nullptr)
   {
+    if (MODE == 0 && ts_supported(w))
+    {
+      de::TsArgs a{};
+      a.n = n;
+      a.X = X;
+      a.ldx = ldx;
+      a.R = R;
+      a.Out = Y;
+      a.ldo = ldy;
+      a.upper = upper;
+      a.skip_flag = skip_flag;
+      return launch_ts<true, false, false, true>(ctx, w, a, nullptr);
+    }
     switch (w)
     {
     case 8:
@@ -543,10 +649,10 @@ namespace
   }
 
   // ---- (B-)orthonormalisation: CholQR2 ------------------------------------------------------------------
-  int chol_inverse(de_context *ctx, int m, const double *G, double *Rinv, double *info)
+  int chol_inverse(de_context *ctx, int m, const double *G, double *Rinv, double *info, int *identity_flag = nullptr)
   {
     ProfScope prof(ctx, DE_PROF_SMALL);
-    de::chol_inverse_kernel<<<1, 256, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info);
+    de::chol_inverse_kernel<<<1, 256, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -557,6 +663,25 @@ namespace
    *  Gram-Schmidt up to round-off; the second sweep restores orthogonality to O(eps) for cond(X) < ~1e7. */
   int orthonormalize_device(de_context *ctx, long long n, int m, double *X)
   {
+    if (ts_supported(m))
+    {
+      // sweep 1: G = X^T X ; R1 = chol(G) ; X <- X R1^-1 fused with G2 = X^T X of the result
+      DE_TRY(gram_device(ctx, m, n, X, m, X, m, true, ctx->dG()));
+      DE_TRY(chol_inverse(ctx, m, ctx->dG(), ctx->dR(), nullptr, nullptr));
+      de::TsArgs a{};
+      a.n = n;
+      a.X = X;
+      a.ldx = m;
+      a.R = ctx->dR();
+      a.Out = X;
+      a.ldo = m;
+      a.upper = 1;
+      DE_TRY((launch_ts<true, true, true, true>(ctx, m, a, ctx->dG())));
+      DE_TRY(allreduce_sum(ctx, ctx->dG(), (size_t)m * m));
+      // sweep 2: R2 = chol(G2) ; X <- X R2^-1, skipped on the device when G2 = I to working precision
+      DE_TRY(chol_inverse(ctx, m, ctx->dG(), ctx->dR(), nullptr, ctx->dflags));
+      return update_device<0>(ctx, m, n, X, m, ctx->dR(), X, m, 1, ctx->dflags);
+    }
     for (int sweep = 0; sweep < 2; ++sweep)
     {
       DE_TRY(gram_device(ctx, m, n, X, m, X, m, true, ctx->dG()));
@@ -881,6 +1006,8 @@ extern "C"
               cudaMalloc((void **)&ctx->partials, kPartialDoubles * sizeof(double)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->dsmall, kSmall * sizeof(double)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->dstatus, sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->dflags, 4 * sizeof(int)) == cudaSuccess &&
+              cudaMemset(ctx->dflags, 0, 4 * sizeof(int)) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->hsmall, kSmall * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->hstatus, sizeof(int)) == cudaSuccess &&
               cudaMemset(ctx->dstatus, 0, sizeof(int)) == cudaSuccess;
@@ -910,6 +1037,7 @@ extern "C"
     cudaFree(ctx->partials);
     cudaFree(ctx->dsmall);
     cudaFree(ctx->dstatus);
+    cudaFree(ctx->dflags);
     cudaFree(ctx->stage);
     if (ctx->hsmall)
       cudaFreeHost(ctx->hsmall);

@@ -251,10 +251,12 @@ namespace de
   /** G = R^T R (R upper, positive diagonal), Rinv = R^-1 (upper). Only the upper triangle of G is read.
    *  This is the L D L^T / U = L^-T D^-1/2 construction of kernels_cpp.hh:247-291, :468-512 for the whole block.
    *  status[0] (sticky) = 1 + index of the first pivot that is non-finite or not above 4 m eps G(k,k); untouched on success.
-   *  info[0] (optional) = largest strict-upper entry of G (the `norm` diagnostic of kernels_cpp.hh:464-466). */
+   *  info[0] (optional) = largest strict-upper entry of G (the `norm` diagnostic of kernels_cpp.hh:464-466).
+   *  identity_flag[0] (optional) = 1 if max |G - I| <= 1e-14: lets the second CholQR sweep's update skip itself. */
   __global__ void __launch_bounds__(256) chol_inverse_kernel(int m, const double *__restrict__ G,
                                                              double *__restrict__ Rinv, int *__restrict__ status,
-                                                             double *__restrict__ info)
+                                                             double *__restrict__ info,
+                                                             int *__restrict__ identity_flag)
   {
     // upper triangle + diagonal: R ; strict lower triangle: (R^-1)^T ; dinv: diagonal of R^-1
     __shared__ double A[DE_KERNEL_MAX_M][DE_KERNEL_MAX_M + 1];
@@ -265,7 +267,7 @@ namespace de
     const int tid = threadIdx.x;
     if (tid == 0)
       bad = 0;
-    double mx = -1.0e300;
+    double mx = -1.0e300, dev = 0.0; // dev: max |G - I| over the upper triangle
     for (int e = tid; e < m * m; e += blockDim.x)
     {
       const int i = e / m, j = e % m;
@@ -275,6 +277,22 @@ namespace de
         dorig[i] = v;
       if (i < j)
         mx = fmax(mx, v);
+      if (i <= j)
+        dev = fmax(dev, fabs(v - (i == j ? 1.0 : 0.0)));
+    }
+    if (identity_flag != nullptr)
+    {
+      // G equals I to working precision: the factor is I and the following update would change nothing
+      red[tid] = dev;
+      __syncthreads();
+      if (tid == 0)
+      {
+        double t = 0.0;
+        for (int q = 0; q < (int)blockDim.x; ++q)
+          t = fmax(t, red[q]);
+        identity_flag[0] = (t <= 1.0e-14) ? 1 : 0; // also false for NaN
+      }
+      __syncthreads();
     }
     red[tid] = mx;
     __syncthreads();

@@ -152,6 +152,86 @@ namespace de
     }
   }
 
+  /** Second-generation SpMM for m = 2*TPR exactly (m = 8/16/32/64). Same mapping as spmm_kernel (TPR lanes own the
+   *  m columns of a row as double2 pairs; CSR-order FMA accumulation), but built around what ncu showed for the first
+   *  version (profiles/r01_ncu_kernels_baseline.csv: 28 warp instructions per nonzero, issue slots 49 % busy,
+   *  no memory unit saturated): 32-bit element offsets instead of 64-bit address arithmetic, the halo select
+   *  compiled out for single-GPU matrices, no per-column predicates, and nonzeros consumed in predicated chunks
+   *  of 8 so that 8 independent X-row gathers are in flight per thread (the whole 7-point row, a third of a
+   *  27-point row) instead of 4 followed by a serial tail. */
+  template <int TPR, bool DOT, bool HALO>
+  __global__ void __launch_bounds__(256, 3) spmm_kernel_v2(const SpmmArgs a)
+  {
+    constexpr int RPB = 256 / TPR;
+    constexpr int CH = 8;
+    const int t = threadIdx.x % TPR;
+    const int rslot = threadIdx.x / TPR;
+    const unsigned ldh = (unsigned)TPR; // double2 elements per row
+    const double2 *__restrict__ Xv = reinterpret_cast<const double2 *>(a.X) + t;
+    const double2 *__restrict__ Hv = reinterpret_cast<const double2 *>(a.H) + t;
+    double2 *__restrict__ Yv = reinterpret_cast<double2 *>(a.Y) + t;
+    const int n_owned = (int)a.n_owned;
+    double2 dacc = make_double2(0.0, 0.0);
+
+    for (long long r = (long long)blockIdx.x * RPB + rslot; r < a.nrows; r += (long long)gridDim.x * RPB)
+    {
+      const int row = a.rowlist ? a.rowlist[r] : (int)r;
+      const int kbeg = __ldg(a.rowptr + row), kend = __ldg(a.rowptr + row + 1);
+      double2 acc = make_double2(0.0, 0.0);
+      const int klast = kend - 1;
+      for (int k = kbeg; k < kend; k += CH)
+      {
+        // Slots past the end of the row re-read the row's last nonzero with a zero coefficient: every load is
+        // unpredicated, so all 8 index/value loads and then all 8 X-row gathers issue back to back.
+        int j[CH];
+        double av[CH];
+        double2 xv[CH];
+#pragma unroll
+        for (int u = 0; u < CH; ++u)
+        {
+          const int kk = min(k + u, klast);
+          j[u] = __ldg(a.col + kk);
+          av[u] = __ldg(a.val + kk);
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u)
+        {
+          if (HALO)
+            xv[u] = __ldg((j[u] < n_owned) ? Xv + (unsigned)j[u] * ldh : Hv + (unsigned)(j[u] - n_owned) * ldh);
+          else
+            xv[u] = __ldg(Xv + (unsigned)j[u] * ldh);
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u)
+          fma2(acc, (k + u <= klast) ? av[u] : 0.0, xv[u]);
+      }
+      Yv[(unsigned)row * ldh] = acc;
+      if (DOT)
+      {
+        const double2 z = __ldg(Xv + (unsigned)row * ldh);
+        dacc.x = fma(z.x, acc.x, dacc.x);
+        dacc.y = fma(z.y, acc.y, dacc.y);
+      }
+    }
+
+    if (DOT)
+    {
+      __shared__ double2 red[256];
+      red[threadIdx.x] = dacc;
+      __syncthreads();
+      if (rslot == 0)
+      {
+        double2 s = make_double2(0.0, 0.0);
+        for (int q = 0; q < RPB; ++q) // fixed order: deterministic
+        {
+          s.x += red[q * TPR + t].x;
+          s.y += red[q * TPR + t].y;
+        }
+        st2(a.partials + (size_t)blockIdx.x * a.m + 2 * t, s);
+      }
+    }
+  }
+
   /** dp[j] = sum_i X(i,j) Y(i,j) (reference dot_products_diagonal_blocked, kernels_cpp.hh:24-55).
    *  blockDim = (m/2, 256/(m/2)): x indexes a column pair, y a row lane; rows are strided over the grid.
    *  Leaves one partial vector per CTA. */

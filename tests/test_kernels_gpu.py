@@ -138,6 +138,24 @@ def test_orthonormalize_matches_oracle(ctx, oracle, n, m):
     assert np.all(np.diag(Rf) > 0)
 
 
+@pytest.mark.parametrize("m", [8, 16, 32, 64])
+@pytest.mark.parametrize("cond", [1.0, 1e3, 1e6])
+def test_orthonormalize_conditioning(ctx, oracle, m, cond):
+    """CholQR2 across conditioning regimes: cond = 1 exercises the device-side skip of the second sweep (the fused
+    Gram of the first sweep is already I), cond = 1e6 needs the second sweep to restore orthogonality."""
+    n = 20011
+    rng = np.random.default_rng(m)
+    Q0, _ = np.linalg.qr(rng.standard_normal((n, m)))
+    T = np.triu(rng.standard_normal((m, m)), 1) * 0.1 + np.diag(np.logspace(0, -np.log10(cond), m))
+    X = Q0 @ T if cond > 1.0 else Q0
+    dX = E.MultiVector.from_array(ctx, X)
+    E.orthonormalize_blocked(dX)
+    Q = dX.download()
+    assert np.abs(Q.T @ Q - np.eye(m)).max() <= 5e-14
+    ref = oracle.orthonormalize(X)
+    assert np.abs(Q - ref).max() <= 1e-10 * max(cond, 1.0)
+
+
 def test_orthonormalize_golden_and_rank_deficient(ctx, golden):
     dX = E.MultiVector.from_array(ctx, golden["k_X"])
     E.orthonormalize_blocked(dX)
