@@ -258,7 +258,7 @@ def run_b200(args):
         step()
     barrier()
     ctx.profile(reset=True)
-    ctx.set_profiling(True)
+    ctx.set_profiling(os.environ.get("DE_BENCH_NOPROF", "") == "")
     launches0 = ctx.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:

@@ -332,12 +332,14 @@ namespace
     const int rpb = 256 / tpr;
     const long long need = (nrows + rpb - 1) / rpb;
     const int cap = DOT ? kMaxPartials : ctx->sm_count * 8;
-    const int grid = (int)std::min<long long>(need, cap);
+    int grid = (int)std::min<long long>(need, cap);
     ProfScope prof(ctx, DE_PROF_SPMM);
     const bool exact = (m == 2 * tpr) && ((A->n + A->n_halo) * (long long)(m / 2) < (1LL << 31));
     const bool halo = A->n_halo > 0;
     if (exact)
     {
+      // spmm_kernel_v2 is compiled for 3 resident CTAs per SM: launch exactly one wave of the grid-stride loop
+      grid = (int)std::min<long long>(need, (long long)ctx->sm_count * 3);
 #define DE_SPMM_V2(T)                                                                                        \
   if (halo)                                                                                                  \
     de::spmm_kernel_v2<T, DOT, true><<<grid, 256, 0, ctx->stream>>>(a);                                      \
@@ -1069,6 +1071,17 @@ extern "C"
     if (!ctx)
       return set_error(nullptr, DE_ERR_INVALID, "null context");
     ctx->profiling = enable != 0;
+    if (ctx->profiling)
+    {
+      // events are created up front so that no cudaEventCreate happens inside a timed region
+      DE_TRY(bind_device(ctx));
+      while (ctx->prof_pool.size() < 16384)
+      {
+        cudaEvent_t e = nullptr;
+        DE_CUDA(ctx, cudaEventCreate(&e));
+        ctx->prof_pool.push_back(e);
+      }
+    }
     return DE_OK;
   }
 

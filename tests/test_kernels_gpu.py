@@ -146,8 +146,8 @@ def test_orthonormalize_conditioning(ctx, oracle, m, cond):
     n = 20011
     rng = np.random.default_rng(m)
     Q0, _ = np.linalg.qr(rng.standard_normal((n, m)))
-    T = np.triu(rng.standard_normal((m, m)), 1) * 0.1 + np.diag(np.logspace(0, -np.log10(cond), m))
-    X = Q0 @ T if cond > 1.0 else Q0
+    V, _ = np.linalg.qr(rng.standard_normal((m, m)))
+    X = (Q0 * np.logspace(0, -np.log10(cond), m)) @ V.T if cond > 1.0 else Q0  # singular values 1 .. 1/cond
     dX = E.MultiVector.from_array(ctx, X)
     E.orthonormalize_blocked(dX)
     Q = dX.download()
