@@ -8,8 +8,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
-#include <climits>
-#include <cstdint>
 #include <cstring>
 #include <dlfcn.h>
 #include <new>
@@ -130,29 +128,6 @@ struct de_mv
   double *d;
 };
 
-/** "RG4" row-group form of a CSR matrix (kernels_sparse.cuh, spmm_rg4_kernel) */
-struct RowGroups
-{
-  bool valid = false;
-  int ngroups = 0;
-  long long nunion = 0;
-  int *grow = nullptr, *gptr = nullptr, *gvptr = nullptr;
-  unsigned *gcm = nullptr;
-  double *gval = nullptr;
-  void release()
-  {
-    cudaFree(grow);
-    cudaFree(gptr);
-    cudaFree(gvptr);
-    cudaFree(gcm);
-    cudaFree(gval);
-    grow = gptr = gvptr = nullptr;
-    gcm = nullptr;
-    gval = nullptr;
-    valid = false;
-  }
-};
-
 struct de_matrix
 {
   de_context *ctx;
@@ -169,7 +144,6 @@ struct de_matrix
   long long n_interior = 0, n_boundary = 0;
   double *send_buf = nullptr, *halo_buf = nullptr;
   int buf_m = 0;
-  RowGroups rg_all, rg_interior, rg_boundary;
 };
 
 struct TrsvSegment
@@ -409,169 +383,6 @@ namespace
     return DE_OK;
   }
 
-  /** Host construction of the RG4 form for the rows `rowlist[0..nlist)` (or 0..nlist-1 when rowlist is null):
-   *  groups of four rows, 4-way merge of their ascending column lists into union columns with a 4-bit row mask,
-   *  values packed in (column, row) order. Rows whose columns are not ascending are sorted on a copy. A matrix
-   *  with duplicate entries or >= 2^28 local columns keeps the CSR kernels (valid stays false). */
-  int build_rowgroups(de_context *ctx, long long nlist, const int *rowlist, const int64_t *rowptr, const int64_t *col,
-                      const double *val, long long ncols_local, RowGroups &out)
-  {
-    out.valid = false;
-    if (nlist <= 0 || ncols_local >= (1LL << 28))
-      return DE_OK;
-    const long long ng = (nlist + 3) / 4;
-    if (ng >= (1LL << 31) - 1)
-      return DE_OK;
-    std::vector<int> grow((size_t)ng * 4, -1), gptr((size_t)ng + 1, 0), gvptr((size_t)ng + 1, 0);
-    std::vector<unsigned> gcm;
-    std::vector<double> gval;
-    long long total = 0;
-    for (long long i = 0; i < nlist; ++i)
-    {
-      const long long r = rowlist ? rowlist[i] : i;
-      total += rowptr[r + 1] - rowptr[r];
-    }
-    gcm.reserve((size_t)(total / 2 + 16));
-    gval.reserve((size_t)total);
-    std::vector<std::pair<int64_t, double>> sorted[4];
-    for (long long g = 0; g < ng; ++g)
-    {
-      const int64_t *cptr[4];
-      const double *vptr[4];
-      int64_t len[4], pos[4];
-      for (int q = 0; q < 4; ++q)
-      {
-        const long long i = 4 * g + q;
-        len[q] = pos[q] = 0;
-        cptr[q] = nullptr;
-        vptr[q] = nullptr;
-        if (i >= nlist)
-          continue;
-        const long long r = rowlist ? rowlist[i] : i;
-        grow[(size_t)4 * g + q] = (int)r;
-        const int64_t b = rowptr[r], e = rowptr[r + 1];
-        len[q] = e - b;
-        cptr[q] = col + b;
-        vptr[q] = val + b;
-        bool ascending = true;
-        for (int64_t k = b + 1; k < e && ascending; ++k)
-          ascending = col[k] > col[k - 1];
-        if (!ascending)
-        {
-          sorted[q].clear();
-          for (int64_t k = b; k < e; ++k)
-            sorted[q].emplace_back(col[k], val[k]);
-          std::stable_sort(sorted[q].begin(), sorted[q].end(),
-                           [](const std::pair<int64_t, double> &x, const std::pair<int64_t, double> &y) { return x.first < y.first; });
-          for (size_t k = 1; k < sorted[q].size(); ++k)
-            if (sorted[q][k].first == sorted[q][k - 1].first)
-              return DE_OK; // duplicate entries: keep CSR
-          // point the merge at the sorted copy through two scratch arrays
-          static thread_local std::vector<int64_t> sc[4];
-          static thread_local std::vector<double> sv[4];
-          sc[q].resize(sorted[q].size());
-          sv[q].resize(sorted[q].size());
-          for (size_t k = 0; k < sorted[q].size(); ++k)
-          {
-            sc[q][k] = sorted[q][k].first;
-            sv[q][k] = sorted[q][k].second;
-          }
-          cptr[q] = sc[q].data();
-          vptr[q] = sv[q].data();
-        }
-      }
-      for (;;)
-      {
-        int64_t c = INT64_MAX;
-        for (int q = 0; q < 4; ++q)
-          if (pos[q] < len[q] && cptr[q][pos[q]] < c)
-            c = cptr[q][pos[q]];
-        if (c == INT64_MAX)
-          break;
-        unsigned mask = 0;
-        for (int q = 0; q < 4; ++q)
-          if (pos[q] < len[q] && cptr[q][pos[q]] == c)
-          {
-            mask |= 1u << q;
-            gval.push_back(vptr[q][pos[q]]);
-            ++pos[q];
-          }
-        gcm.push_back((unsigned)c | (mask << 28));
-      }
-      if (gcm.size() >= (size_t)1 << 31 || gval.size() >= (size_t)1 << 31)
-        return DE_OK;
-      gptr[(size_t)g + 1] = (int)gcm.size();
-      gvptr[(size_t)g + 1] = (int)gval.size();
-    }
-    out.ngroups = (int)ng;
-    out.nunion = (long long)gcm.size();
-    DE_TRY(upload_converted(ctx, &out.grow, grow.data(), grow.size()));
-    DE_TRY(upload_converted(ctx, &out.gptr, gptr.data(), gptr.size()));
-    DE_TRY(upload_converted(ctx, &out.gvptr, gvptr.data(), gvptr.size()));
-    DE_TRY(upload_converted(ctx, &out.gcm, gcm.data(), gcm.size()));
-    DE_TRY(upload_converted(ctx, &out.gval, gval.data(), gval.size()));
-    out.valid = true;
-    return DE_OK;
-  }
-
-  template <bool DOT>
-  int launch_spmm_rg(de_context *ctx, const de_matrix *A, const RowGroups &rg, bool identity_rows, const double *X,
-                     double *Y, int m, double *partials, int *grid_out)
-  {
-    *grid_out = 0;
-    if (rg.ngroups <= 0)
-      return DE_OK;
-    de::RgArgs a;
-    a.ngroups = rg.ngroups;
-    a.grow = identity_rows ? nullptr : rg.grow;
-    a.n_rows = (int)A->n;
-    a.gptr = rg.gptr;
-    a.gcm = rg.gcm;
-    a.gvptr = rg.gvptr;
-    a.gval = rg.gval;
-    a.X = X;
-    a.H = A->halo_buf;
-    a.n_owned = (int)A->n;
-    a.m = m;
-    a.Y = Y;
-    a.partials = partials;
-    const int tpr = m / 2;
-    const int gpb = 256 / tpr;
-    const long long need = ((long long)rg.ngroups + gpb - 1) / gpb;
-    const int grid = (int)std::min<long long>(need, (long long)ctx->sm_count * 2); // 2 resident CTAs per SM
-    const bool halo = A->n_halo > 0;
-    ProfScope prof(ctx, DE_PROF_SPMM);
-#define DE_SPMM_RG(T)                                                                                        \
-  if (halo)                                                                                                  \
-    de::spmm_rg4_kernel<T, DOT, true><<<grid, 256, 0, ctx->stream>>>(a);                                     \
-  else                                                                                                       \
-    de::spmm_rg4_kernel<T, DOT, false><<<grid, 256, 0, ctx->stream>>>(a);
-    switch (tpr)
-    {
-    case 4:
-      DE_SPMM_RG(4)
-      break;
-    case 8:
-      DE_SPMM_RG(8)
-      break;
-    case 16:
-      DE_SPMM_RG(16)
-      break;
-    default:
-      DE_SPMM_RG(32)
-      break;
-    }
-#undef DE_SPMM_RG
-    DE_LAUNCH_CHECK(ctx);
-    *grid_out = grid;
-    return DE_OK;
-  }
-
-  inline bool rg_usable(const de_matrix *A, int m)
-  {
-    return (m == 8 || m == 16 || m == 32 || m == 64) && (A->n + A->n_halo) * (long long)(m / 2) < (1LL << 31);
-  }
-
   int ensure_halo_buffers(de_context *ctx, de_matrix *A, int m)
   {
     if (A->buf_m >= m)
@@ -598,10 +409,7 @@ namespace
     const bool dist = ctx->nranks > 1 && (A->n_halo > 0 || A->n_send > 0);
     if (!dist)
     {
-      if (A->rg_all.valid && rg_usable(A, m))
-        DE_TRY(launch_spmm_rg<DOT>(ctx, A, A->rg_all, true, X, Y, m, ctx->partials, &g1));
-      else
-        DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, nullptr, A->n, ctx->partials, &g1));
+      DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, nullptr, A->n, ctx->partials, &g1));
     }
     else
     {
@@ -629,17 +437,9 @@ namespace
       }
       DE_NCCL(ctx, nc.GroupEnd());
       DE_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
-      const bool rg = rg_usable(A, m) && (A->rg_interior.valid || A->n_interior == 0) &&
-                      (A->rg_boundary.valid || A->n_boundary == 0);
-      if (rg)
-        DE_TRY(launch_spmm_rg<DOT>(ctx, A, A->rg_interior, false, X, Y, m, ctx->partials, &g1));
-      else
-        DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->interior, A->n_interior, ctx->partials, &g1));
+      DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->interior, A->n_interior, ctx->partials, &g1));
       DE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
-      if (rg)
-        DE_TRY(launch_spmm_rg<DOT>(ctx, A, A->rg_boundary, false, X, Y, m, ctx->partials + (size_t)g1 * m, &g2));
-      else
-        DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->boundary, A->n_boundary, ctx->partials + (size_t)g1 * m, &g2));
+      DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->boundary, A->n_boundary, ctx->partials + (size_t)g1 * m, &g2));
     }
     if (DOT)
     {
@@ -1394,8 +1194,6 @@ extern "C"
     de_matrix *A = new de_matrix();
     A->ctx = ctx;
     int s = matrix_upload(ctx, n, n, nnz, rowptr, col, val, A);
-    if (s == DE_OK)
-      s = build_rowgroups(ctx, n, nullptr, rowptr, col, val, n, A->rg_all);
     if (s != DE_OK)
     {
       de_matrix_destroy(A);
@@ -1462,12 +1260,6 @@ extern "C"
       return fail(s);
     if ((s = upload_converted(ctx, &A->boundary, bd.data(), bd.size())) != DE_OK)
       return fail(s);
-    if ((s = build_rowgroups(ctx, (long long)in.size(), in.data(), rowptr, col_local, val, n_owned + n_halo,
-                             A->rg_interior)) != DE_OK)
-      return fail(s);
-    if ((s = build_rowgroups(ctx, (long long)bd.size(), bd.data(), rowptr, col_local, val, n_owned + n_halo,
-                             A->rg_boundary)) != DE_OK)
-      return fail(s);
     *out = A;
     return DE_OK;
   }
@@ -1485,9 +1277,6 @@ extern "C"
     cudaFree(A->boundary);
     cudaFree(A->send_buf);
     cudaFree(A->halo_buf);
-    A->rg_all.release();
-    A->rg_interior.release();
-    A->rg_boundary.release();
     delete A;
     return DE_OK;
   }

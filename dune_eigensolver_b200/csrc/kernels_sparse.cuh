@@ -232,138 +232,6 @@ namespace de
     }
   }
 
-  // ------------------------------------------------------------------------------------------------
-  // Row-group SpMM ("RG4"): register-level reuse of X rows across 4 neighbouring matrix rows
-  // ------------------------------------------------------------------------------------------------
-  // ncu on spmm_kernel_v2 (profiles/r01_ncu_kernels_v2.csv): for the 27-point stencil at m = 32 the kernel is bound
-  // by L1 wavefronts -- every nonzero pulls a full 8m-byte X row through the 128 B/clk L1 pipe (6.9 KB per matrix
-  // row against 0.83 KB of HBM traffic) -- and for the 7-point stencil by the three dependent memory latencies per
-  // row (rowptr -> col/val -> X). Both are cured by letting one thread group own FOUR matrix rows: the union of
-  // their column indices is walked once, each X row is loaded once into registers and fused into up to four
-  // accumulators. Neighbouring rows of a stencil share most columns (27-point: 54 distinct columns for 108
-  // nonzeros), so L1 traffic halves and the dependent chain is paid once per four rows.
-  //
-  // Format (built on the host at matrix creation): for group g the union columns
-  // cm[gptr[g] .. gptr[g+1]) ascending, each a 28-bit local column index plus a 4-bit mask of the rows that have
-  // an entry there, and the nonzero values packed in (column, row) order starting at gvptr[g]. 8 bytes per nonzero
-  // + 4 bytes per union column: never more than CSR's 12 bytes per nonzero. Per row the accumulation order is
-  // still ascending column order, i.e. bit-identical to the CSR kernels and to the CPU loop (kernels_cpp.hh:644-655).
-  struct RgArgs
-  {
-    int ngroups;
-    const int *grow;        // optional: 4 row indices per group (-1 = padding); null: rows 4g .. 4g+3 (< n_rows)
-    int n_rows;
-    const int *gptr;
-    const unsigned *gcm;    // column | mask << 28
-    const int *gvptr;
-    const double *gval;
-    const double *X;
-    const double *H;
-    int n_owned;
-    int m;
-    double *Y;
-    double *partials;       // DOT: [gridDim.x][m]
-  };
-
-  template <int TPR, bool DOT, bool HALO>
-  __global__ void __launch_bounds__(256, 2) spmm_rg4_kernel(const RgArgs a)
-  {
-    constexpr int GPB = 256 / TPR; // row groups per CTA step
-    constexpr int CH = 8;
-    const int t = threadIdx.x % TPR;
-    const int gslot = threadIdx.x / TPR;
-    const unsigned ldh = (unsigned)TPR;
-    const double2 *__restrict__ Xv = reinterpret_cast<const double2 *>(a.X) + t;
-    const double2 *__restrict__ Hv = reinterpret_cast<const double2 *>(a.H) + t;
-    double2 *__restrict__ Yv = reinterpret_cast<double2 *>(a.Y) + t;
-    double2 dacc = make_double2(0.0, 0.0);
-
-    for (int g = blockIdx.x * GPB + gslot; g < a.ngroups; g += gridDim.x * GPB)
-    {
-      const int kbeg = __ldg(a.gptr + g), kend = __ldg(a.gptr + g + 1);
-      int p = __ldg(a.gvptr + g);
-      const int klast = kend - 1;
-      double2 acc[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        acc[r] = make_double2(0.0, 0.0);
-
-      for (int k = kbeg; k < kend; k += CH)
-      {
-        unsigned cm[CH];
-        double2 xv[CH];
-#pragma unroll
-        for (int u = 0; u < CH; ++u)
-        {
-          cm[u] = __ldg(a.gcm + min(k + u, klast));
-          if (k + u > klast)
-            cm[u] &= 0x0FFFFFFFu; // slot past the end: valid column, empty mask
-        }
-#pragma unroll
-        for (int u = 0; u < CH; ++u)
-        {
-          const int j = (int)(cm[u] & 0x0FFFFFFFu);
-          if (HALO)
-            xv[u] = __ldg((j < a.n_owned) ? Xv + (unsigned)j * ldh : Hv + (unsigned)(j - a.n_owned) * ldh);
-          else
-            xv[u] = __ldg(Xv + (unsigned)j * ldh);
-        }
-        // packed values: position = running count of mask bits
-        double v[CH][4];
-#pragma unroll
-        for (int u = 0; u < CH; ++u)
-        {
-          const unsigned mask = cm[u] >> 28;
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-          {
-            const bool on = (mask >> r) & 1u;
-            v[u][r] = on ? __ldg(a.gval + p + __popc(mask & ((1u << r) - 1u))) : 0.0;
-          }
-          p += __popc(mask);
-        }
-#pragma unroll
-        for (int u = 0; u < CH; ++u)
-#pragma unroll
-          for (int r = 0; r < 4; ++r)
-            if ((cm[u] >> (28 + r)) & 1u)
-              fma2(acc[r], v[u][r], xv[u]);
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-      {
-        const int row = a.grow ? __ldg(a.grow + 4 * g + r) : ((4 * g + r < a.n_rows) ? 4 * g + r : -1);
-        if (row >= 0)
-        {
-          Yv[(unsigned)row * ldh] = acc[r];
-          if (DOT)
-          {
-            const double2 z = __ldg(Xv + (unsigned)row * ldh);
-            dacc.x = fma(z.x, acc[r].x, dacc.x);
-            dacc.y = fma(z.y, acc[r].y, dacc.y);
-          }
-        }
-      }
-    }
-
-    if (DOT)
-    {
-      __shared__ double2 red[256];
-      red[threadIdx.x] = dacc;
-      __syncthreads();
-      if (gslot == 0)
-      {
-        double2 s = make_double2(0.0, 0.0);
-        for (int q = 0; q < GPB; ++q)
-        {
-          s.x += red[q * TPR + t].x;
-          s.y += red[q * TPR + t].y;
-        }
-        st2(a.partials + (size_t)blockIdx.x * a.m + 2 * t, s);
-      }
-    }
-  }
-
   /** dp[j] = sum_i X(i,j) Y(i,j) (reference dot_products_diagonal_blocked, kernels_cpp.hh:24-55).
    *  blockDim = (m/2, 256/(m/2)): x indexes a column pair, y a row lane; rows are strided over the grid.
    *  Leaves one partial vector per CTA. */
