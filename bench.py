@@ -93,14 +93,23 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        """start polling and wait until nvidia-smi has initialised (its start-up stalls the driver for ~0.1 s,
+        which must not fall into the timed region)"""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:
+                time.sleep(0.05)
+            self.skip = len(self.lines)  # samples taken before the timed region
         except Exception:
             self.proc = None
+
+    def mark(self):
+        self.skip = len(self.lines)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -117,7 +126,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "skip", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -254,15 +263,17 @@ def run_b200(args):
         iters_seen.append(it)
         return ev
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     ctx.profile(reset=True)
     ctx.set_profiling(os.environ.get("DE_BENCH_NOPROF", "") == "")
     launches0 = ctx.launch_count()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()

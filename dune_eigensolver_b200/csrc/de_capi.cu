@@ -128,6 +128,32 @@ struct de_mv
   double *d;
 };
 
+/** a set of rows prepared for spmm_staged_kernel: CSR (possibly a row-permuted copy) + row-block metadata */
+struct StagedRows
+{
+  bool valid = false;
+  bool owns_csr = false;
+  int nblocks = 0;
+  int *rowptr = nullptr, *col = nullptr, *rowmap = nullptr;
+  double *val = nullptr;
+  int4 *blk_meta = nullptr;
+  void release()
+  {
+    if (owns_csr)
+    {
+      cudaFree(rowptr);
+      cudaFree(col);
+      cudaFree(val);
+    }
+    cudaFree(rowmap);
+    cudaFree(blk_meta);
+    rowptr = col = rowmap = nullptr;
+    val = nullptr;
+    blk_meta = nullptr;
+    valid = false;
+  }
+};
+
 struct de_matrix
 {
   de_context *ctx;
@@ -144,6 +170,7 @@ struct de_matrix
   long long n_interior = 0, n_boundary = 0;
   double *send_buf = nullptr, *halo_buf = nullptr;
   int buf_m = 0;
+  StagedRows st_all, st_interior, st_boundary;
 };
 
 struct TrsvSegment
@@ -277,7 +304,7 @@ namespace
     std::vector<T> tmp(count);
     for (size_t i = 0; i < count; ++i)
       tmp[i] = (T)src[i];
-    DE_TRY(dev_alloc(ctx, dst, count));
+    DE_TRY(dev_alloc(ctx, dst, count + 16 / sizeof(T))); // 16 bytes of tail padding: staged kernels copy 16-byte chunks
     DE_CUDA(ctx, cudaMemcpyAsync(*dst, tmp.data(), count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // tmp dies here
     return DE_OK;
@@ -383,6 +410,142 @@ namespace
     return DE_OK;
   }
 
+  /** cut rows 0..nrows of a (host) row pointer into blocks of <= 256 rows and <= 2048 nonzeros */
+  template <class Ptr>
+  std::vector<int4> cut_row_blocks(long long nrows, const Ptr *rowptr)
+  {
+    std::vector<int4> meta;
+    long long r0 = 0;
+    while (r0 < nrows)
+    {
+      long long r1 = r0;
+      while (r1 < nrows && r1 - r0 < de::kStageMaxRows && (long long)(rowptr[r1 + 1] - rowptr[r0]) <= de::kStageCapNnz)
+        ++r1;
+      if (r1 == r0)
+        r1 = r0 + 1; // a single row longer than the staging capacity: read directly from global memory
+      meta.push_back(make_int4((int)r0, (int)r1, (int)rowptr[r0], (int)rowptr[r1]));
+      r0 = r1;
+    }
+    return meta;
+  }
+
+  /** staged view of the whole matrix (shares the CSR arrays already on the device) */
+  int build_staged_all(de_context *ctx, de_matrix *A, const int64_t *rowptr)
+  {
+    std::vector<int4> meta = cut_row_blocks(A->n, rowptr);
+    StagedRows &S = A->st_all;
+    S.rowptr = A->rowptr;
+    S.col = A->col;
+    S.val = A->val;
+    S.owns_csr = false;
+    S.nblocks = (int)meta.size();
+    DE_TRY(dev_alloc(ctx, &S.blk_meta, meta.size()));
+    DE_CUDA(ctx, cudaMemcpyAsync(S.blk_meta, meta.data(), meta.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    S.valid = true;
+    return DE_OK;
+  }
+
+  /** staged copy of the rows in `list` (interior or boundary rows of a distributed matrix), permuted to be contiguous */
+  int build_staged_subset(de_context *ctx, const std::vector<int> &list, const int64_t *rowptr, const int64_t *col,
+                          const double *val, StagedRows &S)
+  {
+    S.valid = false;
+    if (list.empty())
+      return DE_OK;
+    std::vector<int> ptr(list.size() + 1, 0), c;
+    std::vector<double> v;
+    for (size_t i = 0; i < list.size(); ++i)
+    {
+      const int r = list[i];
+      for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
+      {
+        c.push_back((int)col[k]);
+        v.push_back(val[k]);
+      }
+      ptr[i + 1] = (int)c.size();
+    }
+    std::vector<int4> meta = cut_row_blocks((long long)list.size(), ptr.data());
+    S.owns_csr = true;
+    S.nblocks = (int)meta.size();
+    DE_TRY(upload_converted(ctx, &S.rowptr, ptr.data(), ptr.size()));
+    DE_TRY(upload_converted(ctx, &S.col, c.data(), c.size()));
+    DE_TRY(upload_converted(ctx, &S.val, v.data(), v.size()));
+    DE_TRY(upload_converted(ctx, &S.rowmap, list.data(), list.size()));
+    DE_TRY(dev_alloc(ctx, &S.blk_meta, meta.size()));
+    DE_CUDA(ctx, cudaMemcpyAsync(S.blk_meta, meta.data(), meta.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    S.valid = true;
+    return DE_OK;
+  }
+
+  inline bool staged_usable(const de_matrix *A, int m)
+  {
+    return (m == 8 || m == 16 || m == 32 || m == 64) && (A->n + A->n_halo) * (long long)(m / 2) < (1LL << 31);
+  }
+
+  template <bool DOT>
+  int launch_spmm_staged(de_context *ctx, const de_matrix *A, const StagedRows &S, const double *X, double *Y, int m,
+                         double *partials, int *grid_out)
+  {
+    *grid_out = 0;
+    if (!S.valid || S.nblocks <= 0)
+      return DE_OK;
+    de::StagedArgs a;
+    a.nblocks = S.nblocks;
+    a.blk_meta = S.blk_meta;
+    a.rowmap = S.rowmap;
+    a.rowptr = S.rowptr;
+    a.col = S.col;
+    a.val = S.val;
+    a.X = X;
+    a.H = A->halo_buf;
+    a.n_owned = (int)A->n;
+    a.m = m;
+    a.Y = Y;
+    a.partials = partials;
+    constexpr size_t smem = de::spmm_staged_smem_bytes();
+    const int grid = std::min(S.nblocks, ctx->sm_count * 3); // 3 resident CTAs per SM
+    const bool halo = A->n_halo > 0;
+    const int tpr = m / 2;
+    ProfScope prof(ctx, DE_PROF_SPMM);
+#define DE_SPMM_ST(T)                                                                                        \
+  {                                                                                                          \
+    static bool cfg = false;                                                                                 \
+    if (!cfg)                                                                                                \
+    {                                                                                                        \
+      DE_CUDA(ctx, cudaFuncSetAttribute(de::spmm_staged_kernel<T, DOT, true>,                                \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      DE_CUDA(ctx, cudaFuncSetAttribute(de::spmm_staged_kernel<T, DOT, false>,                               \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      cfg = true;                                                                                            \
+    }                                                                                                        \
+    if (halo)                                                                                                \
+      de::spmm_staged_kernel<T, DOT, true><<<grid, 256, smem, ctx->stream>>>(a);                             \
+    else                                                                                                     \
+      de::spmm_staged_kernel<T, DOT, false><<<grid, 256, smem, ctx->stream>>>(a);                            \
+  }
+    switch (tpr)
+    {
+    case 4:
+      DE_SPMM_ST(4)
+      break;
+    case 8:
+      DE_SPMM_ST(8)
+      break;
+    case 16:
+      DE_SPMM_ST(16)
+      break;
+    default:
+      DE_SPMM_ST(32)
+      break;
+    }
+#undef DE_SPMM_ST
+    DE_LAUNCH_CHECK(ctx);
+    *grid_out = grid;
+    return DE_OK;
+  }
+
   int ensure_halo_buffers(de_context *ctx, de_matrix *A, int m)
   {
     if (A->buf_m >= m)
@@ -409,7 +572,10 @@ namespace
     const bool dist = ctx->nranks > 1 && (A->n_halo > 0 || A->n_send > 0);
     if (!dist)
     {
-      DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, nullptr, A->n, ctx->partials, &g1));
+      if (A->st_all.valid && staged_usable(A, m))
+        DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_all, X, Y, m, ctx->partials, &g1));
+      else
+        DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, nullptr, A->n, ctx->partials, &g1));
     }
     else
     {
@@ -437,9 +603,17 @@ namespace
       }
       DE_NCCL(ctx, nc.GroupEnd());
       DE_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
-      DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->interior, A->n_interior, ctx->partials, &g1));
+      const bool staged = staged_usable(A, m) && (A->st_interior.valid || A->n_interior == 0) &&
+                          (A->st_boundary.valid || A->n_boundary == 0);
+      if (staged)
+        DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_interior, X, Y, m, ctx->partials, &g1));
+      else
+        DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->interior, A->n_interior, ctx->partials, &g1));
       DE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
-      DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->boundary, A->n_boundary, ctx->partials + (size_t)g1 * m, &g2));
+      if (staged)
+        DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_boundary, X, Y, m, ctx->partials + (size_t)g1 * m, &g2));
+      else
+        DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->boundary, A->n_boundary, ctx->partials + (size_t)g1 * m, &g2));
     }
     if (DOT)
     {
@@ -1178,7 +1352,7 @@ extern "C"
     A->nnz = nnz;
     DE_TRY(upload_converted(ctx, &A->rowptr, rowptr, (size_t)n + 1));
     DE_TRY(upload_converted(ctx, &A->col, col, (size_t)nnz));
-    DE_TRY(dev_alloc(ctx, &A->val, (size_t)nnz));
+    DE_TRY(dev_alloc(ctx, &A->val, (size_t)nnz + 2));
     DE_CUDA(ctx, cudaMemcpyAsync(A->val, val, sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx->stream));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DE_OK;
@@ -1194,6 +1368,8 @@ extern "C"
     de_matrix *A = new de_matrix();
     A->ctx = ctx;
     int s = matrix_upload(ctx, n, n, nnz, rowptr, col, val, A);
+    if (s == DE_OK)
+      s = build_staged_all(ctx, A, rowptr);
     if (s != DE_OK)
     {
       de_matrix_destroy(A);
@@ -1260,6 +1436,10 @@ extern "C"
       return fail(s);
     if ((s = upload_converted(ctx, &A->boundary, bd.data(), bd.size())) != DE_OK)
       return fail(s);
+    if ((s = build_staged_subset(ctx, in, rowptr, col_local, val, A->st_interior)) != DE_OK)
+      return fail(s);
+    if ((s = build_staged_subset(ctx, bd, rowptr, col_local, val, A->st_boundary)) != DE_OK)
+      return fail(s);
     *out = A;
     return DE_OK;
   }
@@ -1277,6 +1457,9 @@ extern "C"
     cudaFree(A->boundary);
     cudaFree(A->send_buf);
     cudaFree(A->halo_buf);
+    A->st_all.release();
+    A->st_interior.release();
+    A->st_boundary.release();
     delete A;
     return DE_OK;
   }

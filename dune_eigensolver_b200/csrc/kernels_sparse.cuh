@@ -23,6 +23,12 @@ namespace de
     acc.y = fma(a, x.y, acc.y);
   }
 
+  __device__ __forceinline__ void cp_async16_sparse(void *smem_dst, const void *gmem_src)
+  {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(gmem_src));
+  }
+
   struct SpmmArgs
   {
     long long nrows;     // rows to process (length of rowlist if given, else rows 0..nrows-1)
@@ -228,6 +234,167 @@ namespace de
           s.y += red[q * TPR + t].y;
         }
         st2(a.partials + (size_t)blockIdx.x * a.m + 2 * t, s);
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------------------------------------
+  // Staged SpMM: the CSR stream of a block of rows is brought into shared memory with coalesced cp.async
+  // ------------------------------------------------------------------------------------------------
+  // spmm_kernel_v2 pays three DEPENDENT memory latencies per row (row pointer -> column/value -> X row); for short
+  // rows (7-point stencil: one chunk per row) that chain, not bandwidth, bounds the kernel (ncu: issue 30-38 %,
+  // no unit saturated). Here a CTA owns contiguous row blocks (<= 256 rows, <= 2048 nonzeros, cut on the host at
+  // matrix creation, `blk_meta` = {first row, end row, first nonzero, end nonzero}); the block's row pointers,
+  // column indices and values are copied to shared memory with 16-byte cp.async, double-buffered one block ahead,
+  // so each matrix byte is read from HBM exactly once, fully coalesced, and the per-row chain shrinks to
+  // shared-memory read -> X gather. Rows are then processed exactly as in spmm_kernel_v2 (same lanes, same CSR
+  // accumulation order, same DOT epilogue). A block whose single row exceeds the staging capacity is read from
+  // global memory directly.
+  constexpr int kStageCapNnz = 2048;
+  constexpr int kStageMaxRows = 256;
+
+  struct StagedArgs
+  {
+    int nblocks;
+    const int4 *blk_meta;  // {r0, r1, k0, k1}
+    const int *rowmap;     // optional: local output row of each matrix row (permuted sub-matrix); null = identity
+    const int *rowptr;     // arrays are allocated with 16 bytes of tail padding
+    const int *col;
+    const double *val;
+    const double *X;
+    const double *H;
+    int n_owned;
+    int m;
+    double *Y;
+    double *partials;
+  };
+
+  constexpr size_t spmm_staged_smem_bytes()
+  {
+    return 2 * ((kStageMaxRows + 8) * sizeof(int) + (kStageCapNnz + 8) * sizeof(int) + (kStageCapNnz + 4) * sizeof(double));
+  }
+
+  template <int TPR, bool DOT, bool HALO>
+  __global__ void __launch_bounds__(256, 3) spmm_staged_kernel(const StagedArgs a)
+  {
+    constexpr int RPB = 256 / TPR;
+    constexpr int CH = 8;
+    extern __shared__ __align__(16) unsigned char dyn[];
+    double *s_val0 = reinterpret_cast<double *>(dyn);                    // 2 x (CAP+4) doubles
+    int *s_col0 = reinterpret_cast<int *>(s_val0 + 2 * (kStageCapNnz + 4)); // 2 x (CAP+8) ints
+    int *s_ptr0 = s_col0 + 2 * (kStageCapNnz + 8);                       // 2 x (MAXROWS+8) ints
+
+    const int tid = threadIdx.x;
+    const int t = tid % TPR, gslot = tid / TPR;
+    const unsigned ldh = (unsigned)TPR;
+    const double2 *__restrict__ Xv = reinterpret_cast<const double2 *>(a.X) + t;
+    const double2 *__restrict__ Hv = reinterpret_cast<const double2 *>(a.H) + t;
+    double2 *__restrict__ Yv = reinterpret_cast<double2 *>(a.Y) + t;
+    double2 dacc = make_double2(0.0, 0.0);
+
+    auto stage_block = [&](int4 mt, int s)
+    {
+      // mt.x >= mt.y marks "no block"
+      if (mt.x < mt.y)
+      {
+        const int ra = mt.x & ~3;
+        const int nptr = (mt.y + 1 - ra + 3) >> 2;
+        int *sp = s_ptr0 + s * (kStageMaxRows + 8);
+        for (int c = tid; c < nptr; c += 256)
+          cp_async16_sparse(sp + 4 * c, a.rowptr + ra + 4 * c);
+        if (mt.w - mt.z <= kStageCapNnz)
+        {
+          const int ka = mt.z & ~3, kva = mt.z & ~1;
+          const int ncol = (mt.w - ka + 3) >> 2, nval = (mt.w - kva + 1) >> 1;
+          int *sc = s_col0 + s * (kStageCapNnz + 8);
+          double *sv = s_val0 + s * (kStageCapNnz + 4);
+          for (int c = tid; c < ncol; c += 256)
+            cp_async16_sparse(sc + 4 * c, a.col + ka + 4 * c);
+          for (int c = tid; c < nval; c += 256)
+            cp_async16_sparse(sv + 2 * c, a.val + kva + 2 * c);
+        }
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+    };
+    auto load_meta = [&](int b) { return (b < a.nblocks) ? __ldg(a.blk_meta + b) : make_int4(0, 0, 0, 0); };
+
+    int b = blockIdx.x;
+    int4 cur = load_meta(b);
+    int4 nxt = load_meta(b + gridDim.x);
+    stage_block(cur, 0);
+    int s = 0;
+    for (; b < a.nblocks; b += gridDim.x)
+    {
+      stage_block(nxt, s ^ 1);                       // prefetch one block ahead
+      const int4 nxt2 = load_meta(b + 2 * gridDim.x); // metadata two blocks ahead (no dependent latency later)
+      asm volatile("cp.async.wait_group 1;\n" ::);
+      __syncthreads();
+
+      const bool direct = (cur.w - cur.z) > kStageCapNnz;
+      const int *sp = s_ptr0 + s * (kStageMaxRows + 8) - (cur.x & ~3);
+      const int *cp = direct ? a.col : s_col0 + s * (kStageCapNnz + 8) - (cur.z & ~3);
+      const double *vp = direct ? a.val : s_val0 + s * (kStageCapNnz + 4) - (cur.z & ~1);
+
+      for (int r = cur.x + gslot; r < cur.y; r += RPB)
+      {
+        const int kbeg = sp[r], kend = sp[r + 1];
+        const int klast = kend - 1;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int k = kbeg; k < kend; k += CH)
+        {
+          int j[CH];
+          double av[CH];
+          double2 xv[CH];
+#pragma unroll
+          for (int u = 0; u < CH; ++u)
+          {
+            const int kk = min(k + u, klast);
+            j[u] = cp[kk];
+            av[u] = vp[kk];
+          }
+#pragma unroll
+          for (int u = 0; u < CH; ++u)
+          {
+            if (HALO)
+              xv[u] = __ldg((j[u] < a.n_owned) ? Xv + (unsigned)j[u] * ldh : Hv + (unsigned)(j[u] - a.n_owned) * ldh);
+            else
+              xv[u] = __ldg(Xv + (unsigned)j[u] * ldh);
+          }
+#pragma unroll
+          for (int u = 0; u < CH; ++u)
+            fma2(acc, (k + u <= klast) ? av[u] : 0.0, xv[u]);
+        }
+        const int orow = a.rowmap ? __ldg(a.rowmap + r) : r;
+        Yv[(unsigned)orow * ldh] = acc;
+        if (DOT)
+        {
+          const double2 z = __ldg(Xv + (unsigned)orow * ldh);
+          dacc.x = fma(z.x, acc.x, dacc.x);
+          dacc.y = fma(z.y, acc.y, dacc.y);
+        }
+      }
+      __syncthreads(); // stage s may be overwritten by the prefetch issued in the next iteration
+      cur = nxt;
+      nxt = nxt2;
+      s ^= 1;
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::);
+
+    if (DOT)
+    {
+      __syncthreads();
+      double2 *red = reinterpret_cast<double2 *>(dyn);
+      red[tid] = dacc;
+      __syncthreads();
+      if (gslot == 0)
+      {
+        double2 sum = make_double2(0.0, 0.0);
+        for (int q = 0; q < RPB; ++q)
+        {
+          sum.x += red[q * TPR + t].x;
+          sum.y += red[q * TPR + t].y;
+        }
+        st2(a.partials + (size_t)blockIdx.x * a.m + 2 * t, sum);
       }
     }
   }
