@@ -658,8 +658,16 @@ namespace
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = true;
     }
+    static int ctas_per_sm = 0; // resident CTAs per SM of this instantiation (registers / shared memory decide)
+    if (ctas_per_sm == 0)
+    {
+      int occ = 1;
+      DE_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                       &occ, de::tall_skinny_kernel<M, DO_UPDATE, DO_GRAM, UPPER, SAME>, C::THREADS, smem));
+      ctas_per_sm = std::max(1, std::min(occ, 2));
+    }
     const long long ntiles = (a.n + C::TR - 1) / C::TR;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, ctx->sm_count));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * ctas_per_sm));
     a.partials = ctx->partials;
     {
       ProfScope prof(ctx, DO_UPDATE ? DE_PROF_UPDATE : DE_PROF_GRAM);

@@ -4,10 +4,19 @@
 // a Gram matrix in registers. Doing (a) and (b) in one pass is what makes CholQR2 cost
 //      8nm (Gram) + 16nm (update fused with the Gram of the result) [+ 16nm second update, skipped when the
 //      fused Gram already equals I to working precision]
-// instead of 48nm bytes. ncu of the first-generation kernels (profiles/r01_ncu_kernels_baseline.csv) showed them
-// bound by shared-memory wavefronts (l1tex 57-72 %) at 30 % occupancy with single-buffered tiles; this version
-// uses 8-wide register tiles (4x8 Gram blocks, 2x8 update blocks), 128-bit shared loads that are conflict-free
-// for the padded row stride M+2, and keeps two tiles in flight per SM.
+// instead of 48nm bytes.
+//
+// The small dense products run on the FP64 tensor path, mma.sync.m8n8k4.f64 (SASS DMMA): measured on B200 it has
+// the same peak as the FP64 FMA pipe (37.0 vs 34.8 TFLOP/s, tools/micro/fp64_peak.cu) -- tcgen05 has no FP64
+// kind -- but one DMMA does 256 FMAs from two operand registers per lane. ncu of the FMA formulation
+// (profiles/r01_ncu_kernels_v2.csv) showed it bound by shared-memory wavefronts (l1tex 65-80 %, FP64 pipe 30 %):
+// a 4x8 register block needs 6 128-bit shared loads per 32 FMAs. With DMMA a 4-row slab of the tile needs M/8
+// 64-bit fragment loads for M/8*(M/8+1)/2 Gram tiles (the same fragment serves as A and as B operand when Y = X),
+// and the update's B operand (the M x M factor) lives in registers for the whole kernel.
+//
+// Shared-memory layout: row stride M+4 doubles. Both fragment patterns -- (4 rows x 8 columns) for the Gram
+// operands and (8 rows x 4 columns) for the update's A operand -- then touch 16 distinct 8-byte bank pairs per
+// half-warp, i.e. every fragment load is conflict-free; rows stay 16-byte aligned for cp.async.
 //
 // Roofline: HBM-bound for M <= 32 (16nm or 8nm bytes); at M = 64 the FP64 pipe (2 n M^2 flops, halved by
 // the triangular / symmetric structure) is the second limiter.
@@ -34,6 +43,14 @@ namespace de
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
   }
 
+  /** D(8x8) += A(8x4) * B(4x8), fp64. Lane l holds a = A[l/4][l%4], b = B[l%4][l/4], c0 = C[l/4][2(l%4)], c1 = C[l/4][2(l%4)+1]. */
+  __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+  {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+  }
+
   template <int M, bool UPPER, int NOPS>
   struct TsCfg
   {
@@ -41,26 +58,19 @@ namespace de
     static constexpr int STAGES = 3;
     static constexpr int TR = (NOPS == 2 ? 2048 : 4096) / M; // rows per tile: ~32 KB of operand data per stage, so
                                                              // two stages in flight on 148 SMs cover HBM latency
-    static constexpr int LDT = M + 2;                     // padded row stride (doubles); rows stay 16-byte aligned
+    static constexpr int LDT = M + 4;                     // padded row stride (doubles), see file comment
     static constexpr int TILE = TR * LDT;                 // doubles per staged tile
-    // update phase: a warp unit is (32*RT rows) x (8 columns); 16/RT units per tile for every M
-    static constexpr int RT = 2;
-    static constexpr int NCG = M / 8;
-    static constexpr int NRB = TR / (32 * RT);
-    static constexpr int UNITS = NCG * NRB;
-    // Gram phase: 4 x 8 register blocks of G
-    static constexpr int NBI = M / 4, NBJ = M / 8;
-    static constexpr int count_tiles()
-    {
-      int c = 0;
-      for (int bi = 0; bi < NBI; ++bi)
-        for (int bj = 0; bj < NBJ; ++bj)
-          if (!UPPER || 4 * bi <= 8 * bj + 7)
-            ++c;
-      return c;
-    }
-    static constexpr int NT = count_tiles();              // threads that tile G once
-    static constexpr int RG = THREADS / NT;               // row groups
+    static constexpr int NB = M / 8;                      // 8-column blocks
+    // update phase: a warp owns NJ column blocks (their factor fragments live in registers) and every RBG-th 8-row block
+    static constexpr int NJ = (M == 64) ? 2 : NB;
+    static constexpr int JG = NB / NJ;                    // column-block groups
+    static constexpr int RBG = 8 / JG;                    // row-block groups
+    static constexpr int KS = M / 4;                      // k steps of the update
+    // Gram phase: 8x8 tiles of G split over TG tile groups, 4-row slabs of the tile split over KG slab groups
+    static constexpr int NTILES = UPPER ? NB * (NB + 1) / 2 : NB * NB;
+    static constexpr int TG = (M == 64) ? 2 : 1;
+    static constexpr int KG = 8 / TG;
+    static constexpr int NTW = (NTILES + TG - 1) / TG;    // tiles per warp
   };
 
   struct TsArgs
@@ -73,7 +83,7 @@ namespace de
     const double *R;      // M x M row-major factor (DO_UPDATE)
     double *Out;          // updated block (DO_UPDATE); may alias X
     int ldo;
-    int upper;            // R is upper triangular: column group c only needs k < 8c+8
+    int upper;            // R is upper triangular: column block c only needs k < 8c+8
     const int *skip_flag; // optional: if *skip_flag != 0 the kernel returns immediately (second CholQR sweep)
     double *partials;     // DO_GRAM: [gridDim.x][M*M]
   };
@@ -81,52 +91,41 @@ namespace de
   /** see file comment. Template switches:
    *   DO_UPDATE  Out = X R (tile staged in shared memory first, so Out may alias X)
    *   DO_GRAM    accumulate G = A^T B over all rows, A = (DO_UPDATE ? updated X : X), B = (SAME ? A : Y)
-   *   UPPER      G is symmetric: only the blocks meeting the upper triangle are computed, mirrored on output
+   *   UPPER      G is symmetric: only the 8x8 tiles on or above the diagonal are computed, mirrored on output
    *   SAME       single Gram operand (B aliases A) */
   template <int M, bool DO_UPDATE, bool DO_GRAM, bool UPPER, bool SAME>
-  __global__ void __launch_bounds__(256, 1) tall_skinny_kernel(const TsArgs a)
+  __global__ void __launch_bounds__(256, (M <= 32 && !(DO_UPDATE && DO_GRAM)) ? 2 : 1) tall_skinny_kernel(const TsArgs a)
   {
     constexpr int NOPS = (DO_GRAM && !SAME) ? 2 : 1;
     using C = TsCfg<M, UPPER, NOPS>;
     static_assert(!(DO_UPDATE && DO_GRAM) || SAME, "fused update+Gram works on one operand");
     extern __shared__ __align__(16) double smem[];
-    double *tiles = smem;                                            // STAGES x NOPS x TILE
-    double *Rs = smem + (size_t)C::STAGES * NOPS * C::TILE;          // M x M (DO_UPDATE)
+    double *tiles = smem; // STAGES x NOPS x TILE
 
     if (a.skip_flag != nullptr && *a.skip_flag != 0)
       return;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (DO_UPDATE)
-      for (int e = tid; e < M * M; e += C::THREADS)
-        Rs[e] = __ldg(a.R + e);
+    const int lq = lane >> 2, lr = lane & 3; // lane / 4, lane % 4
 
-    // Gram block of this thread
-    int bi = 0, bj = 0, grp = 0;
-    bool gram_thread = false;
-    if (DO_GRAM)
+    // ---- update: factor fragments of this warp's column blocks, B[k][j] = R[k0+k][j0+j] -> lane holds R[k0+lr][j0+lq]
+    const int jg = warp % C::JG, rbg = warp / C::JG;
+    double rfrag[DO_UPDATE ? C::KS : 1][DO_UPDATE ? C::NJ : 1];
+    if (DO_UPDATE)
     {
-      grp = tid / C::NT;
-      gram_thread = grp < C::RG;
-      int want = tid % C::NT, seen = 0;
-      for (int i = 0; i < C::NBI; ++i)
-        for (int j = 0; j < C::NBJ; ++j)
-          if (!UPPER || 4 * i <= 8 * j + 7)
-          {
-            if (seen == want)
-            {
-              bi = i;
-              bj = j;
-            }
-            ++seen;
-          }
+#pragma unroll
+      for (int ks = 0; ks < C::KS; ++ks)
+#pragma unroll
+        for (int q = 0; q < C::NJ; ++q)
+          rfrag[ks][q] = __ldg(a.R + (4 * ks + lr) * M + 8 * (jg * C::NJ + q) + lq);
     }
-    double acc[4][8];
+
+    // ---- Gram: this warp's tiles (bi <= bj when UPPER), enumerated row-major, dealt round-robin to the tile groups
+    const int tgi = warp % C::TG, kgi = warp / C::TG;
+    double gacc[DO_GRAM ? C::NTW : 1][2];
 #pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        acc[p][q] = 0.0;
+    for (int w = 0; w < (DO_GRAM ? C::NTW : 1); ++w)
+      gacc[w][0] = gacc[w][1] = 0.0;
 
     const long long ntiles = (a.n + C::TR - 1) / C::TR;
     constexpr int HP = M / 2;
@@ -150,7 +149,6 @@ namespace de
       cp_async_commit(); // always commit (possibly empty) so that the group accounting stays uniform
     };
 
-    // prologue: two tiles in flight
     long long tile = blockIdx.x;
     issue_tile(tile, 0);
     issue_tile(tile + gridDim.x, 1);
@@ -166,60 +164,44 @@ namespace de
 
       if (DO_UPDATE)
       {
-        // ---- Y = X R on the staged tile. Each warp owns one (32*RT rows) x (8 columns) patch; lane = row, so the
-        //      R(k, 8 cols) operand is a warp-wide broadcast and X(row, k..k+1) a conflict-free 128-bit load.
-        static_assert(C::UNITS <= 8, "one update unit per warp");
-        const bool has_unit = warp < C::UNITS;
-        const int cg = warp % C::NCG, rb = warp / C::NCG;
-        const int c0 = cg * 8;
-        double out[C::RT][8];
-        if (has_unit)
+        // ---- Y = X R on the staged tile, 8-row blocks: A[i][k] = X[rb*8+i][k0+k] -> lane loads X[rb*8+lq][k0+lr]
+        constexpr int NRB = C::TR / 8;
+        constexpr int MAXRB = (NRB + C::RBG - 1) / C::RBG;
+        double out[MAXRB][C::NJ][2];
+#pragma unroll
+        for (int i = 0; i < MAXRB; ++i)
         {
-          const int kmax = a.upper ? c0 + 8 : M;
+          const int rb = rbg + i * C::RBG;
 #pragma unroll
-          for (int q = 0; q < C::RT; ++q)
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              out[q][c] = 0.0;
-          const double *xrow = Xs + (rb * 32 * C::RT + lane) * C::LDT;
-#pragma unroll 2
-          for (int k = 0; k < kmax; k += 2)
+          for (int q = 0; q < C::NJ; ++q)
+            out[i][q][0] = out[i][q][1] = 0.0;
+          if (rb < NRB)
           {
-            double2 xv[C::RT];
+            const double *xr = Xs + (rb * 8 + lq) * C::LDT + lr;
 #pragma unroll
-            for (int q = 0; q < C::RT; ++q)
-              xv[q] = ld2(xrow + q * 32 * C::LDT + k);
-            double r0v[8], r1v[8];
-#pragma unroll
-            for (int c = 0; c < 8; c += 2)
+            for (int ks = 0; ks < C::KS; ++ks)
             {
-              const double2 u = ld2(Rs + k * M + c0 + c), w = ld2(Rs + (k + 1) * M + c0 + c);
-              r0v[c] = u.x;
-              r0v[c + 1] = u.y;
-              r1v[c] = w.x;
-              r1v[c + 1] = w.y;
-            }
+              const double av = xr[4 * ks];
 #pragma unroll
-            for (int q = 0; q < C::RT; ++q)
-#pragma unroll
-              for (int c = 0; c < 8; ++c)
+              for (int q = 0; q < C::NJ; ++q)
               {
-                out[q][c] = fma(xv[q].x, r0v[c], out[q][c]);
-                out[q][c] = fma(xv[q].y, r1v[c], out[q][c]);
+                // triangular factor: column block jb only sees k < 8 jb + 8, i.e. k steps ks <= 2 jb + 1 (warp-uniform)
+                const int jb = jg * C::NJ + q;
+                if (!a.upper || ks <= 2 * jb + 1)
+                  dmma884(out[i][q][0], out[i][q][1], av, rfrag[ks][q]);
               }
+            }
           }
         }
         __syncthreads(); // every warp has finished READING the tile: the result may now overwrite it in place
-        if (has_unit)
+#pragma unroll
+        for (int i = 0; i < MAXRB; ++i)
         {
+          const int rb = rbg + i * C::RBG;
+          if (rb < NRB)
 #pragma unroll
-          for (int q = 0; q < C::RT; ++q)
-          {
-            double *y = Xs + (rb * 32 * C::RT + q * 32 + lane) * C::LDT + c0;
-#pragma unroll
-            for (int c = 0; c < 8; c += 2)
-              st2(y + c, make_double2(out[q][c], out[q][c + 1]));
-          }
+            for (int q = 0; q < C::NJ; ++q)
+              st2(Xs + (rb * 8 + lq) * C::LDT + 8 * (jg * C::NJ + q) + 2 * lr, make_double2(out[i][q][0], out[i][q][1]));
         }
         __syncthreads();
         // ---- coalesced write-out of the updated tile ----
@@ -233,28 +215,31 @@ namespace de
 
       if (DO_GRAM)
       {
+        // ---- G += A^T B over 4-row slabs: fragment of column block c = X[slab*4 + lr][8c + lq] (A and B alike)
         const double *Ys = SAME ? Xs : Xs + C::TILE;
-        if (gram_thread)
+        for (int slab = kgi; slab < C::TR / 4; slab += C::KG)
         {
-#pragma unroll 2
-          for (int r = grp; r < C::TR; r += C::RG)
+          double fa[C::NB], fb[SAME ? 1 : C::NB];
+          const double *xs = Xs + (slab * 4 + lr) * C::LDT + lq;
+          const double *ys = Ys + (slab * 4 + lr) * C::LDT + lq;
+#pragma unroll
+          for (int c = 0; c < C::NB; ++c)
           {
-            const double2 x01 = ld2(Xs + r * C::LDT + 4 * bi), x23 = ld2(Xs + r * C::LDT + 4 * bi + 2);
-            const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
-            double yv[8];
-#pragma unroll
-            for (int q = 0; q < 8; q += 2)
-            {
-              const double2 t = ld2(Ys + r * C::LDT + 8 * bj + q);
-              yv[q] = t.x;
-              yv[q + 1] = t.y;
-            }
-#pragma unroll
-            for (int p = 0; p < 4; ++p)
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                acc[p][q] = fma(xv[p], yv[q], acc[p][q]);
+            fa[c] = xs[8 * c];
+            if (!SAME)
+              fb[c] = ys[8 * c];
           }
+          // tile idx (compile-time after unrolling) belongs to tile group idx % TG and is slot idx / TG of that group
+          int idx = 0;
+#pragma unroll
+          for (int bi = 0; bi < C::NB; ++bi)
+#pragma unroll
+            for (int bj = (UPPER ? bi : 0); bj < C::NB; ++bj)
+            {
+              if (idx % C::TG == tgi)
+                dmma884(gacc[idx / C::TG][0], gacc[idx / C::TG][1], fa[bi], SAME ? fa[bj] : fb[bj]);
+              ++idx;
+            }
         }
       }
       __syncthreads(); // all reads of this stage are done: it may be refilled by the next iteration's prefetch
@@ -264,35 +249,49 @@ namespace de
 
     if (DO_GRAM)
     {
-      // combine the row groups (fixed order) through shared memory, 8 values per thread at a time
+      // combine the slab groups in fixed order into one M x M matrix in shared memory, then emit the CTA partial
       __syncthreads();
-      double *red = smem; // THREADS x 8 doubles
-      double *outp = a.partials + (size_t)blockIdx.x * M * M;
-      for (int p = 0; p < 4; ++p)
+      double *G = smem; // M x M
+      for (int turn = 0; turn < C::KG; ++turn)
       {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          red[q * C::THREADS + tid] = acc[p][q];
-        __syncthreads();
-        if (tid < C::NT)
+        if (kgi == turn)
         {
+          int idx = 0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-          {
-            double s = 0.0;
-            for (int g = 0; g < C::RG; ++g)
-              s += red[q * C::THREADS + g * C::NT + tid];
-            const int gi = 4 * bi + p, gj = 8 * bj + q;
-            if (!UPPER)
-              outp[gi * M + gj] = s;
-            else if (gi <= gj)
+          for (int bi = 0; bi < C::NB; ++bi)
+#pragma unroll
+            for (int bj = (UPPER ? bi : 0); bj < C::NB; ++bj)
             {
-              outp[gi * M + gj] = s;
-              outp[gj * M + gi] = s;
+              if (idx % C::TG == tgi)
+              {
+                double *g = G + (8 * bi + lq) * M + 8 * bj + 2 * lr;
+                const double v0 = gacc[idx / C::TG][0], v1 = gacc[idx / C::TG][1];
+                if (turn == 0)
+                  st2(g, make_double2(v0, v1));
+                else
+                {
+                  const double2 o = ld2(g);
+                  st2(g, make_double2(o.x + v0, o.y + v1));
+                }
+              }
+              ++idx;
             }
-          }
         }
         __syncthreads();
+      }
+      double *outp = a.partials + (size_t)blockIdx.x * M * M;
+      for (int e = tid; e < M * M; e += C::THREADS)
+      {
+        const int i = e / M, j = e % M;
+        if (!UPPER)
+          outp[e] = G[e];
+        else if ((i >> 3) <= (j >> 3))
+        {
+          // tiles on or above the block diagonal were computed in full; mirror them below it
+          outp[e] = G[e];
+          if ((i >> 3) < (j >> 3))
+            outp[j * M + i] = G[e];
+        }
       }
     }
   }
@@ -302,10 +301,10 @@ namespace de
   {
     constexpr int NOPS = (DO_GRAM && !SAME) ? 2 : 1;
     using C = TsCfg<M, UPPER, NOPS>;
-    size_t d = (size_t)C::STAGES * NOPS * C::TILE + (DO_UPDATE ? (size_t)M * M : 0);
-    const size_t red = (size_t)C::THREADS * 8;
-    if (d < red)
-      d = red;
+    size_t d = (size_t)C::STAGES * NOPS * C::TILE;
+    const size_t g = (size_t)M * M;
+    if (d < g)
+      d = g;
     return d * sizeof(double);
   }
 
