@@ -24,7 +24,6 @@ N > 1 GPUs: the same global problem row-partitioned into z-slabs (strong scaling
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -81,67 +80,66 @@ def workload_name(args):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event (throttle) reasons DURING the timed region, read through NVML inside this process
+    (nvidia_ml_py). Polling with an `nvidia-smi -lms` child, as the profiling recipe's one-liner does, stalled the
+    CUDA context of this process for 0.3-0.7 s per sample on the B200 boxes (measured: steps of 28 ms became
+    30-750 ms, gpurun_out/ round 1), which is longer than a whole solve; NVML calls from a thread do not."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, device):
-        self.device = device
-        self.proc = None
-        self.lines = []
+    def __init__(self, device, period=0.02):
+        self.device, self.period = device, period
+        self.samples, self.marked = [], 0
+        self.thread, self.stop_flag, self.err = None, False, None
 
     def start(self):
-        """start polling and wait until nvidia-smi has initialised (its start-up stalls the driver for ~0.1 s,
-        which must not fall into the timed region)"""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-            t0 = time.time()
-            while not self.lines and time.time() - t0 < 5.0:
-                time.sleep(0.05)
-            self.skip = len(self.lines)  # samples taken before the timed region
-        except Exception:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES if it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.device
+            if vis and all(t.strip().isdigit() for t in vis.split(",")):
+                idx = int(vis.split(",")[self.device])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = "nvml unavailable: %s" % e
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001  (older binding name)
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((sm, rs))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(self.period)
 
     def mark(self):
-        self.skip = len(self.lines)
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.marked = len(self.samples)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines[getattr(self, "skip", 0):]:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "sampler not started"]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        use = self.samples[self.marked:]
+        if not use:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
+        reasons = sorted(name for name, bit in self.REASONS.items() if any(rs & bit for _, rs in use))
+        return {"sm_mhz": float(np.median([sm for sm, _ in use])), "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(use), "source": "NVML in-process, every %g ms" % (self.period * 1e3)}
 
 
 def cpu_reference_sample(args, sample_iters, iterations_full):
@@ -264,28 +262,40 @@ def run_b200(args):
         return ev
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get("DE_BENCH_NOCLOCKS", "") == "":
         sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     ctx.profile(reset=True)
-    ctx.set_profiling(os.environ.get("DE_BENCH_NOPROF", "") == "")
+    # inside the timed region only the dominant kernel (SpMM) is bracketed by CUDA events; bracketing all ~9
+    # launches of every iteration costs ~15 % of the step (measured) -- the other kernels are timed in one extra,
+    # untimed solve after the region
+    ctx.set_profiling(os.environ.get("DE_BENCH_NOPROF", "") == "", only=["spmm"])
     launches0 = ctx.launch_count()
     if rank == 0:
         sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         ev = step()
+        marks[k].record()
     e1.record()
     barrier()
+    step_ms = [(e0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]) for k in range(args.steps)]
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     prof = ctx.profile(reset=True)
     ctx.set_profiling(False)
     launches = ctx.launch_count() - launches0
+    # one more solve, outside the timed region, with every kernel category timed: the shares of the step
+    ctx.set_profiling(True)
+    step()
+    barrier()
+    prof_all = ctx.profile(reset=True)
+    ctx.set_profiling(False)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -343,20 +353,23 @@ def run_b200(args):
     spmm_bytes = 12.0 * nnz_local + 4.0 * (n_loc + 1) + 16.0 * n_loc * m
     launches_per_spmm = 1 if world == 1 else 2  # interior + boundary launches of a distributed SpMM
     achieved = (spmm_bytes * (spmm_cnt / launches_per_spmm)) / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
-    total_kernel_ms = sum(val[0] for val in prof.values())
-    shares = {k: (val[0] / total_kernel_ms if total_kernel_ms > 0 else 0.0) for k, val in prof.items()}
-    gram_ms, gram_cnt = prof["gram"]
-    upd_ms, upd_cnt = prof["update"]
+    total_kernel_ms = sum(val[0] for val in prof_all.values())
+    shares = {k: (val[0] / total_kernel_ms if total_kernel_ms > 0 else 0.0) for k, val in prof_all.items()}
+    gram_ms, gram_cnt = prof_all["gram"]
+    upd_ms, upd_cnt = prof_all["update"]
     other = {
         "gram": {"GBps": (8.0 * n_loc * m * gram_cnt) / (gram_ms * 1e-3) / 1e9 if gram_ms > 0 else 0.0,
                  "avg_ms": gram_ms / max(gram_cnt, 1), "algorithmic_bytes": 8.0 * n_loc * m},
         "update": {"GBps": (16.0 * n_loc * m * upd_cnt) / (upd_ms * 1e-3) / 1e9 if upd_ms > 0 else 0.0,
                    "avg_ms": upd_ms / max(upd_cnt, 1), "algorithmic_bytes": 16.0 * n_loc * m},
     }
-    roofline = {"bound": "hbm", "kernel": "spmm_kernel (SpMM + fused Rayleigh-quotient dots)",
+    roofline = {"bound": "hbm", "kernel": "spmm_brb_kernel (SpMM + fused Rayleigh-quotient dots)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "avg_launch_ms": spmm_ms / max(spmm_cnt, 1),
-                "algorithmic_bytes_per_launch": spmm_bytes, "kernel_time_shares": shares, "other_kernels": other}
+                "algorithmic_bytes_per_launch": spmm_bytes, "kernel_time_shares": shares,
+                "kernel_time_shares_source": "one extra solve after the timed region with all categories timed "
+                                             "(sum of kernel time %.2f ms per solve)" % total_kernel_ms,
+                "other_kernels": other}
 
     key = (args.grid, args.stencil, args.nev, args.tol)
     known = ITERATIONS_TO_CONVERGENCE.get(key)
@@ -380,7 +393,7 @@ def run_b200(args):
                          ((12.0 * nnz_local + 4 * n_loc) / 1e6, 8.0 * n_loc * m / 1e6),
                    "parallelism": "row-partitioned z-slabs x%d" % world if world > 1 else "single GPU"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "eigenvalues_head": [float(x) for x in ev[:4]],
+        "eigenvalues_head": [float(x) for x in ev[:4]], "step_ms": [round(x, 3) for x in step_ms],
     }
     print(json.dumps(line))
     if world > 1:

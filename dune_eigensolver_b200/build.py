@@ -15,7 +15,8 @@ LIB = os.path.join(CSRC, "libdune_eigensolver_b200.so")
 METIS = "/usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a"
 
 SOURCES = ["de_capi.cu"]
-HEADERS = ["kernels_sparse.cuh", "kernels_dense.cuh", "kernels_trsv.cuh",
+HEADERS = ["kernels_sparse.cuh", "kernels_dense.cuh", "kernels_trsv.cuh", "kernels_tallskinny.cuh",
+           "kernels_spmm_blocked.cuh", "brb_format.hpp",
            os.path.join("..", "..", "include", "dune_eigensolver_b200.h"),
            os.path.join("..", "..", "include", "dune", "eigensolver", "sparse_lu.hh")]
 
@@ -43,7 +44,7 @@ def build_library(force=False, verbose=False):
     cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo",
            "-gencode", "arch=compute_100a,code=sm_100a",
            "-ccbin", hostcxx,
-           "-Xcompiler", "-fPIC,-O3,-march=x86-64-v3,-Wno-sign-compare",
+           "-Xcompiler", "-fPIC,-O3,-march=x86-64-v3,-Wno-sign-compare,-pthread",
            "-shared", "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]

@@ -12,6 +12,7 @@ from . import build as _build
 
 DE_OK, DE_ERR_INVALID, DE_ERR_ALLOC, DE_ERR_CUDA, DE_ERR_NCCL, DE_ERR_SINGULAR, DE_ERR_UNSUPPORTED = range(7)
 DE_MAX_COLS = 64
+DE_SPMM_AUTO, DE_SPMM_CSR, DE_SPMM_BRB = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)
@@ -38,6 +39,10 @@ SIGNATURES = {
                                      _i64p, _i64p, _vpp],
     "de_matrix_destroy": [_vp],
     "de_matrix_rows": [_vp, _i64p, _i64p],
+    "de_matrix_set_spmm_format": [_vp, C.c_int],
+    "de_matrix_spmm_info": [_vp, _ip, _i64p, _i64p, _i64p, _i64p, _ip],
+    "de_matrix_brb_selfcheck": [_vp, C.c_int64, C.c_int64, _i64p, _i64p, _dp, _i64p],
+    "de_brb_format_check": [C.c_int64, C.c_int64, C.c_int64, _i64p, _i64p, _dp, C.c_int, _i64p, _dp],
     "de_halo_plan_local": [C.c_int64, _i64p, _i64p, C.c_int, C.c_int, _i64p, _i64p, _i64p, _i64p, _i64p],
     "de_mv_create": [_vp, C.c_int64, C.c_int, _vpp],
     "de_mv_destroy": [_vp],

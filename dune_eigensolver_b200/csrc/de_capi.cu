@@ -10,7 +10,12 @@
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
+#include <limits>
+#include <map>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <unordered_map>
 #include <random>
 #include <string>
 #include <vector>
@@ -24,6 +29,9 @@
 #include "../../include/dune/eigensolver/sparse_lu.hh"
 #include "kernels_dense.cuh"
 #include "kernels_sparse.cuh"
+#include "kernels_spmm_blocked.cuh"
+#include "brb_format.hpp"
+#include "kernels_brb_build.cuh"
 #include "kernels_tallskinny.cuh"
 #include "kernels_trsv.cuh"
 
@@ -96,7 +104,13 @@ struct de_context
   double *partials = nullptr; // kPartialDoubles
   double *dsmall = nullptr;   // kSmall doubles: G | Rinv | dp | info
   int *dstatus = nullptr;     // sticky Cholesky status
-  int *dflags = nullptr;      // device flag: second CholQR sweep not needed
+  int *dflags = nullptr;      // device flags: [0] second CholQR sweep not needed, [1] driver loop converged, [2] last iteration
+  const int *done_ptr = nullptr; // = dflags + 1 while an asynchronous driver loop is enqueuing, else null
+  int *hflags = nullptr;      // pinned: 2 slots x 4 ints, polled copies of dflags
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+  double *dconv = nullptr;    // s_prev[64] | hist[dconv_cap]
+  void *xfer = nullptr;       // XferEngine: pinned staging buffers and copy streams (created on first use)
+  size_t dconv_cap = 0;
   double *hsmall = nullptr;   // pinned mirror of dsmall
   int *hstatus = nullptr;     // pinned
   double *stage = nullptr;    // layout-conversion staging
@@ -104,6 +118,7 @@ struct de_context
   long long launches = 0;
   // optional per-kernel CUDA-event timing (bench.py's roofline numbers)
   bool profiling = false;
+  unsigned prof_mask = ~0u; // categories that are timed while profiling is on
   struct ProfRecord
   {
     int cat;
@@ -128,6 +143,11 @@ struct de_mv
   double *d;
 };
 
+namespace
+{
+  void dev_free(void *p);
+}
+
 /** a set of rows prepared for spmm_staged_kernel: CSR (possibly a row-permuted copy) + row-block metadata */
 struct StagedRows
 {
@@ -141,15 +161,37 @@ struct StagedRows
   {
     if (owns_csr)
     {
-      cudaFree(rowptr);
-      cudaFree(col);
-      cudaFree(val);
+      dev_free(rowptr);
+      dev_free(col);
+      dev_free(val);
     }
-    cudaFree(rowmap);
-    cudaFree(blk_meta);
+    dev_free(rowmap);
+    dev_free(blk_meta);
     rowptr = col = rowmap = nullptr;
     val = nullptr;
     blk_meta = nullptr;
+    valid = false;
+  }
+};
+
+/** BRB form of a matrix on the device (brb_format.hpp): tiles [0, n_interior) touch owned columns only */
+struct BrbDevice
+{
+  bool valid = false;
+  int ntiles = 0, n_interior = 0, max_len16 = 0, max_u = 0;
+  long long nblocks = 0, nsteps = 0, nvals = 0;
+  bool grid = false;
+  int tw = 0, th = 0, td = 0;
+  int4 *tile = nullptr, *blob = nullptr;
+  int *ucol = nullptr;
+  size_t blob16 = 0, nucol = 0; // sizes of blob (16-byte units) and ucol
+  void release()
+  {
+    dev_free(tile);
+    dev_free(blob);
+    dev_free(ucol);
+    tile = blob = nullptr;
+    ucol = nullptr;
     valid = false;
   }
 };
@@ -171,6 +213,8 @@ struct de_matrix
   double *send_buf = nullptr, *halo_buf = nullptr;
   int buf_m = 0;
   StagedRows st_all, st_interior, st_boundary;
+  BrbDevice brb;
+  int spmm_format = DE_SPMM_AUTO; // which SpMM kernel family to use (de_matrix_set_spmm_format)
 };
 
 struct TrsvSegment
@@ -235,7 +279,7 @@ namespace
     }
     ProfScope(de_context *ctx, int category) : c(ctx), cat(category)
     {
-      if (c->profiling)
+      if (c->profiling && ((c->prof_mask >> category) & 1u))
       {
         e0 = take(c);
         e1 = take(c);
@@ -285,18 +329,143 @@ namespace
 
   bool valid_cols(int m) { return m > 0 && m % 8 == 0 && m <= DE_MAX_COLS; }
 
-  template <class T>
-  int dev_alloc(de_context *ctx, T **p, size_t count)
+  // ---- device memory: a caching allocator ------------------------------------------------------------------
+  // cudaMalloc / cudaFree take driver-wide locks; on the shared B200 boxes single calls were seen to stall for
+  // 0.3-1 s (a 256 MB block allocated and freed per solve made one step in ten take 800 ms instead of 28). Blocks
+  // released by the library are therefore kept, keyed by (device, stream, size), and handed out again; reuse on the
+  // same stream is ordered after the previous user's kernels. Freed for real when the owning context is destroyed.
+  struct DevBlockInfo
+  {
+    size_t bytes;
+    int device;
+    cudaStream_t stream;
+  };
+  struct DevCache
+  {
+    std::mutex mu;
+    std::unordered_map<void *, DevBlockInfo> live;
+    std::map<std::tuple<int, cudaStream_t, size_t>, std::vector<void *>> idle;
+    size_t idle_bytes = 0;
+  };
+  DevCache &dev_cache()
+  {
+    static DevCache c;
+    return c;
+  }
+  constexpr size_t kDevCacheMaxIdle = (size_t)96 << 30;
+
+  int dev_alloc_bytes(de_context *ctx, void **p, size_t bytes)
   {
     *p = nullptr;
-    if (count == 0)
-      count = 1;
-    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    bytes = std::max<size_t>((bytes + 511) & ~(size_t)511, 512);
+    DevCache &C = dev_cache();
+    {
+      std::lock_guard<std::mutex> lock(C.mu);
+      auto it = C.idle.find(std::make_tuple(ctx->device, ctx->stream, bytes));
+      if (it != C.idle.end() && !it->second.empty())
+      {
+        *p = it->second.back();
+        it->second.pop_back();
+        C.idle_bytes -= bytes;
+        C.live[*p] = DevBlockInfo{bytes, ctx->device, ctx->stream};
+        return DE_OK;
+      }
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess)
+    {
+      // give the idle blocks back to the driver and try once more
+      std::vector<void *> drop;
+      {
+        std::lock_guard<std::mutex> lock(C.mu);
+        for (auto &kv : C.idle)
+          if (std::get<0>(kv.first) == ctx->device)
+          {
+            for (void *q : kv.second)
+              drop.push_back(q);
+            C.idle_bytes -= std::get<2>(kv.first) * kv.second.size();
+            kv.second.clear();
+          }
+      }
+      cudaGetLastError();
+      for (void *q : drop)
+        cudaFree(q);
+      e = cudaMalloc(p, bytes);
+    }
     if (e != cudaSuccess)
       return set_error(ctx, e == cudaErrorMemoryAllocation ? DE_ERR_ALLOC : DE_ERR_CUDA,
                        std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lock(C.mu);
+    C.live[*p] = DevBlockInfo{bytes, ctx->device, ctx->stream};
     return DE_OK;
   }
+
+  template <class T>
+  int dev_alloc(de_context *ctx, T **p, size_t count)
+  {
+    return dev_alloc_bytes(ctx, (void **)p, std::max<size_t>(count, 1) * sizeof(T));
+  }
+
+  /** release a device pointer: blocks of this library go back to the cache, anything else to cudaFree */
+  void dev_free(void *p)
+  {
+    if (!p)
+      return;
+    DevCache &C = dev_cache();
+    {
+      std::lock_guard<std::mutex> lock(C.mu);
+      auto it = C.live.find(p);
+      if (it != C.live.end())
+      {
+        const DevBlockInfo b = it->second;
+        C.live.erase(it);
+        if (C.idle_bytes + b.bytes <= kDevCacheMaxIdle)
+        {
+          C.idle[std::make_tuple(b.device, b.stream, b.bytes)].push_back(p);
+          C.idle_bytes += b.bytes;
+          return;
+        }
+      }
+    }
+    cudaFree(p);
+  }
+
+  /** really free the idle blocks of one (device, stream): context destruction */
+  void dev_cache_trim(int device, cudaStream_t stream)
+  {
+    DevCache &C = dev_cache();
+    std::vector<void *> drop;
+    {
+      std::lock_guard<std::mutex> lock(C.mu);
+      for (auto &kv : C.idle)
+        if (std::get<0>(kv.first) == device && std::get<1>(kv.first) == stream)
+        {
+          for (void *q : kv.second)
+            drop.push_back(q);
+          C.idle_bytes -= std::get<2>(kv.first) * kv.second.size();
+          kv.second.clear();
+        }
+    }
+    for (void *q : drop)
+      cudaFree(q);
+  }
+
+  // ---- host <-> device transfers of caller (pageable) memory -------------------------------------------------
+  // A plain cudaMemcpy from pageable memory is staged by the driver through one pinned buffer on one thread
+  // (~10 GB/s); here kXferThreads workers convert / copy 8 MB chunks into their own pinned buffers and issue
+  // asynchronous copies on their own streams, so the PCIe link and several host cores work at the same time.
+  constexpr int kXferThreads = 4;
+  constexpr size_t kXferChunk = (size_t)8 << 20; // bytes per pinned buffer
+
+  struct XferEngine
+  {
+    bool ready = false;
+    unsigned char *pinned[kXferThreads][2] = {};
+    cudaStream_t stream[kXferThreads] = {};
+    cudaEvent_t ev[kXferThreads][2] = {};
+  };
+
+  int xfer_init(de_context *ctx);
 
   template <class T, class S>
   int upload_converted(de_context *ctx, T **dst, const S *src, size_t count)
@@ -307,6 +476,188 @@ namespace
     DE_TRY(dev_alloc(ctx, dst, count + 16 / sizeof(T))); // 16 bytes of tail padding: staged kernels copy 16-byte chunks
     DE_CUDA(ctx, cudaMemcpyAsync(*dst, tmp.data(), count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // tmp dies here
+    return DE_OK;
+  }
+
+  int xfer_init(de_context *ctx)
+  {
+    if (ctx->xfer)
+      return DE_OK;
+    XferEngine *X = new XferEngine();
+    for (int t = 0; t < kXferThreads; ++t)
+    {
+      DE_CUDA(ctx, cudaStreamCreateWithFlags(&X->stream[t], cudaStreamNonBlocking));
+      for (int b = 0; b < 2; ++b)
+      {
+        DE_CUDA(ctx, cudaMallocHost((void **)&X->pinned[t][b], kXferChunk));
+        DE_CUDA(ctx, cudaEventCreateWithFlags(&X->ev[t][b], cudaEventDisableTiming));
+      }
+    }
+    X->ready = true;
+    ctx->xfer = X;
+    return DE_OK;
+  }
+
+  void xfer_destroy(de_context *ctx)
+  {
+    XferEngine *X = static_cast<XferEngine *>(ctx->xfer);
+    if (!X)
+      return;
+    for (int t = 0; t < kXferThreads; ++t)
+    {
+      for (int b = 0; b < 2; ++b)
+      {
+        if (X->pinned[t][b])
+          cudaFreeHost(X->pinned[t][b]);
+        if (X->ev[t][b])
+          cudaEventDestroy(X->ev[t][b]);
+      }
+      if (X->stream[t])
+        cudaStreamDestroy(X->stream[t]);
+    }
+    delete X;
+    ctx->xfer = nullptr;
+  }
+
+  /** dst[i] = (T) src[i], i < count, host -> device. `range` (optional) receives min and max of the source values.
+   *  Work that ctx->stream has already queued on dst must be complete (callers upload into fresh allocations);
+   *  on return the data is on the device. */
+  template <class T, class S>
+  int upload_parallel(de_context *ctx, T *dst, const S *src, size_t count, long long *range = nullptr)
+  {
+    if (range)
+    {
+      range[0] = 0;
+      range[1] = -1;
+    }
+    if (count == 0)
+      return DE_OK;
+    DE_TRY(xfer_init(ctx));
+    XferEngine *X = static_cast<XferEngine *>(ctx->xfer);
+    const size_t per = kXferChunk / sizeof(T);
+    const size_t nchunks = (count + per - 1) / per;
+    const int nthreads = (int)std::min<size_t>(kXferThreads, nchunks);
+    cudaError_t err[kXferThreads];
+    long long lo[kXferThreads], hi[kXferThreads];
+    auto work = [&](int t)
+    {
+      cudaSetDevice(ctx->device);
+      err[t] = cudaSuccess;
+      lo[t] = std::numeric_limits<long long>::max();
+      hi[t] = std::numeric_limits<long long>::min();
+      int b = 0;
+      for (size_t c = (size_t)t; c < nchunks && err[t] == cudaSuccess; c += (size_t)nthreads, b ^= 1)
+      {
+        const size_t i0 = c * per, i1 = std::min(count, i0 + per);
+        T *buf = reinterpret_cast<T *>(X->pinned[t][b]);
+        cudaError_t e = cudaEventSynchronize(X->ev[t][b]); // the copy that last used this buffer
+        if (e != cudaSuccess)
+        {
+          err[t] = e;
+          break;
+        }
+        if (std::is_same<T, S>::value && !range)
+          std::memcpy(buf, src + i0, (i1 - i0) * sizeof(T));
+        else if (range)
+        {
+          long long l = lo[t], h = hi[t];
+          for (size_t i = i0; i < i1; ++i)
+          {
+            const long long v = (long long)src[i];
+            l = std::min(l, v);
+            h = std::max(h, v);
+            buf[i - i0] = (T)src[i];
+          }
+          lo[t] = l;
+          hi[t] = h;
+        }
+        else
+          for (size_t i = i0; i < i1; ++i)
+            buf[i - i0] = (T)src[i];
+        e = cudaMemcpyAsync(dst + i0, buf, (i1 - i0) * sizeof(T), cudaMemcpyHostToDevice, X->stream[t]);
+        if (e == cudaSuccess)
+          e = cudaEventRecord(X->ev[t][b], X->stream[t]);
+        err[t] = e;
+      }
+      if (err[t] == cudaSuccess)
+        err[t] = cudaStreamSynchronize(X->stream[t]);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t)
+      th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th)
+      x.join();
+    for (int t = 0; t < nthreads; ++t)
+    {
+      if (err[t] != cudaSuccess)
+        return set_error(ctx, DE_ERR_CUDA, std::string("host-to-device transfer: ") + cudaGetErrorString(err[t]));
+      if (range && lo[t] <= hi[t])
+      {
+        if (range[0] > range[1])
+        {
+          range[0] = lo[t];
+          range[1] = hi[t];
+        }
+        else
+        {
+          range[0] = std::min(range[0], lo[t]);
+          range[1] = std::max(range[1], hi[t]);
+        }
+      }
+    }
+    return DE_OK;
+  }
+
+  /** device -> caller memory, `bytes` bytes; src must be complete on ctx->stream (the function synchronises it first) */
+  int download_parallel(de_context *ctx, void *dst, const void *src, size_t bytes)
+  {
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bytes == 0)
+      return DE_OK;
+    DE_TRY(xfer_init(ctx));
+    XferEngine *X = static_cast<XferEngine *>(ctx->xfer);
+    const size_t nchunks = (bytes + kXferChunk - 1) / kXferChunk;
+    const int nthreads = (int)std::min<size_t>(kXferThreads, nchunks);
+    cudaError_t err[kXferThreads];
+    auto work = [&](int t)
+    {
+      cudaSetDevice(ctx->device);
+      err[t] = cudaSuccess;
+      // two chunks in flight per worker: issue c, then drain the previous one
+      size_t prev = (size_t)-1;
+      int b = 0;
+      for (size_t c = (size_t)t; err[t] == cudaSuccess; c += (size_t)nthreads, b ^= 1)
+      {
+        if (c < nchunks)
+        {
+          const size_t o = c * kXferChunk, len = std::min(bytes - o, kXferChunk);
+          cudaError_t e = cudaMemcpyAsync(X->pinned[t][b], (const unsigned char *)src + o, len, cudaMemcpyDeviceToHost, X->stream[t]);
+          if (e == cudaSuccess)
+            e = cudaEventRecord(X->ev[t][b], X->stream[t]);
+          err[t] = e;
+        }
+        if (prev != (size_t)-1 && err[t] == cudaSuccess)
+        {
+          const size_t o = prev * kXferChunk, len = std::min(bytes - o, kXferChunk);
+          err[t] = cudaEventSynchronize(X->ev[t][b ^ 1]);
+          if (err[t] == cudaSuccess)
+            std::memcpy((unsigned char *)dst + o, X->pinned[t][b ^ 1], len);
+        }
+        if (c >= nchunks)
+          break;
+        prev = c;
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t)
+      th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th)
+      x.join();
+    for (int t = 0; t < nthreads; ++t)
+      if (err[t] != cudaSuccess)
+        return set_error(ctx, DE_ERR_CUDA, std::string("device-to-host transfer: ") + cudaGetErrorString(err[t]));
     return DE_OK;
   }
 
@@ -321,7 +672,7 @@ namespace
   {
     dim3 block(32, 32);
     ProfScope prof(ctx, DE_PROF_SMALL);
-    de::reduce_partials_kernel<<<(len + 31) / 32, block, 0, ctx->stream>>>(partials, nparts, len, out);
+    de::reduce_partials_kernel<<<(len + 31) / 32, block, 0, ctx->stream>>>(partials, nparts, len, out, ctx->done_ptr);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -354,6 +705,7 @@ namespace
     a.m = m;
     a.Y = Y;
     a.partials = partials;
+    a.done = ctx->done_ptr;
     const int hp = m / 2;
     const int tpr = hp <= 4 ? 4 : (hp <= 8 ? 8 : (hp <= 16 ? 16 : 32));
     const int rpb = 256 / tpr;
@@ -504,6 +856,7 @@ namespace
     a.m = m;
     a.Y = Y;
     a.partials = partials;
+    a.done = ctx->done_ptr;
     constexpr size_t smem = de::spmm_staged_smem_bytes();
     const int grid = std::min(S.nblocks, ctx->sm_count * 3); // 3 resident CTAs per SM
     const bool halo = A->n_halo > 0;
@@ -546,14 +899,236 @@ namespace
     return DE_OK;
   }
 
+  /** BRB form of the matrix. The host only plans which rows form the tiles (brb::plan: pattern detection on a few
+   *  sample rows + O(n) index arithmetic); the blobs are built on the device from the CSR arrays already uploaded
+   *  (kernels_brb_build.cuh: COUNT pass -> offsets on the host -> FILL pass). A matrix the format cannot represent
+   *  (or an empty one) simply keeps the CSR kernels: not an error. */
+  int build_brb(de_context *ctx, de_matrix *A, long long n, long long ncols, const int64_t *rowptr, const int64_t *col,
+                const double *val)
+  {
+    BrbDevice &B = A->brb;
+    B.release();
+    if (n <= 0 || rowptr[n] <= 0)
+      return DE_OK;
+    static_assert(sizeof(de::brb::TileDesc) == sizeof(int4), "tile descriptors are loaded as int4");
+    de::brb::Plan P;
+    int first = 0;
+    int *d_rows = nullptr, *d_cut = nullptr;
+    int4 *d_info = nullptr, *d_place = nullptr;
+    auto cleanup = [&]()
+    {
+      dev_free(d_rows);
+      dev_free(d_cut);
+      dev_free(d_info);
+      dev_free(d_place);
+      d_rows = d_cut = nullptr;
+      d_info = d_place = nullptr;
+    };
+    struct Scope
+    {
+      decltype(cleanup) &f;
+      ~Scope() { f(); }
+    } scope{cleanup};
+    while (de::brb::plan(n, ncols, rowptr, col, val, n, first, P))
+    {
+      first = P.next;
+      cleanup();
+      const int ntiles = (int)P.order.tilecut.size() - 1;
+      if (ntiles <= 0)
+        continue;
+      DE_TRY(dev_alloc(ctx, &d_rows, P.order.rows.size()));
+      DE_TRY(dev_alloc(ctx, &d_cut, P.order.tilecut.size()));
+      DE_TRY(dev_alloc(ctx, &d_info, (size_t)ntiles));
+      DE_TRY(dev_alloc(ctx, &d_place, (size_t)ntiles));
+      DE_CUDA(ctx, cudaMemcpyAsync(d_rows, P.order.rows.data(), P.order.rows.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      DE_CUDA(ctx, cudaMemcpyAsync(d_cut, P.order.tilecut.data(), P.order.tilecut.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      de::BrbBuildArgs a{};
+      a.ntiles = ntiles;
+      a.tilecut = d_cut;
+      a.rows = d_rows;
+      a.rowptr = A->rowptr;
+      a.col = A->col;
+      a.val = A->val;
+      a.n_owned = (int)n;
+      a.info = d_info;
+      {
+        ProfScope prof(ctx, DE_PROF_MISC);
+        de::brb_build_kernel<false><<<ntiles, de::kBldThreads, 0, ctx->stream>>>(a);
+      }
+      DE_LAUNCH_CHECK(ctx);
+      std::vector<int4> info((size_t)ntiles);
+      DE_CUDA(ctx, cudaMemcpyAsync(info.data(), d_info, info.size() * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
+      DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      // sizes -> placement (tile order of the plan); the SpMM kernel sees the tiles interior-first
+      std::vector<int4> place((size_t)ntiles);
+      size_t blob16 = 0, ucols = 0;
+      int max_len16 = 0, max_u = 0;
+      long long nsteps = 0, nvals = 0;
+      bool ok = true;
+      for (int t = 0; t < ntiles && ok; ++t)
+      {
+        const int nb = P.order.tilecut[t + 1] - P.order.tilecut[t];
+        const int4 f = info[t];
+        if (f.w & 2)
+        {
+          ok = false;
+          break;
+        }
+        const size_t words = (((size_t)4 + (nb + 1) + 8 * (size_t)nb + 3) & ~(size_t)3) + 4 * (size_t)f.x + (((size_t)2 * f.y + 3) & ~(size_t)3);
+        const int len16 = (int)(words / 4);
+        place[t] = make_int4((int)blob16, len16, (int)ucols, f.z);
+        blob16 += (size_t)len16;
+        ucols += (size_t)f.z;
+        max_len16 = std::max(max_len16, len16);
+        max_u = std::max(max_u, f.z);
+        nsteps += f.x;
+        nvals += f.y;
+        if (blob16 >= ((size_t)1 << 31) || ucols >= ((size_t)1 << 31))
+          ok = false;
+      }
+      if (!ok || !de::brb::fits_budget(max_len16, max_u))
+        continue; // next candidate (smaller tiles / consecutive rows)
+      DE_TRY(dev_alloc(ctx, &B.blob, blob16 + 4));
+      DE_TRY(dev_alloc(ctx, &B.ucol, ucols + 64));
+      DE_TRY(dev_alloc(ctx, &B.tile, (size_t)ntiles));
+      DE_CUDA(ctx, cudaMemsetAsync(B.blob, 0, (blob16 + 4) * sizeof(int4), ctx->stream));
+      DE_CUDA(ctx, cudaMemcpyAsync(d_place, place.data(), place.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+      a.place = d_place;
+      a.blob = reinterpret_cast<int *>(B.blob);
+      a.ucol = B.ucol;
+      {
+        ProfScope prof(ctx, DE_PROF_MISC);
+        de::brb_build_kernel<true><<<ntiles, de::kBldThreads, 0, ctx->stream>>>(a);
+      }
+      DE_LAUNCH_CHECK(ctx);
+      std::vector<int4> tiles;
+      tiles.reserve((size_t)ntiles);
+      int n_interior = 0;
+      for (int pass = 0; pass < 2; ++pass)
+      {
+        for (int t = 0; t < ntiles; ++t)
+          if (((info[t].w & 1) != 0) == (pass == 1))
+            tiles.push_back(place[t]);
+        if (pass == 0)
+          n_interior = (int)tiles.size();
+      }
+      DE_CUDA(ctx, cudaMemcpyAsync(B.tile, tiles.data(), tiles.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+      DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // host vectors die here
+      B.ntiles = ntiles;
+      B.n_interior = n_interior;
+      B.max_len16 = max_len16;
+      B.max_u = max_u;
+      B.nblocks = (long long)(P.order.rows.size() / 8);
+      B.nsteps = nsteps;
+      B.nvals = nvals;
+      B.grid = P.grid;
+      B.tw = P.tw;
+      B.th = P.th;
+      B.td = P.td;
+      B.blob16 = blob16;
+      B.nucol = ucols;
+      B.valid = true;
+      return DE_OK;
+    }
+    return DE_OK;
+  }
+
+  /** AUTO policy (measured, profiles/r01_spmm_lab_*.log): the BRB kernel wins for long rows at every width (27-point:
+   *  1.5-2.4x) and for short rows from m = 32 up; narrow blocks on a 7-point matrix leave the tensor-core steps mostly
+   *  zero-filled and the CSR kernel is faster there. */
+  inline bool brb_usable(const de_matrix *A, int m)
+  {
+    if (!A->brb.valid || A->spmm_format == DE_SPMM_CSR || m % 8 != 0 || m < 8 || m > DE_MAX_COLS)
+      return false;
+    if (A->spmm_format == DE_SPMM_BRB)
+      return true;
+    return m >= 32 || A->nnz >= 12 * A->n;
+  }
+
+  constexpr int kBrbMaxSmem = 227 * 1024;
+
+  template <int NP, bool DOT, bool HALO>
+  int launch_brb_pass(de_context *ctx, const de::BrbArgs &a, int grid)
+  {
+    static bool cfg = false; // one per instantiation
+    if (!cfg)
+    {
+      DE_CUDA(ctx, cudaFuncSetAttribute(de::spmm_brb_kernel<NP, DOT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrbMaxSmem));
+      cfg = true;
+    }
+    const size_t smem = de::spmm_brb_smem_bytes(NP, a.blob_cap16, a.xs_cap, a.stages);
+    de::spmm_brb_kernel<NP, DOT, HALO><<<grid, de::kBrbThreads, smem, ctx->stream>>>(a);
+    DE_LAUNCH_CHECK(ctx);
+    return DE_OK;
+  }
+
+  /** Y = A X on tiles [t0, t0 + nt) of the BRB form. m columns are covered by passes of 32 / 16 / 8 columns (one
+   *  kernel launch each; every pass re-streams the matrix blobs, so m = 64 costs two passes). */
+  template <bool DOT>
+  int launch_spmm_brb(de_context *ctx, const de_matrix *A, int t0, int nt, const double *X, double *Y, int m, double *partials,
+                      int *grid_out)
+  {
+    *grid_out = 0;
+    if (nt <= 0)
+      return DE_OK;
+    const BrbDevice &B = A->brb;
+    const int grid = std::min(nt, ctx->sm_count);
+    const bool halo = A->n_halo > 0;
+    ProfScope prof(ctx, DE_PROF_SPMM);
+    for (int c0 = 0; c0 < m;)
+    {
+      const int left = (m - c0) / 8;
+      const int np = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+      de::BrbArgs a;
+      a.ntiles = nt;
+      a.n = A->n;
+      a.tile = B.tile + t0;
+      a.blob = B.blob;
+      a.ucol = B.ucol;
+      a.X = X + c0;
+      a.H = A->halo_buf ? A->halo_buf + c0 : nullptr;
+      a.n_owned = (int)A->n;
+      a.ldx = m;
+      a.Y = Y + c0;
+      a.partials = partials ? partials + c0 : nullptr;
+      a.pstride = m;
+      a.blob_cap16 = B.max_len16;
+      a.xs_cap = B.max_u;
+      a.done = ctx->done_ptr;
+      int stages = de::kBrbMaxStages;
+      while (stages > 2 && de::spmm_brb_smem_bytes(np, a.blob_cap16, a.xs_cap, stages) > (size_t)kBrbMaxSmem)
+        --stages;
+      a.stages = stages;
+      if (de::spmm_brb_smem_bytes(np, a.blob_cap16, a.xs_cap, stages) > (size_t)kBrbMaxSmem)
+        return set_error(ctx, DE_ERR_UNSUPPORTED, "BRB tile does not fit in shared memory");
+#define DE_BRB(NPV)                                                       \
+  {                                                                       \
+    if (halo)                                                             \
+      DE_TRY((launch_brb_pass<NPV, DOT, true>(ctx, a, grid)));            \
+    else                                                                  \
+      DE_TRY((launch_brb_pass<NPV, DOT, false>(ctx, a, grid)));           \
+  }
+      if (np == 4)
+        DE_BRB(4)
+      else if (np == 2)
+        DE_BRB(2)
+      else
+        DE_BRB(1)
+#undef DE_BRB
+      c0 += 8 * np;
+    }
+    *grid_out = grid;
+    return DE_OK;
+  }
+
   int ensure_halo_buffers(de_context *ctx, de_matrix *A, int m)
   {
     if (A->buf_m >= m)
       return DE_OK;
     if (A->send_buf)
-      cudaFree(A->send_buf);
+      dev_free(A->send_buf);
     if (A->halo_buf)
-      cudaFree(A->halo_buf);
+      dev_free(A->halo_buf);
     A->send_buf = A->halo_buf = nullptr;
     DE_TRY(dev_alloc(ctx, &A->send_buf, (size_t)A->n_send * m));
     DE_TRY(dev_alloc(ctx, &A->halo_buf, (size_t)A->n_halo * m));
@@ -572,7 +1147,9 @@ namespace
     const bool dist = ctx->nranks > 1 && (A->n_halo > 0 || A->n_send > 0);
     if (!dist)
     {
-      if (A->st_all.valid && staged_usable(A, m))
+      if (brb_usable(A, m))
+        DE_TRY(launch_spmm_brb<DOT>(ctx, A, 0, A->brb.ntiles, X, Y, m, ctx->partials, &g1));
+      else if (A->st_all.valid && staged_usable(A, m))
         DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_all, X, Y, m, ctx->partials, &g1));
       else
         DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, nullptr, A->n, ctx->partials, &g1));
@@ -605,12 +1182,18 @@ namespace
       DE_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
       const bool staged = staged_usable(A, m) && (A->st_interior.valid || A->n_interior == 0) &&
                           (A->st_boundary.valid || A->n_boundary == 0);
-      if (staged)
+      const bool brb = brb_usable(A, m);
+      if (brb)
+        DE_TRY(launch_spmm_brb<DOT>(ctx, A, 0, A->brb.n_interior, X, Y, m, ctx->partials, &g1));
+      else if (staged)
         DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_interior, X, Y, m, ctx->partials, &g1));
       else
         DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->interior, A->n_interior, ctx->partials, &g1));
       DE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
-      if (staged)
+      if (brb)
+        DE_TRY(launch_spmm_brb<DOT>(ctx, A, A->brb.n_interior, A->brb.ntiles - A->brb.n_interior, X, Y, m,
+                                    ctx->partials + (size_t)g1 * m, &g2));
+      else if (staged)
         DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_boundary, X, Y, m, ctx->partials + (size_t)g1 * m, &g2));
       else
         DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->boundary, A->n_boundary, ctx->partials + (size_t)g1 * m, &g2));
@@ -669,6 +1252,7 @@ namespace
     const long long ntiles = (a.n + C::TR - 1) / C::TR;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * ctas_per_sm));
     a.partials = ctx->partials;
+    a.done = ctx->done_ptr;
     {
       ProfScope prof(ctx, DO_UPDATE ? DE_PROF_UPDATE : DE_PROF_GRAM);
       de::tall_skinny_kernel<M, DO_UPDATE, DO_GRAM, UPPER, SAME><<<grid, C::THREADS, smem, ctx->stream>>>(a);
@@ -836,7 +1420,8 @@ namespace
   int chol_inverse(de_context *ctx, int m, const double *G, double *Rinv, double *info, int *identity_flag = nullptr)
   {
     ProfScope prof(ctx, DE_PROF_SMALL);
-    de::chol_inverse_kernel<<<1, 256, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag);
+    de::chol_inverse_kernel<<<1, 256, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag,
+                                                        const_cast<int *>(ctx->done_ptr));
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -984,12 +1569,12 @@ namespace
 
   void free_schedule(TrsvSchedule &S)
   {
-    cudaFree(S.rows);
-    cudaFree(S.rowptr);
-    cudaFree(S.col);
-    cudaFree(S.val);
-    cudaFree(S.level_ptr);
-    cudaFree(S.invdiag);
+    dev_free(S.rows);
+    dev_free(S.rowptr);
+    dev_free(S.col);
+    dev_free(S.val);
+    dev_free(S.level_ptr);
+    dev_free(S.invdiag);
   }
 
   template <int LC>
@@ -1028,7 +1613,7 @@ namespace
     if (F->W_m >= m)
       return DE_OK;
     if (F->W)
-      cudaFree(F->W);
+      dev_free(F->W);
     F->W = nullptr;
     DE_TRY(dev_alloc(ctx, &F->W, (size_t)F->n * m));
     F->W_m = m;
@@ -1065,7 +1650,7 @@ namespace
     if (ctx->stage_bytes >= bytes)
       return DE_OK;
     if (ctx->stage)
-      cudaFree(ctx->stage);
+      dev_free(ctx->stage);
     ctx->stage = nullptr;
     ctx->stage_bytes = 0;
     DE_TRY(dev_alloc(ctx, (char **)&ctx->stage, bytes));
@@ -1091,7 +1676,8 @@ namespace
     if (bytes == 0)
       return DE_OK;
     DE_TRY(ensure_stage(ctx, bytes));
-    DE_CUDA(ctx, cudaMemcpyAsync(ctx->stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the staging block may still be read by earlier work
+    DE_TRY(upload_parallel(ctx, reinterpret_cast<double *>(ctx->stage), host, (size_t)n * m));
     return convert_layout(ctx, n, m, ctx->stage, dst, 1);
   }
 
@@ -1110,9 +1696,7 @@ namespace
       de::extract_columns_kernel<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, m, nev, Q, ctx->stage);
     }
     DE_LAUNCH_CHECK(ctx);
-    DE_CUDA(ctx, cudaMemcpyAsync(evec, ctx->stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return DE_OK;
+    return download_parallel(ctx, evec, ctx->stage, bytes);
   }
 
   struct ScopedBlocks
@@ -1121,7 +1705,7 @@ namespace
     ~ScopedBlocks()
     {
       for (double *q : p)
-        cudaFree(q);
+        dev_free(q);
     }
     int alloc(de_context *ctx, double **out, size_t count)
     {
@@ -1194,6 +1778,9 @@ extern "C"
               cudaMemset(ctx->dflags, 0, 4 * sizeof(int)) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->hsmall, kSmall * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->hstatus, sizeof(int)) == cudaSuccess &&
+              cudaMallocHost((void **)&ctx->hflags, 8 * sizeof(int)) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_poll[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_poll[1], cudaEventDisableTiming) == cudaSuccess &&
               cudaMemset(ctx->dstatus, 0, sizeof(int)) == cudaSuccess;
     if (!ok)
     {
@@ -1218,15 +1805,23 @@ extern "C"
     }
     for (cudaEvent_t e : ctx->prof_pool)
       cudaEventDestroy(e);
-    cudaFree(ctx->partials);
-    cudaFree(ctx->dsmall);
-    cudaFree(ctx->dstatus);
-    cudaFree(ctx->dflags);
-    cudaFree(ctx->stage);
+    dev_free(ctx->partials);
+    dev_free(ctx->dsmall);
+    dev_free(ctx->dstatus);
+    dev_free(ctx->dflags);
+    dev_free(ctx->stage);
     if (ctx->hsmall)
       cudaFreeHost(ctx->hsmall);
     if (ctx->hstatus)
       cudaFreeHost(ctx->hstatus);
+    if (ctx->hflags)
+      cudaFreeHost(ctx->hflags);
+    for (cudaEvent_t e : ctx->ev_poll)
+      if (e)
+        cudaEventDestroy(e);
+    dev_free(ctx->dconv);
+    xfer_destroy(ctx);
+    dev_cache_trim(ctx->device, ctx->stream);
     if (ctx->ev_pack)
       cudaEventDestroy(ctx->ev_pack);
     if (ctx->ev_halo)
@@ -1252,7 +1847,9 @@ extern "C"
   {
     if (!ctx)
       return set_error(nullptr, DE_ERR_INVALID, "null context");
+    // enable: 0 = off, 1 = every category, otherwise a bit mask of categories shifted left by one (2 << DE_PROF_SPMM ...)
     ctx->profiling = enable != 0;
+    ctx->prof_mask = (enable == 0 || enable == 1) ? ~0u : ((unsigned)enable >> 1);
     if (ctx->profiling)
     {
       // events are created up front so that no cudaEventCreate happens inside a timed region
@@ -1353,15 +1950,19 @@ extern "C"
       return set_error(ctx, DE_ERR_UNSUPPORTED, "matrix too large for 32-bit indices on one GPU");
     if (rowptr[0] != 0 || rowptr[n] != nnz)
       return set_error(ctx, DE_ERR_INVALID, "de_matrix_create: rowptr does not match nnz");
-    for (long long k = 0; k < nnz; ++k)
-      if (col[k] < 0 || col[k] >= ncols)
-        return set_error(ctx, DE_ERR_INVALID, "de_matrix_create: column index out of range");
     A->n = n;
     A->nnz = nnz;
-    DE_TRY(upload_converted(ctx, &A->rowptr, rowptr, (size_t)n + 1));
-    DE_TRY(upload_converted(ctx, &A->col, col, (size_t)nnz));
+    // 16 bytes of tail padding: the staged kernels copy 16-byte chunks
+    DE_TRY(dev_alloc(ctx, &A->rowptr, (size_t)n + 1 + 4));
+    DE_TRY(dev_alloc(ctx, &A->col, (size_t)nnz + 4));
     DE_TRY(dev_alloc(ctx, &A->val, (size_t)nnz + 2));
-    DE_CUDA(ctx, cudaMemcpyAsync(A->val, val, sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx->stream));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // recycled blocks: their previous users are done
+    long long range[2];
+    DE_TRY(upload_parallel(ctx, A->rowptr, rowptr, (size_t)n + 1));
+    DE_TRY(upload_parallel(ctx, A->col, col, (size_t)nnz, range));
+    if (nnz > 0 && (range[0] < 0 || range[1] >= ncols))
+      return set_error(ctx, DE_ERR_INVALID, "de_matrix_create: column index out of range");
+    DE_TRY(upload_parallel(ctx, A->val, val, (size_t)nnz));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return DE_OK;
   }
@@ -1378,6 +1979,8 @@ extern "C"
     int s = matrix_upload(ctx, n, n, nnz, rowptr, col, val, A);
     if (s == DE_OK)
       s = build_staged_all(ctx, A, rowptr);
+    if (s == DE_OK)
+      s = build_brb(ctx, A, n, n, rowptr, col, val);
     if (s != DE_OK)
     {
       de_matrix_destroy(A);
@@ -1448,6 +2051,8 @@ extern "C"
       return fail(s);
     if ((s = build_staged_subset(ctx, bd, rowptr, col_local, val, A->st_boundary)) != DE_OK)
       return fail(s);
+    if ((s = build_brb(ctx, A, n_owned, n_owned + n_halo, rowptr, col_local, val)) != DE_OK)
+      return fail(s);
     *out = A;
     return DE_OK;
   }
@@ -1457,17 +2062,18 @@ extern "C"
     if (!A)
       return DE_OK;
     cudaSetDevice(A->ctx->device);
-    cudaFree(A->rowptr);
-    cudaFree(A->col);
-    cudaFree(A->val);
-    cudaFree(A->send_rows);
-    cudaFree(A->interior);
-    cudaFree(A->boundary);
-    cudaFree(A->send_buf);
-    cudaFree(A->halo_buf);
+    dev_free(A->rowptr);
+    dev_free(A->col);
+    dev_free(A->val);
+    dev_free(A->send_rows);
+    dev_free(A->interior);
+    dev_free(A->boundary);
+    dev_free(A->send_buf);
+    dev_free(A->halo_buf);
     A->st_all.release();
     A->st_interior.release();
     A->st_boundary.release();
+    A->brb.release();
     delete A;
     return DE_OK;
   }
@@ -1480,6 +2086,153 @@ extern "C"
       *n_owned = A->n;
     if (nnz)
       *nnz = A->nnz;
+    return DE_OK;
+  }
+
+  int de_brb_format_check(int64_t n, int64_t ncols, int64_t n_owned, const int64_t *rowptr, const int64_t *col,
+                          const double *val, int nthreads, int64_t *info8, double *max_abs_diff)
+  {
+    if (n < 0 || ncols < 0 || !rowptr || !info8 || !max_abs_diff)
+      return set_error(nullptr, DE_ERR_INVALID, "de_brb_format_check: bad arguments");
+    for (int i = 0; i < 8; ++i)
+      info8[i] = 0;
+    *max_abs_diff = 0.0;
+    de::brb::Format F;
+    if (n == 0 || !de::brb::build(n, ncols, rowptr, col, val, n_owned, F, nthreads) || !F.valid)
+      return DE_OK; // info8[0] == 0: no BRB form
+    info8[0] = 1;
+    info8[1] = F.grid ? 1 : 0;
+    info8[2] = F.ntiles;
+    info8[3] = F.n_interior;
+    info8[4] = F.nblocks;
+    info8[5] = F.nsteps;
+    info8[6] = F.max_u;
+    info8[7] = (int64_t)F.tw | ((int64_t)F.th << 16) | ((int64_t)F.td << 32);
+    // decode every tile exactly as the kernel does and apply it to a probe vector
+    auto probe = [](int64_t c) { return 1.0 + (double)((c * 2654435761ull) % 1021) / 1021.0; };
+    std::vector<double> y((size_t)n, 0.0);
+    std::vector<char> seen((size_t)n, 0);
+    for (const de::brb::TileDesc &d : F.tile)
+    {
+      const int *h = &F.blob[(size_t)d.blob16 * 4];
+      const int nb = h[0], ns = h[1];
+      const int *blkstep = h + 4, *blkrows = blkstep + nb + 1;
+      const int o_step = (4 + (nb + 1) + 8 * nb + 3) & ~3;
+      const int *st = h + o_step;
+      const double *v = reinterpret_cast<const double *>(h + o_step + 4 * ns);
+      if (d.nu != h[3] || (size_t)d.len16 * 4 < (size_t)o_step + 4 * (size_t)ns + 2 * (size_t)h[2])
+        return set_error(nullptr, DE_ERR_INVALID, "de_brb_format_check: inconsistent tile header");
+      for (int b = 0; b < nb; ++b)
+      {
+        for (int g = 0; g < 8; ++g)
+          if (blkrows[8 * b + g] >= 0)
+            seen[blkrows[8 * b + g]]++;
+        for (int q = blkstep[b]; q < blkstep[b + 1]; ++q)
+        {
+          const unsigned lc[4] = {(unsigned)st[4 * q] & 0xffffu, (unsigned)st[4 * q] >> 16, (unsigned)st[4 * q + 1] & 0xffffu,
+                                  (unsigned)st[4 * q + 1] >> 16};
+          const unsigned mask = (unsigned)st[4 * q + 2];
+          int k = st[4 * q + 3];
+          for (int bit = 0; bit < 32; ++bit)
+            if ((mask >> bit) & 1u)
+            {
+              const int row = blkrows[8 * b + bit / 4];
+              if (row < 0 || row >= n || (int)lc[bit % 4] >= d.nu)
+                return set_error(nullptr, DE_ERR_INVALID, "de_brb_format_check: entry outside its tile");
+              y[row] += v[k++] * probe(F.ucol[(size_t)d.ucol0 + lc[bit % 4]]);
+            }
+        }
+      }
+    }
+    double mx = 0.0;
+    for (int64_t r = 0; r < n; ++r)
+    {
+      if (seen[r] != 1)
+        return set_error(nullptr, DE_ERR_INVALID, "de_brb_format_check: a row is not covered exactly once");
+      double ref = 0.0;
+      for (int64_t k = rowptr[r]; k < rowptr[r + 1]; ++k)
+        ref += val[k] * probe(col[k]);
+      mx = std::max(mx, std::fabs(ref - y[r]));
+    }
+    *max_abs_diff = mx;
+    return DE_OK;
+  }
+
+  int de_matrix_brb_selfcheck(const de_matrix *A, int64_t n, int64_t ncols, const int64_t *rowptr, const int64_t *col,
+                              const double *val, int64_t *mismatches)
+  {
+    if (!A || !rowptr || !mismatches)
+      return set_error(A ? A->ctx : nullptr, DE_ERR_INVALID, "de_matrix_brb_selfcheck: bad arguments");
+    de_context *ctx = A->ctx;
+    *mismatches = -1;
+    if (!A->brb.valid)
+      return DE_OK;
+    if (n != A->n)
+      return set_error(ctx, DE_ERR_INVALID, "de_matrix_brb_selfcheck: matrix size does not match");
+    DE_TRY(bind_device(ctx));
+    de::brb::Format F;
+    if (!de::brb::build(n, ncols, rowptr, col, val, n, F))
+    {
+      *mismatches = -2; // the host builder found no BRB form although the device did
+      return DE_OK;
+    }
+    const BrbDevice &B = A->brb;
+    int64_t bad = 0;
+    bad += (B.ntiles != F.ntiles) + (B.n_interior != F.n_interior) + (B.max_len16 != F.max_len16) + (B.max_u != F.max_u) +
+           (B.nsteps != F.nsteps) + (B.nvals != F.nvals) + (B.blob16 * 4 != F.blob.size()) + (B.nucol != F.ucol.size());
+    if (bad == 0)
+    {
+      std::vector<int> blob(F.blob.size()), ucol(F.ucol.size());
+      std::vector<de::brb::TileDesc> tile(F.tile.size());
+      DE_CUDA(ctx, cudaMemcpy(blob.data(), B.blob, blob.size() * sizeof(int), cudaMemcpyDeviceToHost));
+      DE_CUDA(ctx, cudaMemcpy(ucol.data(), B.ucol, ucol.size() * sizeof(int), cudaMemcpyDeviceToHost));
+      DE_CUDA(ctx, cudaMemcpy(tile.data(), B.tile, tile.size() * sizeof(int4), cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < blob.size(); ++i)
+        bad += blob[i] != F.blob[i];
+      for (size_t i = 0; i < ucol.size(); ++i)
+        bad += ucol[i] != F.ucol[i];
+      bad += std::memcmp(tile.data(), F.tile.data(), tile.size() * sizeof(int4)) != 0;
+    }
+    else
+      bad += 1000000;
+    *mismatches = bad;
+    return DE_OK;
+  }
+
+  int de_matrix_set_spmm_format(de_matrix *A, int format)
+  {
+    if (!A)
+      return set_error(nullptr, DE_ERR_INVALID, "null matrix");
+    if (format != DE_SPMM_AUTO && format != DE_SPMM_CSR && format != DE_SPMM_BRB)
+      return set_error(A->ctx, DE_ERR_INVALID, "de_matrix_set_spmm_format: unknown format");
+    if (format == DE_SPMM_BRB && !A->brb.valid)
+      return set_error(A->ctx, DE_ERR_UNSUPPORTED, "de_matrix_set_spmm_format: this matrix has no BRB form");
+    A->spmm_format = format;
+    return DE_OK;
+  }
+
+  int de_matrix_spmm_info(const de_matrix *A, int *format, int64_t *tiles, int64_t *row_blocks, int64_t *steps,
+                          int64_t *union_rows_max, int *tile_shape3)
+  {
+    if (!A)
+      return set_error(nullptr, DE_ERR_INVALID, "null matrix");
+    const bool brb = A->brb.valid && A->spmm_format != DE_SPMM_CSR;
+    if (format)
+      *format = brb ? DE_SPMM_BRB : DE_SPMM_CSR;
+    if (tiles)
+      *tiles = A->brb.valid ? A->brb.ntiles : 0;
+    if (row_blocks)
+      *row_blocks = A->brb.valid ? A->brb.nblocks : 0;
+    if (steps)
+      *steps = A->brb.valid ? A->brb.nsteps : 0;
+    if (union_rows_max)
+      *union_rows_max = A->brb.valid ? A->brb.max_u : 0;
+    if (tile_shape3)
+    {
+      tile_shape3[0] = A->brb.grid ? A->brb.tw : 0;
+      tile_shape3[1] = A->brb.grid ? A->brb.th : 0;
+      tile_shape3[2] = A->brb.grid ? A->brb.td : 0;
+    }
     return DE_OK;
   }
 
@@ -1550,7 +2303,7 @@ extern "C"
     cudaError_t e = cudaMemsetAsync(X->d, 0, sizeof(double) * (size_t)n * m, ctx->stream);
     if (e != cudaSuccess)
     {
-      cudaFree(X->d);
+      dev_free(X->d);
       delete X;
       return set_error(ctx, DE_ERR_CUDA, cudaGetErrorString(e));
     }
@@ -1563,7 +2316,7 @@ extern "C"
     if (!X)
       return DE_OK;
     cudaSetDevice(X->ctx->device);
-    cudaFree(X->d);
+    dev_free(X->d);
     delete X;
     return DE_OK;
   }
@@ -1878,10 +2631,10 @@ extern "C"
     cudaSetDevice(F->ctx->device);
     free_schedule(F->L);
     free_schedule(F->U);
-    cudaFree(F->P);
-    cudaFree(F->Q);
-    cudaFree(F->rowscale);
-    cudaFree(F->W);
+    dev_free(F->P);
+    dev_free(F->Q);
+    dev_free(F->rowscale);
+    dev_free(F->W);
     delete F;
     return DE_OK;
   }
@@ -1923,11 +2676,100 @@ extern "C"
    *  and Qb the block it was mapped to (reference Q2). For the largest-eigenvalue variant the product A*Qa that
    *  the reference recomputes at the top of the loop (:78) is the one it already formed for the Rayleigh
    *  quotients (:84) -- it is reused, bit-identically. */
+  /** Asynchronous form of the StandardLargest loop (no factor): the convergence test runs on the device
+   *  (convergence_kernel) and raises a flag that turns every kernel of the iterations already enqueued into a no-op,
+   *  so the host never waits for the GPU inside the loop -- it enqueues kPollEvery iterations, requests a copy of the
+   *  flags, and only looks at the copy requested one batch earlier. The blocks are frozen in the state of the
+   *  converged iteration; which buffer is which follows from the parity of the iteration count. */
+  static int standard_core_async(de_context *ctx, const de_matrix *A, double shift, double tol, int maxiter, int m,
+                                 double *&Qa, double *&Qb, std::vector<double> &s2, int verbose, int *k_exit_out)
+  {
+    constexpr int kPollEvery = 4;
+    const long long n = A->n;
+    struct Guard
+    {
+      de_context *c;
+      ~Guard() { c->done_ptr = nullptr; }
+    } guard{ctx};
+    const size_t need = 64 + (size_t)std::max(maxiter, 2) + 1;
+    if (ctx->dconv_cap < need)
+    {
+      dev_free(ctx->dconv);
+      ctx->dconv = nullptr;
+      ctx->dconv_cap = 0;
+      DE_TRY(dev_alloc(ctx, &ctx->dconv, need));
+      ctx->dconv_cap = need;
+    }
+    double *s_prev = ctx->dconv, *hist = ctx->dconv + 64;
+    DE_TRY(reset_status(ctx));
+    DE_CUDA(ctx, cudaMemsetAsync(ctx->dflags, 0, 4 * sizeof(int), ctx->stream));
+    DE_CUDA(ctx, cudaMemsetAsync(ctx->dconv, 0, need * sizeof(double), ctx->stream));
+    ctx->done_ptr = ctx->dflags + 1;
+    DE_TRY(orthonormalize_device(ctx, n, m, Qa)); // (:69)
+    s2.assign(m, 0.0);
+    int enqueued = 0;
+    bool have_product = false, finished = false;
+    int pending[2] = {0, 0}; // poll slot in flight?
+    int slot = 0;
+    for (int k = 1; k < maxiter && !finished; ++k)
+    {
+      if (!have_product)
+        DE_TRY(spmm_device<false>(ctx, A, Qa, Qb, m)); // Qb = A Qa (:78)
+      DE_TRY(orthonormalize_device(ctx, n, m, Qb));    // (:81)
+      DE_TRY(spmm_device<true>(ctx, A, Qb, Qa, m));    // Qa = A Qb and dp = diag(Qb^T Qa) (:84-85)
+      de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(k, m, shift, tol, ctx->dDP(), s_prev, hist, ctx->dflags);
+      DE_LAUNCH_CHECK(ctx);
+      std::swap(Qa, Qb); // now Qa orthonormal, Qb = A*Qa
+      have_product = true;
+      ++enqueued;
+      if (enqueued % kPollEvery == 0)
+      {
+        // look at the copy requested one batch ago (it has almost always landed), then request a new one
+        const int prev = slot ^ 1;
+        if (pending[prev])
+        {
+          DE_CUDA(ctx, cudaEventSynchronize(ctx->ev_poll[prev]));
+          pending[prev] = 0;
+          if (ctx->hflags[4 * prev + 1] != 0)
+            finished = true;
+        }
+        DE_CUDA(ctx, cudaMemcpyAsync(ctx->hflags + 4 * slot, ctx->dflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        DE_CUDA(ctx, cudaEventRecord(ctx->ev_poll[slot], ctx->stream));
+        pending[slot] = 1;
+        slot ^= 1;
+      }
+    }
+    ctx->done_ptr = nullptr;
+    // final state
+    DE_CUDA(ctx, cudaMemcpyAsync(ctx->hflags, ctx->dflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    DE_TRY(fetch_small(ctx, s_prev, s2.data(), (size_t)m)); // synchronises; reports a failed Cholesky
+    const int done = ctx->hflags[1];
+    int k_exit = ctx->hflags[2];
+    if (!done)
+      k_exit = enqueued; // ran to maxiter - 1
+    if (maxiter <= 1)
+      k_exit = std::min(1, maxiter - 1);
+    if ((enqueued - k_exit) % 2 != 0)
+      std::swap(Qa, Qb); // iterations enqueued after convergence did nothing: undo their pointer swaps
+    if (verbose > 0 && k_exit > 1)
+    {
+      std::vector<double> h((size_t)k_exit + 1);
+      DE_CUDA(ctx, cudaMemcpy(h.data(), hist, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int k = 2; k <= k_exit; ++k)
+        std::printf("Iter=%d %g\n", k, h[k]);
+    }
+    if (k_exit_out)
+      *k_exit_out = k_exit;
+    return DE_OK;
+  }
+
   static int standard_core(de_context *ctx, const de_matrix *A, const de_factor *F, double shift, double tol,
                            int maxiter, int m, double *&Qa, double *&Qb, std::vector<double> &s2, int verbose,
                            int *k_exit_out)
   {
     const long long n = A->n;
+    if (!F && ts_supported(m) && maxiter > 1)
+      return standard_core_async(ctx, A, shift, tol, maxiter, m, Qa, Qb, s2, verbose, k_exit_out);
     DE_TRY(reset_status(ctx));
     DE_TRY(orthonormalize_device(ctx, n, m, Qa)); // (:69, :159)
     std::vector<double> s1(m, 0.0);
@@ -2000,7 +2842,7 @@ extern "C"
     std::vector<double> s2;
     int s = standard_core(ctx, A, F, shift, tol, maxiter, Q->m, Qa, Qb, s2, verbose, iterations);
     Q->d = Qa; // the buffers may have swapped roles; Q keeps the one with the result
-    cudaFree(Qb);
+    dev_free(Qb);
     if (s != DE_OK)
       return s;
     for (int j = 0; j < Q->m; ++j)

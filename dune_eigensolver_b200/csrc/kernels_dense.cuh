@@ -256,8 +256,13 @@ namespace de
   __global__ void __launch_bounds__(256) chol_inverse_kernel(int m, const double *__restrict__ G,
                                                              double *__restrict__ Rinv, int *__restrict__ status,
                                                              double *__restrict__ info,
-                                                             int *__restrict__ identity_flag)
+                                                             int *__restrict__ identity_flag,
+                                                             int *__restrict__ done = nullptr)
   {
+    // `done`: a converged driver loop turns the launch into a no-op; a failed factorisation raises it so that the
+    // iterations already enqueued do not run on garbage
+    if (done != nullptr && *done != 0)
+      return;
     // upper triangle + diagonal: R ; strict lower triangle: (R^-1)^T ; dinv: diagonal of R^-1
     __shared__ double A[DE_KERNEL_MAX_M][DE_KERNEL_MAX_M + 1];
     __shared__ double dinv[DE_KERNEL_MAX_M];
@@ -332,7 +337,11 @@ namespace de
     if (bad != 0)
     {
       if (tid == 0)
+      {
         status[0] = bad; // sticky: success never clears an earlier failure; the host resets it per driver call
+        if (done != nullptr)
+          *done = 1;
+      }
       // leave Rinv = identity so that downstream kernels stay finite; the host reports the failure
       for (int e = tid; e < m * m; e += blockDim.x)
         Rinv[e] = (e / m == e % m) ? 1.0 : 0.0;

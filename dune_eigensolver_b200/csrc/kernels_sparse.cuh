@@ -43,6 +43,7 @@ namespace de
     int m;               // columns
     double *Y;
     double *partials;    // DOT only: [gridDim.x][m] per-CTA partial dot products
+    const int *done;     // optional device flag: a driver loop has converged, the launch is a no-op
   };
 
   /** Y = A X for all m columns in ONE pass over A (the reference re-streams A once per 8-column panel,
@@ -57,6 +58,8 @@ namespace de
   template <int TPR, int VPT, bool DOT>
   __global__ void __launch_bounds__(256) spmm_kernel(const SpmmArgs a)
   {
+    if (a.done != nullptr && *a.done != 0)
+      return;
     constexpr int RPB = 256 / TPR; // rows per CTA per step
     const int t = threadIdx.x % TPR;
     const int rslot = threadIdx.x / TPR;
@@ -168,6 +171,8 @@ namespace de
   template <int TPR, bool DOT, bool HALO>
   __global__ void __launch_bounds__(256, 3) spmm_kernel_v2(const SpmmArgs a)
   {
+    if (a.done != nullptr && *a.done != 0)
+      return;
     constexpr int RPB = 256 / TPR;
     constexpr int CH = 8;
     const int t = threadIdx.x % TPR;
@@ -267,6 +272,7 @@ namespace de
     int m;
     double *Y;
     double *partials;
+    const int *done; // optional: see SpmmArgs
   };
 
   constexpr size_t spmm_staged_smem_bytes()
@@ -277,6 +283,8 @@ namespace de
   template <int TPR, bool DOT, bool HALO>
   __global__ void __launch_bounds__(256, 3) spmm_staged_kernel(const StagedArgs a)
   {
+    if (a.done != nullptr && *a.done != 0)
+      return;
     constexpr int RPB = 256 / TPR;
     constexpr int CH = 8;
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -450,8 +458,11 @@ namespace de
   /** out[e] = sum_p partials[p*len + e], p ascending: the fixed-order (deterministic) second stage of every
    *  reduction. blockDim = (32,32); each CTA owns 32 consecutive outputs. */
   __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__restrict__ partials, int nparts,
-                                                                 int len, double *__restrict__ out)
+                                                                 int len, double *__restrict__ out,
+                                                                 const int *__restrict__ done = nullptr)
   {
+    if (done != nullptr && *done != 0)
+      return;
     __shared__ double red[32][33];
     const int e = blockIdx.x * 32 + threadIdx.x;
     double s = 0.0;
@@ -467,6 +478,41 @@ namespace de
       for (int q = 0; q < 32; ++q)
         tot += red[q][threadIdx.x];
       out[e] = tot;
+    }
+  }
+
+  /** Device-side convergence test of the driver loops (reference eigensolver.hh:86-102, :176-189):
+   *  s_j = dp_j - shift, distance = max_j |s_j - s_prev_j|, s_prev <- s; iteration k > 1 with distance < tol raises
+   *  the `done` flag, after which every kernel of the iterations already enqueued returns at once.
+   *  state: flags[1] = done, flags[2] = last completed iteration; hist[k] = distance of iteration k. One CTA of 64. */
+  __global__ void __launch_bounds__(64) convergence_kernel(int k, int m, double shift, double tol, const double *__restrict__ dp,
+                                                           double *__restrict__ s_prev, double *__restrict__ hist,
+                                                           int *__restrict__ flags)
+  {
+    if (flags[1] != 0)
+      return;
+    __shared__ double red[64];
+    const int j = threadIdx.x;
+    double d = 0.0;
+    if (j < m)
+    {
+      const double s = dp[j] - shift;
+      d = fabs(s - s_prev[j]);
+      if (!(d == d))
+        d = 1.0e300; // NaN never converges
+      s_prev[j] = s;
+    }
+    red[j] = d;
+    __syncthreads();
+    if (j == 0)
+    {
+      double mx = 0.0;
+      for (int q = 0; q < 64; ++q)
+        mx = fmax(mx, red[q]);
+      hist[k] = mx;
+      flags[2] = k;
+      if (k > 1 && mx < tol)
+        flags[1] = 1;
     }
   }
 

@@ -85,6 +85,7 @@ namespace de
     int ldo;
     int upper;            // R is upper triangular: column block c only needs k < 8c+8
     const int *skip_flag; // optional: if *skip_flag != 0 the kernel returns immediately (second CholQR sweep)
+    const int *done;      // optional: a driver loop has converged, the launch is a no-op
     double *partials;     // DO_GRAM: [gridDim.x][M*M]
   };
 
@@ -103,6 +104,8 @@ namespace de
     double *tiles = smem; // STAGES x NOPS x TILE
 
     if (a.skip_flag != nullptr && *a.skip_flag != 0)
+      return;
+    if (a.done != nullptr && *a.done != 0)
       return;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -66,8 +66,13 @@ class Context:
         check(capi.lib().de_context_launch_count(self._h, C.byref(c)), self._h)
         return c.value
 
-    def set_profiling(self, on=True):
-        check(capi.lib().de_context_set_profiling(self._h, int(on)), self._h)
+    def set_profiling(self, on=True, only=None):
+        """per-kernel CUDA-event timers: all categories, or only those named in `only` (e.g. ["spmm"])"""
+        names = ["spmm", "gram", "update", "small", "dot", "trsv", "misc"]
+        code = int(bool(on))
+        if on and only:
+            code = sum(2 << names.index(c) for c in only)
+        check(capi.lib().de_context_set_profiling(self._h, code), self._h)
 
     def profile(self, reset=False):
         """{category: (total_ms, launches)} of the per-kernel CUDA-event timers (synchronises the stream)."""
@@ -130,6 +135,29 @@ class Matrix:
                                                       len(peers), capi.i32ptr(peers), i64ptr(rc), i64ptr(so),
                                                       i64ptr(sr), C.byref(h)), ctx._h)
         return cls(ctx, _handle=h)
+
+    def set_spmm_format(self, fmt):
+        """'auto' | 'csr' | 'brb' (include/dune_eigensolver_b200.h: de_matrix_set_spmm_format)"""
+        code = {"auto": capi.DE_SPMM_AUTO, "csr": capi.DE_SPMM_CSR, "brb": capi.DE_SPMM_BRB}[fmt]
+        check(capi.lib().de_matrix_set_spmm_format(self._h, code), self.ctx._h)
+
+    def spmm_info(self):
+        fmt, tiles, blocks, steps, umax = C.c_int(0), C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        shape = (C.c_int * 3)()
+        check(capi.lib().de_matrix_spmm_info(self._h, C.byref(fmt), C.byref(tiles), C.byref(blocks), C.byref(steps),
+                                             C.byref(umax), shape), self.ctx._h)
+        return {"format": {capi.DE_SPMM_CSR: "csr", capi.DE_SPMM_BRB: "brb"}[fmt.value], "tiles": tiles.value,
+                "row_blocks": blocks.value, "steps": steps.value, "union_rows_max": umax.value,
+                "tile_shape": tuple(shape)}
+
+    def brb_selfcheck(self, A, ncols=None):
+        """words in which the device-built BRB arrays differ from the host builder's (-1: no BRB form)"""
+        rp, ci, v = _csr(A)
+        n = len(rp) - 1
+        bad = C.c_int64(0)
+        check(capi.lib().de_matrix_brb_selfcheck(self._h, n, n if ncols is None else ncols, i64ptr(rp), i64ptr(ci), dptr(v),
+                                                 C.byref(bad)), self.ctx._h)
+        return bad.value
 
     def close(self):
         if self._h:

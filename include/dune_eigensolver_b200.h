@@ -67,6 +67,7 @@ int de_context_launch_count(const de_context *ctx, int64_t *count);
 #define DE_PROF_TRSV 5    /* permute / level / chain kernels of the factored apply */
 #define DE_PROF_MISC 6    /* layout conversion, halo pack, eigenvector extraction */
 #define DE_PROF_CATEGORIES 7
+/* enable: 0 = off, 1 = every category, otherwise a bit mask of categories shifted left by one (2 << DE_PROF_SPMM | ...) */
 int de_context_set_profiling(de_context *ctx, int enable);
 int de_context_profile(de_context *ctx, int category, double *total_ms, int64_t *launches, int reset);
 
@@ -94,6 +95,34 @@ int de_matrix_create_distributed(de_context *ctx, int64_t n_owned, int64_t n_hal
                                  const int64_t *send_rows, de_matrix **out);
 int de_matrix_destroy(de_matrix *A);
 int de_matrix_rows(const de_matrix *A, int64_t *n_owned, int64_t *nnz);
+
+/* SpMM kernel family used for this matrix (kernels_cpp.hh:626-657 on the device). At creation every matrix gets
+ * the CSR form; one whose 8-row blocks fit the shared-memory tile budget also gets the BRB form (8-row blocks x
+ * 4-column steps on the FP64 tensor path, X rows staged per tile; csrc/brb_format.hpp). DE_SPMM_AUTO prefers BRB.
+ * Both families compute the same products; sums differ in rounding only (different association order). */
+enum
+{
+  DE_SPMM_AUTO = 0,
+  DE_SPMM_CSR = 1,
+  DE_SPMM_BRB = 2
+};
+int de_matrix_set_spmm_format(de_matrix *A, int format);
+/* format: the family SpMM calls use now (DE_SPMM_CSR / DE_SPMM_BRB); sizes of the BRB form (0 if absent);
+ * tile_shape3: grid points per tile if a structured-grid pattern was detected, else zeros. Any pointer may be null. */
+int de_matrix_spmm_info(const de_matrix *A, int *format, int64_t *tiles, int64_t *row_blocks, int64_t *steps,
+                        int64_t *union_rows_max, int *tile_shape3);
+/* The BRB form is built ON THE DEVICE from the uploaded CSR arrays (csrc/kernels_brb_build.cuh). This check rebuilds it
+ * with the host builder (csrc/brb_format.hpp) from the caller's CSR arrays and counts the 32-bit words in which the two
+ * differ: 0 for matrices without duplicate entries. *mismatches = -1 if the matrix has no BRB form. */
+int de_matrix_brb_selfcheck(const de_matrix *A, int64_t n, int64_t ncols, const int64_t *rowptr, const int64_t *col,
+                            const double *val, int64_t *mismatches);
+/* Host-only self-check of the BRB construction (no GPU needed; not a compute path): builds the BRB form of a CSR
+ * matrix with columns [0, ncols) of which [0, n_owned) are owned, decodes every tile the way the kernel does, and
+ * returns max_i |(A_brb p)_i - (A_csr p)_i| for a fixed probe vector p. info8 = {has BRB form, structured grid
+ * detected, tiles, interior tiles, row blocks, steps, max union rows, tile shape tw | th << 16 | td << 32}.
+ * nthreads <= 0: as many builder threads as the library would use. */
+int de_brb_format_check(int64_t n, int64_t ncols, int64_t n_owned, const int64_t *rowptr, const int64_t *col,
+                        const double *val, int nthreads, int64_t *info8, double *max_abs_diff);
 
 /* Host-only halo planning for a 1-D row partition (no GPU needed; exercised by the gloo CPU tests).
  * Input: this rank's rows [row_begin,row_end) of the global CSR with GLOBAL column indices and the partition

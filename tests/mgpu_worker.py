@@ -44,15 +44,20 @@ def main():
         Xg = np.random.default_rng(3).standard_normal((n, m))
         dX = E.MultiVector.from_array(ctx, Xg[r0:r1])
         dY = E.MultiVector(ctx, r1 - r0, m)
-        # SpMM with halo exchange + fused all-reduced dots
-        dp = E.matmul_sparse_tallskinny_with_dots(dY, dA, dX)
-        Yg = gather_rows(dY.download(), part)
+        # SpMM with halo exchange + fused all-reduced dots, both kernel families (tensor-core BRB tiles / CSR rows)
         ref = orc.spmm(Aglob, Xg)
-        if np.abs(Yg - ref).max() > 1e-12 * np.abs(ref).max():
-            fails.append(("spmm", shape, float(np.abs(Yg - ref).max())))
         dref = orc.diag_dot(Xg, ref)
-        if np.abs(dp - dref).max() > 1e-11 * np.abs(dref).max():
-            fails.append(("dots", shape, float(np.abs(dp - dref).max())))
+        fmts = ["csr", "brb"] if dA.spmm_info()["tiles"] > 0 else ["csr"]
+        for fmt in fmts:
+            dA.set_spmm_format(fmt)
+            dY.upload(np.zeros((r1 - r0, m)))
+            dp = E.matmul_sparse_tallskinny_with_dots(dY, dA, dX)
+            Yg = gather_rows(dY.download(), part)
+            if np.abs(Yg - ref).max() > 1e-12 * np.abs(ref).max():
+                fails.append(("spmm", fmt, shape, float(np.abs(Yg - ref).max())))
+            if np.abs(dp - dref).max() > 1e-11 * np.abs(dref).max():
+                fails.append(("dots", fmt, shape, float(np.abs(dp - dref).max())))
+        dA.set_spmm_format("auto")
         # Gram with all-reduce
         G = E.dot_products_all_blocked(dX, dY)
         if np.abs(G - Xg.T @ ref).max() > 1e-11 * np.abs(Xg.T @ ref).max():

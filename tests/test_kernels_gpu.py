@@ -55,6 +55,98 @@ def test_spmm_matches_oracle(ctx, oracle, name, m):
     assert np.abs(dp - dref).max() <= 1e-13 * (np.abs(X) * np.abs(ref)).sum(0).max()
 
 
+BRB_MATS = {
+    "lap2d_40": lambda: M.laplacian_dirichlet_2d(40),
+    "fd3d_19x11x7": lambda: M.laplacian_fd((19, 11, 7)),
+    "fd3d_24": lambda: M.laplacian_fd((24, 24, 24)),
+    "q1_3d_13": lambda: M.q1_stiffness((13, 13, 13)),
+    "q1_3d_21x9x10": lambda: M.q1_stiffness((21, 9, 10)),
+    "q1_hc_12": lambda: M.q1_stiffness((12, 12, 12), kappa=M.high_contrast_kappa(1e6, 2)),
+}
+
+
+def _random_csr(n, per_row, seed):
+    rng = np.random.default_rng(seed)
+    rp, ci, v = [0], [], []
+    for i in range(n):
+        k = 0 if i % 17 == 3 else int(rng.integers(1, per_row + 1))  # some empty rows
+        ci.extend(np.sort(rng.choice(n, size=k, replace=False)).tolist())
+        v.extend(rng.standard_normal(k).tolist())
+        rp.append(len(ci))
+    return np.array(rp), np.array(ci), np.array(v)
+
+
+@pytest.mark.parametrize("name", sorted(BRB_MATS) + ["random_900"])
+@pytest.mark.parametrize("m", [8, 16, 24, 32, 40, 56, 64])
+def test_spmm_brb_and_csr_kernels_agree_with_oracle(ctx, oracle, name, m):
+    """both SpMM kernel families (tensor-core BRB tiles, CSR rows) against the reference kernel (kernels_cpp.hh:626-657)"""
+    A = BRB_MATS[name]() if name in BRB_MATS else _random_csr(900, 12, 5)
+    n = len(A[0]) - 1
+    X = rnd(n, m, m + 1)
+    dA, dX, dY = E.Matrix(ctx, A), E.MultiVector.from_array(ctx, X), E.MultiVector(ctx, n, m)
+    ref = oracle.spmm(A, X)
+    scale = np.abs(M.to_scipy(A)).dot(np.abs(X)).max()
+    dref = oracle.diag_dot(X, ref)
+    dscale = (np.abs(X) * np.abs(ref)).sum(0).max()
+    info = dA.spmm_info()
+    assert info["tiles"] > 0, "no BRB form was built"
+    if name in BRB_MATS:
+        assert min(info["tile_shape"][:2]) >= 2, info  # structured grid detected
+    out = {}
+    for fmt in ("brb", "csr"):
+        dA.set_spmm_format(fmt)
+        assert dA.spmm_info()["format"] == fmt
+        dY.upload(np.zeros((n, m)))
+        E.matmul_sparse_tallskinny_blocked(dY, dA, dX)
+        out[fmt] = dY.download()
+        assert np.abs(out[fmt] - ref).max() <= 1e-14 * scale, fmt
+        dY.upload(np.zeros((n, m)))
+        dp = E.matmul_sparse_tallskinny_with_dots(dY, dA, dX)
+        assert np.abs(dY.download() - ref).max() <= 1e-14 * scale, fmt
+        assert np.abs(dp - dref).max() <= 1e-13 * dscale, fmt
+    dA.set_spmm_format("auto")
+
+
+@pytest.mark.parametrize("name", sorted(BRB_MATS) + ["random_900", "lap2d_200"])
+def test_device_built_brb_arrays_equal_the_host_builder(ctx, name):
+    """the BRB form is built by CUDA kernels from the uploaded CSR; the host builder (exercised on the CPU by
+    tests/test_brb_format_cpu.py) must produce the same words"""
+    if name == "lap2d_200":
+        A = M.laplacian_dirichlet_2d(200)
+    else:
+        A = BRB_MATS[name]() if name in BRB_MATS else _random_csr(900, 12, 5)
+    dA = E.Matrix(ctx, A)
+    assert dA.spmm_info()["tiles"] > 0
+    assert dA.brb_selfcheck(A) == 0
+
+
+def test_spmm_brb_is_deterministic_and_linear(ctx):
+    """size-independent properties at a size the oracle would not finish quickly: run-to-run bit identity, and
+    A(aX + bZ) = a AX + b AZ to rounding, on the 27-point 64^3 matrix (m = 32)."""
+    A = M.q1_stiffness((64, 64, 64))
+    n, m = 64 ** 3, 32
+    dA = E.Matrix(ctx, A)
+    dA.set_spmm_format("brb")
+    X, Z = rnd(n, m, 1), rnd(n, m, 2)
+    dX, dZ, dY = E.MultiVector.from_array(ctx, X), E.MultiVector.from_array(ctx, Z), E.MultiVector(ctx, n, m)
+    E.matmul_sparse_tallskinny_blocked(dY, dA, dX)
+    y1 = dY.download()
+    E.matmul_sparse_tallskinny_blocked(dY, dA, dX)
+    assert np.array_equal(y1, dY.download())
+    E.matmul_sparse_tallskinny_blocked(dY, dA, dZ)
+    yz = dY.download()
+    dX.upload(2.0 * X - 0.5 * Z)
+    E.matmul_sparse_tallskinny_blocked(dY, dA, dX)
+    assert np.abs(dY.download() - (2.0 * y1 - 0.5 * yz)).max() <= 1e-13 * np.abs(y1).max()
+    # against the CSR kernel of the same library at full size
+    dA.set_spmm_format("csr")
+    E.matmul_sparse_tallskinny_blocked(dY, dA, dX)
+    ycsr = dY.download()
+    dA.set_spmm_format("brb")
+    E.matmul_sparse_tallskinny_blocked(dY, dA, dX)
+    assert np.abs(dY.download() - ycsr).max() <= 1e-13 * np.abs(ycsr).max()
+
+
 def test_spmm_golden(ctx, golden):
     N, m = int(golden["k_N"]), int(golden["k_m"])
     A = M.laplacian_dirichlet_2d(N)

@@ -14,6 +14,8 @@
 
 #include "../../dune_eigensolver_b200/csrc/kernels_sparse.cuh"
 #include "../../dune_eigensolver_b200/csrc/kernels_spmm_blocked.cuh"
+#include "../../dune_eigensolver_b200/csrc/brb_format.hpp"
+#include <chrono>
 
 #define CK(x)                                                                                     \
   do                                                                                              \
@@ -203,274 +205,94 @@ int main(int argc, char **argv)
     if (m == 64)
       run(de::spmm_staged_kernel<32, false, false>, "staged(v3)");
 
-    // ---- VA: staged CSR with vectorised metadata reads and predicated gathers ----
-    const size_t smem4 = de::spmm_csr4_smem_bytes();
-    auto run4 = [&](auto kern, const char *name, int ctas)
-    {
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-      const int g = std::min((int)meta.size(), sms * ctas);
-      float ms = time_it([&] { kern<<<g, 256, smem4>>>(a); }, reps);
-      check(name, ms);
-    };
-    if (m == 8)
-      run4(de::spmm_csr4_kernel<4, false, false>, "csr4 (VA)", 3);
-    if (m == 16)
-      run4(de::spmm_csr4_kernel<8, false, false>, "csr4 (VA)", 3);
-    if (m == 32)
-      run4(de::spmm_csr4_kernel<16, false, false>, "csr4 (VA)", 3);
-    if (m == 64)
-      run4(de::spmm_csr4_kernel<32, false, false>, "csr4 (VA)", 3);
   }
 
-  // ---- VB: 8-row block-sparse DMMA kernel ------------------------------------------------------------------
+  // ---- production path: BRB format (host builder) + warp-specialised tensor-core kernel ----------------------
   {
-    de::Brb8Host H;
-    de::brb8_build_host(n, rp.data(), ci.data(), v.data(), nullptr, H);
-    std::printf("brb8: %lld row blocks, %lld steps (%.2f per block), fill %.3f, matrix bytes %.3f GB (CSR %.3f GB)\n",
-                (long long)H.nblocks, (long long)H.stepmask.size(), (double)H.stepmask.size() / H.nblocks,
-                (double)nnz / (32.0 * H.stepmask.size()),
-                (20.0 * H.stepmask.size() + 8.0 * nnz + 12.0 * H.nblocks) / 1e9, (12.0 * nnz + 4.0 * n) / 1e9);
-    de::Brb8Args b{};
-    int *d_bs, *d_bv, *d_sc, *d_rows = nullptr;
-    unsigned *d_sm;
-    CK(cudaMalloc(&d_bs, H.blkstep.size() * sizeof(int)));
-    CK(cudaMalloc(&d_bv, H.blkval.size() * sizeof(int)));
-    CK(cudaMalloc(&d_sc, (H.stepcol.size() + 64) * sizeof(int)));
-    CK(cudaMalloc(&d_sm, (H.stepmask.size() + 16) * sizeof(unsigned)));
-    CK(cudaMemset(d_sc, 0, (H.stepcol.size() + 64) * sizeof(int)));
-    CK(cudaMemset(d_sm, 0, (H.stepmask.size() + 16) * sizeof(unsigned)));
-    CK(cudaMemcpy(d_bs, H.blkstep.data(), H.blkstep.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_bv, H.blkval.data(), H.blkval.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_sc, H.stepcol.data(), H.stepcol.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_sm, H.stepmask.data(), H.stepmask.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-    double *d_bval;
-    CK(cudaMalloc(&d_bval, (H.val.size() + 8) * sizeof(double)));
-    CK(cudaMemcpy(d_bval, H.val.data(), H.val.size() * sizeof(double), cudaMemcpyHostToDevice));
-    b.nblocks = H.nblocks;
-    b.n = n;
-    b.blkstep = d_bs;
-    b.blkval = d_bv;
-    b.stepcol = d_sc;
-    b.stepmask = d_sm;
-    b.val = d_bval;
-    b.blkrows = d_rows;
-    b.X = d_X;
-    b.H = nullptr;
-    b.n_owned = (int)n;
-    b.Y = d_Y;
-    b.partials = d_part;
-    auto runb = [&](auto kern, const char *name, int threads, int ctas)
+    de::brb::Format F;
+    const auto t0 = std::chrono::steady_clock::now();
+    const bool ok = de::brb::build(n, n, rp.data(), ci.data(), v.data(), n, F);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("brb: ok=%d grid=%d S=(%lld,%lld) tile %dx%dx%d, %d tiles, %.2f steps/block, fill %.3f, union/rows %.2f, max_u %d, blob %.3f GB, host build %.3f s\n",
+                (int)ok, (int)F.grid, F.S1, F.S2, F.tw, F.th, F.td, F.ntiles, (double)F.nsteps / std::max(1LL, F.nblocks),
+                (double)nnz / (32.0 * std::max(1LL, F.nsteps)), (double)F.ucol.size() / n, F.max_u, F.blob.size() * 4e-9, dt);
+    if (ok)
     {
-      const int wpb = threads / 32;
-      const int g = (int)std::min<long long>((H.nblocks + wpb - 1) / wpb, (long long)sms * ctas);
-      float ms = time_it([&] { kern<<<g, threads>>>(b); }, reps);
-      check(name, ms);
-    };
-    if (m == 8)
-      runb(de::spmm_brb8_kernel<1, false, false>, "brb8 dmma (VB)", 256, 3);
-    if (m == 16)
-      runb(de::spmm_brb8_kernel<2, false, false>, "brb8 dmma (VB)", 256, 3);
-    if (m == 32)
-    {
-      runb(de::spmm_brb8_kernel<4, false, false>, "brb8 dmma (VB) 3cta", 256, 3);
-      runb(de::spmm_brb8_kernel<4, false, false>, "brb8 dmma (VB) 2cta", 256, 2);
-      runb(de::spmm_brb8_kernel<4, false, false>, "brb8 dmma (VB) 4cta", 256, 4);
-    }
-    if (m == 64)
-      runb(de::spmm_brb8_kernel<8, false, false>, "brb8 dmma (VB)", 256, 2);
-  }
-  // ---- VC: tiled BRB8 with the X rows of a tile staged in shared memory --------------------------------------
-  {
-    const char *env = std::getenv("LAB_TILES");
-    std::string spec = env ? env : "8,6,6,8,1,1;8,6,6,2,2,2;8,5,5,2,2,2;4,8,8,2,2,2;8,4,4,2,2,2";
-    size_t pos = 0;
-    while (pos < spec.size())
-    {
-      size_t end = spec.find(';', pos);
-      if (end == std::string::npos)
-        end = spec.size();
-      int tw, th, td, bw, bh, bd;
-      if (std::sscanf(spec.substr(pos, end - pos).c_str(), "%d,%d,%d,%d,%d,%d", &tw, &th, &td, &bw, &bh, &bd) != 6)
-        break;
-      pos = end + 1;
-      std::vector<int> rows, tilecut;
-      de::brb8t_grid_order(n, N, (long long)N * N, tw, th, td, bw, bh, bd, rows, tilecut);
-      de::Brb8THost H;
-      de::brb8t_build_host(rp.data(), ci.data(), v.data(), rows, tilecut, H);
-      const size_t smem = (size_t)H.max_u * (m + 4) * sizeof(double);
-      const double mbytes = 12.0 * H.stepmask.size() + 8.0 * H.val.size() + 40.0 * H.nblocks + 4.0 * H.ucol.size();
-      std::printf("brb8t tile %dx%dx%d block %dx%dx%d: %d tiles, %d blocks, %.2f steps/block, fill %.3f, union/rows %.2f, max_u %d, smem %.1f KB, matrix bytes %.3f GB\n",
-                  tw, th, td, bw, bh, bd, H.ntiles, H.nblocks, (double)H.stepmask.size() / H.nblocks,
-                  (double)nnz / (32.0 * H.stepmask.size()), (double)H.ucol.size() / n, H.max_u, smem / 1024.0, mbytes / 1e9);
-      if (smem > 227 * 1024)
-      {
-        std::printf("  (tile does not fit in shared memory)\n");
-        continue;
-      }
-      de::Brb8TArgs b{};
-      int4 *d_tile;
-      int *d_uc, *d_bs, *d_bv, *d_rows;
-      unsigned short *d_lc;
-      unsigned *d_sm;
-      double *d_bval;
-      CK(cudaMalloc(&d_tile, H.tile.size() * sizeof(int4)));
-      CK(cudaMalloc(&d_uc, H.ucol.size() * sizeof(int)));
-      CK(cudaMalloc(&d_bs, H.blkstep.size() * sizeof(int)));
-      CK(cudaMalloc(&d_bv, H.blkval.size() * sizeof(int)));
-      CK(cudaMalloc(&d_rows, H.blkrows.size() * sizeof(int)));
-      CK(cudaMalloc(&d_lc, (H.steplc.size() + 64) * sizeof(unsigned short)));
-      CK(cudaMalloc(&d_sm, (H.stepmask.size() + 16) * sizeof(unsigned)));
-      CK(cudaMalloc(&d_bval, (H.val.size() + 8) * sizeof(double)));
-      CK(cudaMemset(d_lc, 0, (H.steplc.size() + 64) * sizeof(unsigned short)));
-      CK(cudaMemset(d_sm, 0, (H.stepmask.size() + 16) * sizeof(unsigned)));
-      CK(cudaMemcpy(d_tile, H.tile.data(), H.tile.size() * sizeof(int4), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(d_uc, H.ucol.data(), H.ucol.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(d_bs, H.blkstep.data(), H.blkstep.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(d_bv, H.blkval.data(), H.blkval.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(d_rows, H.blkrows.data(), H.blkrows.size() * sizeof(int), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(d_lc, H.steplc.data(), H.steplc.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(d_sm, H.stepmask.data(), H.stepmask.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(d_bval, H.val.data(), H.val.size() * sizeof(double), cudaMemcpyHostToDevice));
-      b.ntiles = H.ntiles;
-      b.n = n;
-      b.tile = d_tile;
-      b.ucol = d_uc;
-      b.blkstep = d_bs;
-      b.blkval = d_bv;
-      b.steplc = d_lc;
-      b.stepmask = d_sm;
-      b.val = d_bval;
-      b.blkrows = d_rows;
-      b.X = d_X;
-      b.H = nullptr;
-      b.n_owned = (int)n;
-      b.Y = d_Y;
-      b.partials = d_part;
-      auto runt = [&](auto kern, const char *name)
+      int4 *d_tile, *d_blob;
+      int *d_uc;
+      CK(cudaMalloc(&d_tile, F.tile.size() * sizeof(int4)));
+      CK(cudaMalloc(&d_blob, F.blob.size() * 4 + 64));
+      CK(cudaMalloc(&d_uc, F.ucol.size() * 4 + 64));
+      CK(cudaMemcpy(d_tile, F.tile.data(), F.tile.size() * sizeof(int4), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d_blob, F.blob.data(), F.blob.size() * 4, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(d_uc, F.ucol.data(), F.ucol.size() * 4, cudaMemcpyHostToDevice));
+      const int np = std::min(m / 8, 4), passes = m / (8 * np);
+      int stages = de::kBrbMaxStages;
+      while (stages > 2 && de::spmm_brb_smem_bytes(np, F.max_len16, F.max_u, stages) > 227 * 1024)
+        --stages;
+      const size_t smem = de::spmm_brb_smem_bytes(np, F.max_len16, F.max_u, stages);
+      const int grid = std::min(F.ntiles, sms);
+      auto launch = [&](auto kern, bool dot)
       {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
-        const int gridt = std::min(H.ntiles, sms * std::max(occ, 1));
-        float ms = time_it([&] { kern<<<gridt, 256, smem>>>(b); }, reps);
-        char nm[64];
-        std::snprintf(nm, sizeof nm, "%s occ%d", name, occ);
-        check(nm, ms);
+        for (int ps = 0; ps < passes; ++ps)
+        {
+          de::BrbArgs b{};
+          b.ntiles = F.ntiles;
+          b.n = n;
+          b.tile = d_tile;
+          b.blob = d_blob;
+          b.ucol = d_uc;
+          b.X = d_X + 8 * np * ps;
+          b.H = nullptr;
+          b.n_owned = (int)n;
+          b.ldx = m;
+          b.Y = d_Y + 8 * np * ps;
+          b.partials = d_part + 8 * np * ps;
+          b.pstride = m;
+          b.blob_cap16 = F.max_len16;
+          b.xs_cap = F.max_u;
+          b.stages = stages;
+          kern<<<grid, de::kBrbThreads, smem>>>(b);
+        }
+        (void)dot;
       };
-      if (m == 8)
-        runt(de::spmm_brb8t_kernel<1, false, false>, "brb8t (VC)");
-      if (m == 16)
-        runt(de::spmm_brb8t_kernel<2, false, false>, "brb8t (VC)");
-      if (m == 32)
-        runt(de::spmm_brb8t_kernel<4, false, false>, "brb8t (VC)");
-      if (m == 64)
-        runt(de::spmm_brb8t_kernel<8, false, false>, "brb8t (VC)");
-
-      // ---- VD: pipelined tiles ----
+      char nm[64];
+      std::snprintf(nm, sizeof nm, "brb %d stage(s) x%d pass", stages, passes);
+      float ms = 0;
+      if (np == 1)
+        ms = time_it([&] { launch(de::spmm_brb_kernel<1, false, false>, false); }, reps);
+      if (np == 2)
+        ms = time_it([&] { launch(de::spmm_brb_kernel<2, false, false>, false); }, reps);
+      if (np == 4)
+        ms = time_it([&] { launch(de::spmm_brb_kernel<4, false, false>, false); }, reps);
+      check(nm, ms);
+      if (np == 1)
+        ms = time_it([&] { launch(de::spmm_brb_kernel<1, true, false>, true); }, reps);
+      if (np == 2)
+        ms = time_it([&] { launch(de::spmm_brb_kernel<2, true, false>, true); }, reps);
+      if (np == 4)
+        ms = time_it([&] { launch(de::spmm_brb_kernel<4, true, false>, true); }, reps);
+      // dot check on the host: sum of partials vs sum_i X(i,j) Yref(i,j)
       {
-        de::Brb8PHost P;
-        de::brb8p_pack_host(H, P);
-        const size_t smemp = 2 * ((size_t)P.max_len16 * 16 + (size_t)P.max_u * (m + 4) * sizeof(double));
-        std::printf("  brb8p: blob %.3f GB, max blob %.1f KB, smem %.1f KB (2 buffers)\n", P.blob.size() * 4.0 / 1e9,
-                    P.max_len16 * 16.0 / 1024, smemp / 1024.0);
-        if (smemp <= 227 * 1024 && (size_t)P.max_u * (m / 2) <= 16 * 512)
+        std::vector<double> part((size_t)grid * m), X((size_t)n * m), Yr((size_t)n * m);
+        CK(cudaMemcpy(part.data(), d_part, part.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(X.data(), d_X, X.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(Yr.data(), d_Yref, Yr.size() * 8, cudaMemcpyDeviceToHost));
+        double worst = 0;
+        for (int j = 0; j < m; ++j)
         {
-          de::TileDesc *d_td;
-          int4 *d_blob;
-          CK(cudaMalloc(&d_td, P.tile.size() * sizeof(de::TileDesc)));
-          CK(cudaMalloc(&d_blob, P.blob.size() * 4 + 64));
-          CK(cudaMemcpy(d_td, P.tile.data(), P.tile.size() * sizeof(de::TileDesc), cudaMemcpyHostToDevice));
-          CK(cudaMemcpy(d_blob, P.blob.data(), P.blob.size() * 4, cudaMemcpyHostToDevice));
-          de::Brb8PArgs pa{};
-          pa.ntiles = H.ntiles;
-          pa.n = n;
-          pa.tile = d_td;
-          pa.blob = d_blob;
-          pa.ucol = d_uc;
-          pa.X = d_X;
-          pa.H = nullptr;
-          pa.n_owned = (int)n;
-          pa.ldx = m;
-          pa.Y = d_Y;
-          pa.partials = d_part;
-          pa.blob_cap16 = P.max_len16;
-          pa.xs_cap = P.max_u;
-          auto runp = [&](auto kern, const char *name)
-          {
-            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemp));
-            const int gridp = std::min(H.ntiles, sms);
-            float ms = time_it([&] { kern<<<gridp, de::kBrbThreads, smemp>>>(pa); }, reps);
-            check(name, ms);
-          };
-          if (m == 8)
-            runp(de::spmm_brb8p_kernel<1, false, false>, "  brb8p (VD)");
-          if (m == 16)
-            runp(de::spmm_brb8p_kernel<2, false, false>, "  brb8p (VD)");
-          if (m == 32)
-            runp(de::spmm_brb8p_kernel<4, false, false>, "  brb8p (VD)");
-          cudaFree(d_td);
-          cudaFree(d_blob);
+          double sref = 0, sg = 0;
+          for (long long i = 0; i < n; ++i)
+            sref += X[(size_t)i * m + j] * Yr[(size_t)i * m + j];
+          for (int c = 0; c < grid; ++c)
+            sg += part[(size_t)c * m + j];
+          worst = std::max(worst, std::fabs(sref - sg) / std::max(1.0, std::fabs(sref)));
         }
-        else
-          std::printf("  (does not fit)\n");
+        std::printf("  dot: max relative error %.2e\n", worst);
       }
-
-      // ---- VE: warp-specialised TMA pipeline ----
-      {
-        de::Brb8PHost P;
-        de::brb8q_pack_host(H, P);
-        const size_t per = (size_t)P.max_len16 * 16 + (size_t)P.max_u * (m + 4) * sizeof(double);
-        std::printf("  brb8q: blob %.3f GB, max blob %.1f KB, per-stage %.1f KB\n", P.blob.size() * 4.0 / 1e9, P.max_len16 * 16.0 / 1024, per / 1024.0);
-        de::TileDesc *d_td;
-        int4 *d_blob;
-        CK(cudaMalloc(&d_td, P.tile.size() * sizeof(de::TileDesc)));
-        CK(cudaMalloc(&d_blob, P.blob.size() * 4 + 64));
-        CK(cudaMemcpy(d_td, P.tile.data(), P.tile.size() * sizeof(de::TileDesc), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(d_blob, P.blob.data(), P.blob.size() * 4, cudaMemcpyHostToDevice));
-        de::Brb8PArgs pa{};
-        pa.ntiles = H.ntiles;
-        pa.n = n;
-        pa.tile = d_td;
-        pa.blob = d_blob;
-        pa.ucol = d_uc;
-        pa.X = d_X;
-        pa.H = nullptr;
-        pa.n_owned = (int)n;
-        pa.ldx = m;
-        pa.Y = d_Y;
-        pa.partials = d_part;
-        pa.blob_cap16 = P.max_len16;
-        pa.xs_cap = P.max_u;
-        auto runq = [&](auto kern, const char *name, int threads, int stages)
-        {
-          const size_t smemq = 128 + stages * per;
-          if (smemq > 227 * 1024)
-          {
-            std::printf("  %s: does not fit (%.1f KB)\n", name, smemq / 1024.0);
-            return;
-          }
-          CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemq));
-          const int gridq = std::min(H.ntiles, sms);
-          float ms = time_it([&] { kern<<<gridq, threads, smemq>>>(pa); }, reps);
-          check(name, ms);
-        };
-        if (m == 16)
-        {
-          runq(de::spmm_brb8q_kernel<2, 16, 2, false, false>, "  brb8q (VE) 16w 2st", 32 * 18, 2);
-          runq(de::spmm_brb8q_kernel<2, 16, 3, false, false>, "  brb8q (VE) 16w 3st", 32 * 18, 3);
-        }
-        if (m == 32)
-        {
-          runq(de::spmm_brb8q_kernel<4, 12, 2, false, false>, "  brb8q (VE) 12w 2st", 32 * 14, 2);
-          runq(de::spmm_brb8q_kernel<4, 16, 2, false, false>, "  brb8q (VE) 16w 2st", 32 * 18, 2);
-          runq(de::spmm_brb8q_kernel<4, 8, 2, false, false>, "  brb8q (VE) 8w 2st", 32 * 10, 2);
-          runq(de::spmm_brb8q_kernel<4, 12, 3, false, false>, "  brb8q (VE) 12w 3st", 32 * 14, 3);
-          runq(de::spmm_brb8q_kernel<4, 16, 3, false, false>, "  brb8q (VE) 16w 3st", 32 * 18, 3);
-        }
-        cudaFree(d_td);
-        cudaFree(d_blob);
-      }
-      cudaFree(d_tile); cudaFree(d_uc); cudaFree(d_bs); cudaFree(d_bv); cudaFree(d_rows); cudaFree(d_lc); cudaFree(d_sm); cudaFree(d_bval);
+      std::snprintf(nm, sizeof nm, "brb+dot %d stage(s) x%d pass", stages, passes);
+      check(nm, ms);
     }
   }
   return 0;
