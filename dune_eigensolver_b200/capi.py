@@ -55,6 +55,7 @@ SIGNATURES = {
     "de_mv_device_ptr": [_vp, _vpp],
     "de_spmm": [_vp, _vp, _vp],
     "de_spmm_diag_dot": [_vp, _vp, _vp, _dp],
+    "de_spmm_gram": [_vp, _vp, _vp, _dp, _dp],
     "de_diag_dot": [_dp, _vp, _vp],
     "de_gram": [_dp, _vp, _vp],
     "de_block_update": [_vp, _dp],

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <dlfcn.h>
 #include <limits>
@@ -44,7 +45,7 @@ namespace
 
   constexpr int kMaxPartials = 592;               // CTAs of a reduction kernel (4 per SM on 148 SMs)
   constexpr size_t kPartialDoubles = (size_t)2 * kMaxPartials * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M;
-  constexpr int kSmall = 4 * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M + 1024; // doubles of small device / pinned scratch
+  constexpr int kSmall = 5 * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M + 1024; // doubles of small device / pinned scratch
 }
 
 struct NcclApi
@@ -131,8 +132,10 @@ struct de_context
 
   double *dG() const { return dsmall; }
   double *dR() const { return dsmall + DE_KERNEL_MAX_M * DE_KERNEL_MAX_M; }
-  double *dDP() const { return dsmall + 2 * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M; }
+  double *dDP() const { return dsmall + 3 * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M; }
   double *dInfo() const { return dsmall + 2 * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M + 512; }
+  // [dp (m) | G = Y^T Y (m x m)] of the last SpMM with dot (+ Gram) epilogue; dDP() aliases its head
+  double *dDG() const { return dsmall + 3 * DE_KERNEL_MAX_M * DE_KERNEL_MAX_M; }
 };
 
 struct de_mv
@@ -1047,24 +1050,36 @@ namespace
 
   constexpr int kBrbMaxSmem = 227 * 1024;
 
-  template <int NP, bool DOT, bool HALO>
+  template <int NP, bool DOT, bool HALO, bool GRAM>
   int launch_brb_pass(de_context *ctx, const de::BrbArgs &a, int grid)
   {
     static bool cfg = false; // one per instantiation
     if (!cfg)
     {
-      DE_CUDA(ctx, cudaFuncSetAttribute(de::spmm_brb_kernel<NP, DOT, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBrbMaxSmem));
+      DE_CUDA(ctx, cudaFuncSetAttribute(de::spmm_brb_kernel<NP, DOT, HALO, GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kBrbMaxSmem));
       cfg = true;
     }
     const size_t smem = de::spmm_brb_smem_bytes(NP, a.blob_cap16, a.xs_cap, a.stages);
-    de::spmm_brb_kernel<NP, DOT, HALO><<<grid, de::kBrbThreads, smem, ctx->stream>>>(a);
+    de::spmm_brb_kernel<NP, DOT, HALO, GRAM><<<grid, de::brb_threads(GRAM), smem, ctx->stream>>>(a);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
 
+  /** The drivers could take G = Y^T Y from the SpMM epilogue instead of a separate Gram pass (de_spmm_gram does).
+   *  Measured on B200 (100^3 Q1, m = 32): the epilogue adds 0.12 ms to a 0.19 ms SpMM (20 more DMMA per row block
+   *  on accumulators that serialise, 40 more registers, 10 instead of 12 consumer warps), the separate pass costs
+   *  0.056 ms + one launch: the solve went from 22.4 to 25.9 ms. Off until the epilogue is cheaper. */
+  constexpr bool kFuseGramIntoSpmm = false;
+
+  /** can the Gram matrix Y^T Y be accumulated in the SpMM epilogue? (single pass over the columns) */
+  inline bool brb_gram_epilogue(int m) { return m == 8 || m == 16 || m == 32; }
+
   /** Y = A X on tiles [t0, t0 + nt) of the BRB form. m columns are covered by passes of 32 / 16 / 8 columns (one
-   *  kernel launch each; every pass re-streams the matrix blobs, so m = 64 costs two passes). */
-  template <bool DOT>
+   *  kernel launch each; every pass re-streams the matrix blobs, so m = 64 costs two passes).
+   *  DOT: per-CTA partials of diag(X^T Y) at partials[cta * pstride + j]; GRAM (needs brb_gram_epilogue(m)):
+   *  additionally the CTA's partial of Y^T Y at partials[cta * pstride + m + i * m + j], pstride = m + m * m. */
+  template <bool DOT, bool GRAM>
   int launch_spmm_brb(de_context *ctx, const de_matrix *A, int t0, int nt, const double *X, double *Y, int m, double *partials,
                       int *grid_out)
   {
@@ -1091,7 +1106,8 @@ namespace
       a.ldx = m;
       a.Y = Y + c0;
       a.partials = partials ? partials + c0 : nullptr;
-      a.pstride = m;
+      a.pstride = GRAM ? m + m * m : m;
+      a.gram_off = m;
       a.blob_cap16 = B.max_len16;
       a.xs_cap = B.max_u;
       a.done = ctx->done_ptr;
@@ -1101,12 +1117,12 @@ namespace
       a.stages = stages;
       if (de::spmm_brb_smem_bytes(np, a.blob_cap16, a.xs_cap, stages) > (size_t)kBrbMaxSmem)
         return set_error(ctx, DE_ERR_UNSUPPORTED, "BRB tile does not fit in shared memory");
-#define DE_BRB(NPV)                                                       \
-  {                                                                       \
-    if (halo)                                                             \
-      DE_TRY((launch_brb_pass<NPV, DOT, true>(ctx, a, grid)));            \
-    else                                                                  \
-      DE_TRY((launch_brb_pass<NPV, DOT, false>(ctx, a, grid)));           \
+#define DE_BRB(NPV)                                                             \
+  {                                                                             \
+    if (halo)                                                                   \
+      DE_TRY((launch_brb_pass<NPV, DOT, true, GRAM>(ctx, a, grid)));            \
+    else                                                                        \
+      DE_TRY((launch_brb_pass<NPV, DOT, false, GRAM>(ctx, a, grid)));           \
   }
       if (np == 4)
         DE_BRB(4)
@@ -1140,15 +1156,24 @@ namespace
    *  (pack -> NCCL send/recv over NVLink on the communication stream), run the interior rows meanwhile, then the
    *  boundary rows once the halo rows have landed. */
   template <bool DOT>
-  int spmm_device(de_context *ctx, const de_matrix *Ac, const double *X, double *Y, int m)
+  int spmm_device(de_context *ctx, const de_matrix *Ac, const double *X, double *Y, int m, bool *gram_out = nullptr)
   {
     de_matrix *A = const_cast<de_matrix *>(Ac);
     int g1 = 0, g2 = 0;
     const bool dist = ctx->nranks > 1 && (A->n_halo > 0 || A->n_send > 0);
+    // GRAM epilogue: the caller can use G = Y^T Y (in ctx->dDG() + m); only the tensor-core kernel has it
+    const bool gram = DOT && gram_out != nullptr && brb_usable(A, m) && brb_gram_epilogue(m);
+    if (gram_out)
+      *gram_out = gram;
     if (!dist)
     {
       if (brb_usable(A, m))
-        DE_TRY(launch_spmm_brb<DOT>(ctx, A, 0, A->brb.ntiles, X, Y, m, ctx->partials, &g1));
+      {
+        if (gram)
+          DE_TRY((launch_spmm_brb<DOT, DOT>(ctx, A, 0, A->brb.ntiles, X, Y, m, ctx->partials, &g1)));
+        else
+          DE_TRY((launch_spmm_brb<DOT, false>(ctx, A, 0, A->brb.ntiles, X, Y, m, ctx->partials, &g1)));
+      }
       else if (A->st_all.valid && staged_usable(A, m))
         DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_all, X, Y, m, ctx->partials, &g1));
       else
@@ -1183,16 +1208,28 @@ namespace
       const bool staged = staged_usable(A, m) && (A->st_interior.valid || A->n_interior == 0) &&
                           (A->st_boundary.valid || A->n_boundary == 0);
       const bool brb = brb_usable(A, m);
+      const size_t pstride = gram ? (size_t)m + (size_t)m * m : (size_t)m;
       if (brb)
-        DE_TRY(launch_spmm_brb<DOT>(ctx, A, 0, A->brb.n_interior, X, Y, m, ctx->partials, &g1));
+      {
+        if (gram)
+          DE_TRY((launch_spmm_brb<DOT, DOT>(ctx, A, 0, A->brb.n_interior, X, Y, m, ctx->partials, &g1)));
+        else
+          DE_TRY((launch_spmm_brb<DOT, false>(ctx, A, 0, A->brb.n_interior, X, Y, m, ctx->partials, &g1)));
+      }
       else if (staged)
         DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_interior, X, Y, m, ctx->partials, &g1));
       else
         DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->interior, A->n_interior, ctx->partials, &g1));
       DE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
       if (brb)
-        DE_TRY(launch_spmm_brb<DOT>(ctx, A, A->brb.n_interior, A->brb.ntiles - A->brb.n_interior, X, Y, m,
-                                    ctx->partials + (size_t)g1 * m, &g2));
+      {
+        if (gram)
+          DE_TRY((launch_spmm_brb<DOT, DOT>(ctx, A, A->brb.n_interior, A->brb.ntiles - A->brb.n_interior, X, Y, m,
+                                            ctx->partials + (size_t)g1 * pstride, &g2)));
+        else
+          DE_TRY((launch_spmm_brb<DOT, false>(ctx, A, A->brb.n_interior, A->brb.ntiles - A->brb.n_interior, X, Y, m,
+                                              ctx->partials + (size_t)g1 * pstride, &g2)));
+      }
       else if (staged)
         DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_boundary, X, Y, m, ctx->partials + (size_t)g1 * m, &g2));
       else
@@ -1200,11 +1237,13 @@ namespace
     }
     if (DOT)
     {
+      // dp (and G = Y^T Y when the Gram epilogue ran) are reduced, and all-reduced, as ONE vector dDG = [dp | G]
+      const int len = gram ? m + m * m : m;
       if (g1 + g2 > 0)
-        DE_TRY(reduce_partials(ctx, ctx->partials, g1 + g2, m, ctx->dDP()));
+        DE_TRY(reduce_partials(ctx, ctx->partials, g1 + g2, len, ctx->dDG()));
       else
-        DE_CUDA(ctx, cudaMemsetAsync(ctx->dDP(), 0, sizeof(double) * m, ctx->stream));
-      DE_TRY(allreduce_sum(ctx, ctx->dDP(), m));
+        DE_CUDA(ctx, cudaMemsetAsync(ctx->dDG(), 0, sizeof(double) * len, ctx->stream));
+      DE_TRY(allreduce_sum(ctx, ctx->dDG(), (size_t)len));
     }
     return DE_OK;
   }
@@ -1420,8 +1459,12 @@ namespace
   int chol_inverse(de_context *ctx, int m, const double *G, double *Rinv, double *info, int *identity_flag = nullptr)
   {
     ProfScope prof(ctx, DE_PROF_SMALL);
-    de::chol_inverse_kernel<<<1, 256, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag,
-                                                        const_cast<int *>(ctx->done_ptr));
+    if (m <= 32)
+      de::chol_inverse2_kernel<32><<<1, 1024, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag,
+                                                                const_cast<int *>(ctx->done_ptr));
+    else
+      de::chol_inverse2_kernel<64><<<1, 1024, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag,
+                                                                const_cast<int *>(ctx->done_ptr));
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -1430,13 +1473,15 @@ namespace
    *  kernels_cpp.hh:180-351). Two CholQR sweeps over the WHOLE block: G = X^T X, R = chol(G), X <- X R^-1.
    *  The triangular factor of a full-rank block is unique, so the result equals the reference's block
    *  Gram-Schmidt up to round-off; the second sweep restores orthogonality to O(eps) for cond(X) < ~1e7. */
-  int orthonormalize_device(de_context *ctx, long long n, int m, double *X)
+  int orthonormalize_device(de_context *ctx, long long n, int m, double *X, const double *G_ready = nullptr)
   {
     if (ts_supported(m))
     {
-      // sweep 1: G = X^T X ; R1 = chol(G) ; X <- X R1^-1 fused with G2 = X^T X of the result
-      DE_TRY(gram_device(ctx, m, n, X, m, X, m, true, ctx->dG()));
-      DE_TRY(chol_inverse(ctx, m, ctx->dG(), ctx->dR(), nullptr, nullptr));
+      // sweep 1: G = X^T X (already known if the SpMM that produced X ran its Gram epilogue) ; R1 = chol(G) ;
+      // X <- X R1^-1 fused with G2 = X^T X of the result
+      if (G_ready == nullptr)
+        DE_TRY(gram_device(ctx, m, n, X, m, X, m, true, ctx->dG()));
+      DE_TRY(chol_inverse(ctx, m, G_ready ? G_ready : ctx->dG(), ctx->dR(), nullptr, nullptr));
       de::TsArgs a{};
       a.n = n;
       a.X = X;
@@ -2436,6 +2481,29 @@ extern "C"
     return fetch_small(ctx, ctx->dDP(), dp_host, X->m);
   }
 
+  int de_spmm_gram(de_mv *Y, const de_matrix *A, const de_mv *X, double *dp_host, double *G_host)
+  {
+    DE_TRY(check_spmm_shapes(Y ? Y->ctx : nullptr, "de_spmm_gram", Y, A, X));
+    if (!dp_host || !G_host)
+      return set_error(Y->ctx, DE_ERR_INVALID, "de_spmm_gram: null output");
+    de_context *ctx = Y->ctx;
+    DE_TRY(bind_device(ctx));
+    DE_TRY(reset_status(ctx));
+    const int m = X->m;
+    bool fused = false;
+    DE_TRY(spmm_device<true>(ctx, A, X->d, Y->d, m, &fused));
+    const double *G = ctx->dDG() + m;
+    if (!fused)
+    {
+      // no Gram epilogue for this matrix / width: a separate pass over Y
+      DE_TRY(gram_device(ctx, m, Y->n, Y->d, m, Y->d, m, true, ctx->dG()));
+      G = ctx->dG();
+    }
+    DE_TRY(fetch_small(ctx, ctx->dDP(), dp_host, (size_t)m));
+    DE_CUDA(ctx, cudaMemcpy(G_host, G, sizeof(double) * m * m, cudaMemcpyDeviceToHost));
+    return DE_OK;
+  }
+
   int de_diag_dot(double *dp_host, const de_mv *X, const de_mv *Y)
   {
     if (!dp_host || !X || !Y)
@@ -2709,14 +2777,18 @@ extern "C"
     s2.assign(m, 0.0);
     int enqueued = 0;
     bool have_product = false, finished = false;
+    bool have_gram = false; // dDG() + m holds Qb^T Qb of the block the next orthonormalisation works on
     int pending[2] = {0, 0}; // poll slot in flight?
+    const auto t_enq0 = std::chrono::steady_clock::now();
+    double t_wait = 0.0;
     int slot = 0;
     for (int k = 1; k < maxiter && !finished; ++k)
     {
       if (!have_product)
         DE_TRY(spmm_device<false>(ctx, A, Qa, Qb, m)); // Qb = A Qa (:78)
-      DE_TRY(orthonormalize_device(ctx, n, m, Qb));    // (:81)
-      DE_TRY(spmm_device<true>(ctx, A, Qb, Qa, m));    // Qa = A Qb and dp = diag(Qb^T Qa) (:84-85)
+      DE_TRY(orthonormalize_device(ctx, n, m, Qb, have_gram ? ctx->dDG() + m : nullptr)); // (:81)
+      // Qa = A Qb, dp = diag(Qb^T Qa) (:84-85) and, in the same pass, G = Qa^T Qa for the next orthonormalisation
+      DE_TRY(spmm_device<true>(ctx, A, Qb, Qa, m, kFuseGramIntoSpmm ? &have_gram : nullptr));
       de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(k, m, shift, tol, ctx->dDP(), s_prev, hist, ctx->dflags);
       DE_LAUNCH_CHECK(ctx);
       std::swap(Qa, Qb); // now Qa orthonormal, Qb = A*Qa
@@ -2728,7 +2800,9 @@ extern "C"
         const int prev = slot ^ 1;
         if (pending[prev])
         {
+          const auto tw0 = std::chrono::steady_clock::now();
           DE_CUDA(ctx, cudaEventSynchronize(ctx->ev_poll[prev]));
+          t_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count();
           pending[prev] = 0;
           if (ctx->hflags[4 * prev + 1] != 0)
             finished = true;
@@ -2740,6 +2814,7 @@ extern "C"
       }
     }
     ctx->done_ptr = nullptr;
+    const double t_enq = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_enq0).count();
     // final state
     DE_CUDA(ctx, cudaMemcpyAsync(ctx->hflags, ctx->dflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DE_TRY(fetch_small(ctx, s_prev, s2.data(), (size_t)m)); // synchronises; reports a failed Cholesky
@@ -2751,6 +2826,11 @@ extern "C"
       k_exit = std::min(1, maxiter - 1);
     if ((enqueued - k_exit) % 2 != 0)
       std::swap(Qa, Qb); // iterations enqueued after convergence did nothing: undo their pointer swaps
+    if (verbose > 1)
+      std::printf("async loop: %d iterations enqueued in %.3f ms of host time (%.3f ms of it waiting for poll copies), "
+                  "drained %.3f ms later\n",
+                  enqueued, t_enq * 1e3, t_wait * 1e3,
+                  std::chrono::duration<double>(std::chrono::steady_clock::now() - t_enq0).count() * 1e3 - t_enq * 1e3);
     if (verbose > 0 && k_exit > 1)
     {
       std::vector<double> h((size_t)k_exit + 1);

@@ -368,4 +368,183 @@ namespace de
     }
   }
 
+
+  /** Second-generation Cholesky + triangular inverse of the (all-reduced) Gram matrix, same contract as
+   *  chol_inverse_kernel: Rinv = R^-1 with G = R^T R, R upper triangular with positive diagonal; a pivot
+   *  <= 4 m eps G_kk reports rank deficiency (status = k + 1, Rinv = I, `done` raised).
+   *  ncu (profiles/r01_ncu_launches_brb.csv) had the first version at 30 us per call, 13 % of a StandardLargest
+   *  iteration: integer divisions in the trailing update, three CTA barriers per pivot and a 32-thread back
+   *  substitution. Here the matrix is padded with the identity to MP x MP (MP = 32 or 64), every thread keeps its
+   *  (MP/32)^2 elements in registers, row k lives in ONE warp (its pivot is a warp shuffle away), and both phases are
+   *  rank-1 updates with ONE barrier per pivot:
+   *    factorisation   scaled row k -> shared; barrier; a_ij -= r_ki r_kj          (i > k)
+   *    inverse         Gauss-Jordan from the bottom: x_k /= r_kk; x_i -= r_ik x_k   (i < k), X starts as I
+   *  1024 threads: element (i, j) = (w + 32 a, l + 32 b) belongs to warp w, lane l, slot (a, b). */
+  template <int MP>
+  __global__ void __launch_bounds__(1024) chol_inverse2_kernel(int m, const double *__restrict__ G, double *__restrict__ Rinv,
+                                                               int *__restrict__ status, double *__restrict__ info,
+                                                               int *__restrict__ identity_flag, int *__restrict__ done)
+  {
+    constexpr int E = MP / 32;
+    if (done != nullptr && *done != 0)
+      return;
+    __shared__ double rowk[2][MP];
+    __shared__ double colk[2][MP];
+    __shared__ double dorig[MP];
+    __shared__ double redmx[32], reddev[32];
+    __shared__ int bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0)
+      bad = 0;
+
+    double r[E][E], x[E][E];
+    double mx = -1.0e300, dev = 0.0;
+#pragma unroll
+    for (int a = 0; a < E; ++a)
+#pragma unroll
+      for (int b = 0; b < E; ++b)
+      {
+        const int i = warp + 32 * a, j = lane + 32 * b;
+        double v = (i == j) ? 1.0 : 0.0; // identity padding
+        if (i < m && j < m)
+        {
+          v = (i <= j) ? G[i * m + j] : 0.0;
+          if (i < j)
+            mx = fmax(mx, v);
+          if (i <= j)
+            dev = fmax(dev, fabs(v - (i == j ? 1.0 : 0.0)));
+          if (!(v == v))
+            dev = 1.0e300; // NaN: never "identity"
+        }
+        r[a][b] = v;
+        x[a][b] = (i == j) ? 1.0 : 0.0;
+        if (i == j)
+          dorig[i] = v;
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    }
+    if (lane == 0)
+    {
+      redmx[warp] = mx;
+      reddev[warp] = dev;
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+      double t = -1.0e300, u = 0.0;
+      for (int q = 0; q < 32; ++q)
+      {
+        t = fmax(t, redmx[q]);
+        u = fmax(u, reddev[q]);
+      }
+      if (info != nullptr)
+        info[0] = (m > 1) ? t : 0.0;
+      if (identity_flag != nullptr)
+        identity_flag[0] = (u <= 1.0e-14) ? 1 : 0;
+    }
+
+    // ---- factorisation ----
+    for (int k = 0; k < MP; ++k)
+    {
+      const int ka = k >> 5, kw = k & 31, buf = k & 1;
+      if (warp == kw)
+      {
+        // this warp owns row k (slot a = ka); lane kw of slot b = ka holds the pivot
+        const double d = __shfl_sync(0xffffffffu, r[E == 1 ? 0 : ka][E == 1 ? 0 : ka], kw);
+        const bool ok = (d > 4.0 * m * 2.220446049250313e-16 * dorig[k]) && isfinite(d);
+        const double rkk = ok ? sqrt(d) : 1.0;
+        if (!ok && lane == 0)
+          bad = k + 1;
+#pragma unroll
+        for (int b = 0; b < E; ++b)
+        {
+          const int j = lane + 32 * b;
+          double v = r[E == 1 ? 0 : ka][b];
+          v = (j == k) ? rkk : (j > k ? v / rkk : 0.0);
+          r[E == 1 ? 0 : ka][b] = v;
+          rowk[buf][j] = v;
+        }
+      }
+      __syncthreads();
+      if (bad != 0)
+        break;
+#pragma unroll
+      for (int a = 0; a < E; ++a)
+#pragma unroll
+        for (int b = 0; b < E; ++b)
+        {
+          const int i = warp + 32 * a, j = lane + 32 * b;
+          if (i > k && j >= i)
+            r[a][b] = fma(-rowk[buf][i], rowk[buf][j], r[a][b]);
+        }
+    }
+    __syncthreads();
+    if (bad != 0)
+    {
+      if (tid == 0)
+      {
+        status[0] = bad; // sticky: success never clears an earlier failure; the host resets it per driver call
+        if (done != nullptr)
+          *done = 1;
+      }
+#pragma unroll
+      for (int a = 0; a < E; ++a)
+#pragma unroll
+        for (int b = 0; b < E; ++b)
+        {
+          const int i = warp + 32 * a, j = lane + 32 * b;
+          if (i < m && j < m)
+            Rinv[i * m + j] = (i == j) ? 1.0 : 0.0;
+        }
+      return;
+    }
+
+    // ---- inverse: Gauss-Jordan from the last row up ----
+    for (int k = MP - 1; k >= 0; --k)
+    {
+      const int ka = k >> 5, kw = k & 31, buf = k & 1;
+      if (warp == kw)
+      {
+        const double rkk = __shfl_sync(0xffffffffu, r[E == 1 ? 0 : ka][E == 1 ? 0 : ka], kw);
+#pragma unroll
+        for (int b = 0; b < E; ++b)
+        {
+          const double v = x[E == 1 ? 0 : ka][b] / rkk;
+          x[E == 1 ? 0 : ka][b] = v;
+          rowk[buf][lane + 32 * b] = v;
+        }
+      }
+      if (lane == kw)
+      {
+        // column k of R: element (i, k) lives in lane kw of warp i % 32, slot (i / 32, ka)
+#pragma unroll
+        for (int a = 0; a < E; ++a)
+          colk[buf][warp + 32 * a] = r[a][E == 1 ? 0 : ka];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int a = 0; a < E; ++a)
+#pragma unroll
+        for (int b = 0; b < E; ++b)
+        {
+          const int i = warp + 32 * a;
+          if (i < k)
+            x[a][b] = fma(-colk[buf][i], rowk[buf][lane + 32 * b], x[a][b]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < E; ++a)
+#pragma unroll
+      for (int b = 0; b < E; ++b)
+      {
+        const int i = warp + 32 * a, j = lane + 32 * b;
+        if (i < m && j < m)
+          Rinv[i * m + j] = (i <= j) ? x[a][b] : 0.0;
+      }
+  }
+
 } // namespace de

@@ -23,6 +23,13 @@
 // Roofline: HBM. Algorithmic bytes 12 nnz + 4 (n+1) + 16 n m; the BRB stream itself is ~9.4 bytes per nonzero.
 // Second limiter: the FP64 tensor pipe (zero fill: 43 % of the DMMA lanes carry nonzeros for a 27-point stencil).
 //
+// Operand order of the GRAM variant: the product is formed TRANSPOSED, C(8 X-columns x 8 rows) += Xt(8 x 4) * At(4 x 8):
+// the same two registers as for C = A * X, swapped in the instruction. A lane then owns a 2-row x NP-column patch of Y (rows 2k,
+// 2k+1 of the block, columns NP g .. NP g + NP - 1): its stores are contiguous per row, and -- the point -- the
+// accumulators of one quad of lanes already contain, up to a shuffle inside the quad, the operand fragments of the
+// next tensor product over the rows: the Gram matrix Y^T Y of the result (GRAM epilogue) is accumulated in the same
+// kernel, 20 extra DMMA per row block, and the eigensolver's orthonormalisation starts without its own pass over Y.
+//
 // Arithmetic: a row's products are summed in ascending column order in groups of four inside the DMMA instead of
 // one FMA chain: results agree with the CSR order to rounding (bit-identical in the lab runs). A zero pattern entry
 // multiplies an X value by 0.0, so a NaN/Inf in X reaches all 8 rows of every block that stages that X row.
@@ -143,8 +150,9 @@ namespace de
 
 
   constexpr int kBrbProducerWarps = 2;
-  constexpr int kBrbConsumerWarps = 12;
-  constexpr int kBrbThreads = 32 * (kBrbProducerWarps + kBrbConsumerWarps);
+  constexpr int kBrbConsumerWarps = 12;     // plain / DOT variants
+  constexpr int kBrbConsumerWarpsGram = 10; // GRAM variants carry 40 more accumulator registers per thread
+  constexpr int brb_threads(bool gram) { return 32 * (kBrbProducerWarps + (gram ? kBrbConsumerWarpsGram : kBrbConsumerWarps)); }
   constexpr int kBrbMaxStages = 4;
   constexpr int kBrbBarrierBytes = 128; // mbarriers in front of the stage buffers
 
@@ -161,7 +169,8 @@ namespace de
     int ldx;                  // row stride of X, H and Y in doubles
     double *Y;
     double *partials;         // DOT: per-CTA partial dot products, partials[cta * pstride + column]
-    int pstride;
+    int pstride;              //      GRAM: followed by the CTA's partial Gram matrix at partials[cta * pstride + gram_off + i * M + j]
+    int gram_off;
     int blob_cap16;           // shared-memory capacity of one stage: blob (16-byte units) ...
     int xs_cap;               // ... and staged X rows
     int stages;               // pipeline depth (2..kBrbMaxStages)
@@ -180,10 +189,12 @@ namespace de
    *    B fragment   b[p]   = X(step column k, NP g + p), p < NP                   (NP/2 128-bit shared loads)
    *    accumulators c[p]   = Y(row g, 2 k NP + p), Y(row g, (2 k + 1) NP + p)     -> the lane owns 2 NP contiguous columns
    *  i.e. panel p of the tensor product covers the X columns {NP j + p : j < 8}. */
-  template <int NP, bool DOT, bool HALO>
-  __global__ void __launch_bounds__(kBrbThreads, 1) spmm_brb_kernel(const BrbArgs a)
+  template <int NP, bool DOT, bool HALO, bool GRAM>
+  __global__ void __launch_bounds__(brb_threads(GRAM), 1) spmm_brb_kernel(const BrbArgs a)
   {
-    constexpr int NPW = kBrbProducerWarps, NCW = kBrbConsumerWarps;
+    static_assert(!GRAM || DOT, "the Gram epilogue is only built together with the dot epilogue");
+    constexpr int NPW = kBrbProducerWarps, NCW = GRAM ? kBrbConsumerWarpsGram : kBrbConsumerWarps;
+    constexpr int NT = NP * (NP + 1) / 2; // Gram tiles (p <= p') of the column groups {NP j + p}
     constexpr int M = 8 * NP;
     constexpr int LDR = M + 4; // staged row stride (doubles): see lds_frag
     extern __shared__ __align__(128) unsigned char dynq[];
@@ -207,10 +218,14 @@ namespace de
     }
     __syncthreads();
 
-    double dacc[DOT ? 2 * NP : 1];
+    double dacc[DOT ? 2 * NP : 1]; // direct form: 2 NP columns of one row; transposed (GRAM) form: NP columns of two rows
 #pragma unroll
     for (int i = 0; i < (DOT ? 2 * NP : 1); ++i)
       dacc[i] = 0.0;
+    double gacc[GRAM ? NT : 1][2];
+#pragma unroll
+    for (int i = 0; i < (GRAM ? NT : 1); ++i)
+      gacc[i][0] = gacc[i][1] = 0.0;
 
     if (warp < NPW)
     {
@@ -321,33 +336,103 @@ namespace de
             lds_frag<NP>(bv, xs + lc * LDR + NP * g, k);
 #pragma unroll
             for (int p = 0; p < NP; ++p)
-              dmma884_sp(c[p][0], c[p][1], av, bv[p]);
-          }
-          const long long row = (long long)blkrows[8 * blk + g];
-          if (row >= 0 && row < a.n)
-          {
-            double lo[NP], hi[NP];
-#pragma unroll
-            for (int p = 0; p < NP; ++p)
             {
-              lo[p] = c[p][0];
-              hi[p] = c[p][1];
+              if (GRAM)
+                dmma884_sp(c[p][0], c[p][1], bv[p], av); // transposed: c[p] = Y(rows 2k, 2k+1; column NP g + p)
+              else
+                dmma884_sp(c[p][0], c[p][1], av, bv[p]); // c[p] = Y(row g; columns 2 k NP + p, (2 k + 1) NP + p)
             }
-            double *yr = a.Y + (size_t)row * a.ldx + 2 * k * NP;
-            stg_row<NP>(yr, lo);
-            stg_row<NP>(yr + NP, hi);
-            if (DOT)
+          }
+          if (!GRAM)
+          {
+            // the lane owns 2 NP contiguous columns of row g (measured 5 % faster than the transposed epilogue)
+            const long long row = (long long)blkrows[8 * blk + g];
+            if (row >= 0 && row < a.n)
             {
-              double zl[NP], zh[NP];
-              const double *xr = a.X + (size_t)row * a.ldx + 2 * k * NP;
-              ldg_row_if<NP>(zl, xr, true);
-              ldg_row_if<NP>(zh, xr + NP, true);
+              double lo[NP], hi[NP];
 #pragma unroll
               for (int p = 0; p < NP; ++p)
               {
-                dacc[p] = fma(zl[p], lo[p], dacc[p]);
-                dacc[NP + p] = fma(zh[p], hi[p], dacc[NP + p]);
+                lo[p] = c[p][0];
+                hi[p] = c[p][1];
               }
+              double *yr = a.Y + (size_t)row * a.ldx + 2 * k * NP;
+              stg_row<NP>(yr, lo);
+              stg_row<NP>(yr + NP, hi);
+              if (DOT)
+              {
+                double zl[NP], zh[NP];
+                const double *xr = a.X + (size_t)row * a.ldx + 2 * k * NP;
+                ldg_row_if<NP>(zl, xr, true);
+                ldg_row_if<NP>(zh, xr + NP, true);
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+                {
+                  dacc[p] = fma(zl[p], lo[p], dacc[p]);
+                  dacc[NP + p] = fma(zh[p], hi[p], dacc[NP + p]);
+                }
+              }
+            }
+            continue;
+          }
+          const long long row0 = (long long)blkrows[8 * blk + 2 * k], row1 = (long long)blkrows[8 * blk + 2 * k + 1];
+          double y0[NP], y1[NP];
+#pragma unroll
+          for (int p = 0; p < NP; ++p)
+          {
+            y0[p] = c[p][0];
+            y1[p] = c[p][1];
+          }
+          if (row0 >= 0 && row0 < a.n)
+          {
+            stg_row<NP>(a.Y + (size_t)row0 * a.ldx + NP * g, y0);
+            if (DOT)
+            {
+              double z[NP];
+              ldg_row_if<NP>(z, a.X + (size_t)row0 * a.ldx + NP * g, true);
+#pragma unroll
+              for (int p = 0; p < NP; ++p)
+                dacc[p] = fma(z[p], y0[p], dacc[p]);
+            }
+          }
+          if (row1 >= 0 && row1 < a.n)
+          {
+            stg_row<NP>(a.Y + (size_t)row1 * a.ldx + NP * g, y1);
+            if (DOT)
+            {
+              double z[NP];
+              ldg_row_if<NP>(z, a.X + (size_t)row1 * a.ldx + NP * g, true);
+#pragma unroll
+              for (int p = 0; p < NP; ++p)
+                dacc[p] = fma(z[p], y1[p], dacc[p]);
+            }
+          }
+          if (GRAM)
+          {
+            // G += Yb^T Yb for the 8 rows of the block (empty slots hold zeros), as two 4-row slabs. The operand
+            // fragment of column group p is  f[p] = Y(row 4 s + k, column NP g + p): rows 2 kk, 2 kk + 1 sit in lane kk
+            // of this quad, so lane k fetches from lane 2 s + (k >> 1), accumulator (k & 1).
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+            {
+              const int src = (lane & ~3) | (2 * sl + (k >> 1));
+              double f[NP];
+#pragma unroll
+              for (int p = 0; p < NP; ++p)
+              {
+                const double v0 = __shfl_sync(0xffffffffu, c[p][0], src);
+                const double v1 = __shfl_sync(0xffffffffu, c[p][1], src);
+                f[p] = (k & 1) ? v1 : v0;
+              }
+              int t = 0;
+#pragma unroll
+              for (int p = 0; p < NP; ++p)
+#pragma unroll
+                for (int q = p; q < NP; ++q)
+                {
+                  dmma884_sp(gacc[t][0], gacc[t][1], f[p], f[q]); // tile (p, q): G(NP i + p, NP j + q)
+                  ++t;
+                }
             }
           }
         }
@@ -364,30 +449,85 @@ namespace de
 
     if (DOT)
     {
-      // lanes with equal k hold the same 2 NP columns: fold the 8 row lanes, then the consumer warps, in fixed order
+      // fold the lanes that hold the same columns, then the consumer warps, in fixed order; the Gram accumulators of the warps are folded the same way into the natural m x m layout
       __syncthreads(); // every tile of this CTA has been consumed: the stage buffers are free
       double *red = reinterpret_cast<double *>(bufs); // NCW x M
+      double *gred = red + NCW * M;                   // GRAM: M x M
+      const int g = lane >> 2, k = lane & 3;
       if (warp >= NPW)
       {
-        const int g = lane >> 2, k = lane & 3;
-#pragma unroll
-        for (int i = 0; i < 2 * NP; ++i)
+        if (GRAM)
         {
-          double v = dacc[i];
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          v += __shfl_xor_sync(0xffffffffu, v, 8);
-          v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (g == 0)
-            red[(warp - NPW) * M + 2 * k * NP + (i < NP ? i : NP + (i - NP))] = v;
+          // transposed form: the 4 lanes of a quad hold the same NP columns
+#pragma unroll
+          for (int i = 0; i < NP; ++i)
+          {
+            double v = dacc[i];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (k == 0)
+              red[(warp - NPW) * M + NP * g + i] = v;
+          }
+        }
+        else
+        {
+          // direct form: lanes with equal k hold the same 2 NP columns
+#pragma unroll
+          for (int i = 0; i < 2 * NP; ++i)
+          {
+            double v = dacc[i];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (g == 0)
+              red[(warp - NPW) * M + 2 * k * NP + i] = v;
+          }
         }
       }
-      __syncthreads();
+      if (GRAM)
+      {
+        for (int turn = 0; turn < NCW; ++turn)
+        {
+          if (warp - NPW == turn)
+          {
+            int t = 0;
+#pragma unroll
+            for (int p = 0; p < NP; ++p)
+#pragma unroll
+              for (int q = p; q < NP; ++q)
+              {
+                // accumulator tile (p, q): D(i = g, j = 2k, 2k+1) = G(NP g + p, NP j + q)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                {
+                  const int gi = NP * g + p, gj = NP * (2 * k + e) + q;
+                  const double v = gacc[t][e] + (turn == 0 ? 0.0 : gred[gi * M + gj]);
+                  gred[gi * M + gj] = v;
+                }
+                ++t;
+              }
+          }
+          __syncthreads();
+        }
+      }
+      else
+        __syncthreads();
       if (tid < M)
       {
         double sum = 0.0;
         for (int w = 0; w < NCW; ++w)
           sum += red[w * M + tid];
         a.partials[(size_t)blockIdx.x * a.pstride + tid] = sum;
+      }
+      if (GRAM)
+      {
+        // tiles with p < q were computed for (row % NP, column % NP) = (p, q) only: their mirror images complete G
+        double *out = a.partials + (size_t)blockIdx.x * a.pstride + a.gram_off;
+        for (int e = tid; e < M * M; e += blockDim.x)
+        {
+          const int i = e / M, j = e % M;
+          out[e] = (i % NP <= j % NP) ? gred[e] : gred[j * M + i];
+        }
       }
     }
   }

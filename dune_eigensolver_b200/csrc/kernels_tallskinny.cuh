@@ -95,7 +95,7 @@ namespace de
    *   UPPER      G is symmetric: only the 8x8 tiles on or above the diagonal are computed, mirrored on output
    *   SAME       single Gram operand (B aliases A) */
   template <int M, bool DO_UPDATE, bool DO_GRAM, bool UPPER, bool SAME>
-  __global__ void __launch_bounds__(256, (M <= 32 && !(DO_UPDATE && DO_GRAM)) ? 2 : 1) tall_skinny_kernel(const TsArgs a)
+  __global__ void __launch_bounds__(256, (M <= 32) ? 2 : 1) tall_skinny_kernel(const TsArgs a)
   {
     constexpr int NOPS = (DO_GRAM && !SAME) ? 2 : 1;
     using C = TsCfg<M, UPPER, NOPS>;

@@ -316,6 +316,13 @@ def matmul_sparse_tallskinny_blocked(Qout, A, Qin):
     check(capi.lib().de_spmm(Qout._h, A._h, Qin._h), A.ctx._h)
 
 
+def matmul_sparse_tallskinny_with_dots_and_gram(Qout, A, Qin):
+    """Qout = A * Qin, diag(Qin^T Qout) and the Gram matrix Qout^T Qout from the same pass (de_spmm_gram)."""
+    dp, G = np.empty(Qin.m), np.empty((Qin.m, Qin.m))
+    check(capi.lib().de_spmm_gram(Qout._h, A._h, Qin._h, dptr(dp), dptr(G)), A.ctx._h)
+    return dp, G
+
+
 def matmul_sparse_tallskinny_with_dots(Qout, A, Qin):
     """Qout = A * Qin and the column-wise dot products diag(Qin^T Qout) from the same pass."""
     dp = np.empty(Qin.m)

@@ -156,6 +156,10 @@ int de_spmm(de_mv *Y, const de_matrix *A, const de_mv *X);
  * eigensolver.hh:84-85, :174-175, :308-309). dp_host has m entries. */
 int de_spmm_diag_dot(de_mv *Y, const de_matrix *A, const de_mv *X, double *dp_host);
 /* dp[j] = sum_i X(i,j) Y(i,j).  replaces dot_products_diagonal_{blocked,avx2_b8,neon_b8} (kernels_cpp.hh:24-55) */
+/* Y = A X, dp = diag(X^T Y) and G = Y^T Y (m x m, row-major) from ONE pass: the Gram matrix the next
+ * orthonormalisation of Y needs (kernels_cpp.hh:236-242 forms it panel by panel) is accumulated in the SpMM epilogue
+ * when the matrix has the BRB form and m is 8, 16 or 32; otherwise a separate Gram pass produces the same result. */
+int de_spmm_gram(de_mv *Y, const de_matrix *A, const de_mv *X, double *dp_host, double *G_host);
 int de_diag_dot(double *dp_host, const de_mv *X, const de_mv *Y);
 /* G = X^T Y, row-major m x m on the host. replaces dot_products_all_blocked (kernels_cpp.hh:58-96) and the naive
  * dot_products_diagonal(Q) full Gram (kernels_cpp.hh:7-21) */

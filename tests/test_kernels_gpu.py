@@ -120,6 +120,27 @@ def test_device_built_brb_arrays_equal_the_host_builder(ctx, name):
     assert dA.brb_selfcheck(A) == 0
 
 
+@pytest.mark.parametrize("name", ["q1_3d_13", "fd3d_24", "lap2d_40", "random_900"])
+@pytest.mark.parametrize("m", [8, 16, 32, 48, 64])
+def test_spmm_with_gram_epilogue(ctx, oracle, name, m):
+    """Y = A X, diag(X^T Y) and Y^T Y from one pass (the Gram epilogue of the tensor-core kernel for m = 8/16/32, a
+    separate Gram pass otherwise) against the reference kernels (kernels_cpp.hh:626-657, :24-55, :58-96)"""
+    A = BRB_MATS[name]() if name in BRB_MATS else _random_csr(900, 12, 5)
+    n = len(A[0]) - 1
+    X = rnd(n, m, 7 * m)
+    dA, dX, dY = E.Matrix(ctx, A), E.MultiVector.from_array(ctx, X), E.MultiVector(ctx, n, m)
+    ref = oracle.spmm(A, X)
+    scale = np.abs(M.to_scipy(A)).dot(np.abs(X)).max()
+    for fmt in ("brb", "csr"):
+        dA.set_spmm_format(fmt)
+        dp, G = E.matmul_sparse_tallskinny_with_dots_and_gram(dY, dA, dX)
+        assert np.abs(dY.download() - ref).max() <= 1e-14 * scale, fmt
+        assert np.abs(dp - oracle.diag_dot(X, ref)).max() <= 1e-13 * (np.abs(X) * np.abs(ref)).sum(0).max(), fmt
+        Gref = oracle.gram(ref, ref)
+        assert np.abs(G - Gref).max() <= 1e-13 * np.abs(Gref).max() * np.sqrt(n), fmt
+        assert np.abs(G - G.T).max() <= 1e-12 * np.abs(G).max()
+
+
 def test_spmm_brb_is_deterministic_and_linear(ctx):
     """size-independent properties at a size the oracle would not finish quickly: run-to-run bit identity, and
     A(aX + bZ) = a AX + b AZ to rounding, on the 27-point 64^3 matrix (m = 32)."""

@@ -250,10 +250,12 @@ int main(int argc, char **argv)
           b.Y = d_Y + 8 * np * ps;
           b.partials = d_part + 8 * np * ps;
           b.pstride = m;
+          b.gram_off = m;
+          b.done = nullptr;
           b.blob_cap16 = F.max_len16;
           b.xs_cap = F.max_u;
           b.stages = stages;
-          kern<<<grid, de::kBrbThreads, smem>>>(b);
+          kern<<<grid, de::brb_threads(false), smem>>>(b);
         }
         (void)dot;
       };
@@ -261,18 +263,18 @@ int main(int argc, char **argv)
       std::snprintf(nm, sizeof nm, "brb %d stage(s) x%d pass", stages, passes);
       float ms = 0;
       if (np == 1)
-        ms = time_it([&] { launch(de::spmm_brb_kernel<1, false, false>, false); }, reps);
+        ms = time_it([&] { launch(de::spmm_brb_kernel<1, false, false, false>, false); }, reps);
       if (np == 2)
-        ms = time_it([&] { launch(de::spmm_brb_kernel<2, false, false>, false); }, reps);
+        ms = time_it([&] { launch(de::spmm_brb_kernel<2, false, false, false>, false); }, reps);
       if (np == 4)
-        ms = time_it([&] { launch(de::spmm_brb_kernel<4, false, false>, false); }, reps);
+        ms = time_it([&] { launch(de::spmm_brb_kernel<4, false, false, false>, false); }, reps);
       check(nm, ms);
       if (np == 1)
-        ms = time_it([&] { launch(de::spmm_brb_kernel<1, true, false>, true); }, reps);
+        ms = time_it([&] { launch(de::spmm_brb_kernel<1, true, false, false>, true); }, reps);
       if (np == 2)
-        ms = time_it([&] { launch(de::spmm_brb_kernel<2, true, false>, true); }, reps);
+        ms = time_it([&] { launch(de::spmm_brb_kernel<2, true, false, false>, true); }, reps);
       if (np == 4)
-        ms = time_it([&] { launch(de::spmm_brb_kernel<4, true, false>, true); }, reps);
+        ms = time_it([&] { launch(de::spmm_brb_kernel<4, true, false, false>, true); }, reps);
       // dot check on the host: sum of partials vs sum_i X(i,j) Yref(i,j)
       {
         std::vector<double> part((size_t)grid * m), X((size_t)n * m), Yr((size_t)n * m);
