@@ -30,13 +30,21 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # Iterations StandardLargest needs on this workload (N = 100, 27-point Q1, m = 32, tol = 2e-3, seed = 123).
 # Measured by this script's own arm on B200 (asserted there to +-1 on every run); the CPU arms need it only to
 # extrapolate their bounded sample to a full solve.
-ITERATIONS_TO_CONVERGENCE = {(100, "q1", 32, 2e-3): None}
+ITERATIONS_TO_CONVERGENCE = {(100, "q1", 32, 2e-3): 41}
+
+# DRAM traffic of ONE launch of the dominant kernel, from the committed ncu --set full capture of this very command
+# (profiles/r01_ncu_kernels_brb.csv: dram__bytes_read.sum + dram__bytes_write.sum of spmm_brb_kernel<4,1,0,0>):
+# 515.4 MB + 231.1 MB. It is BELOW the algorithmic bytes (833.6 MB, counted for CSR: 12 B per nonzero) because the
+# BRB stream is 9.4 B per nonzero; no byte is read twice.
+NCU_DRAM_TRAFFIC_PER_LAUNCH = {(100, "q1", 32): 746.5e6}
 
 
 def parse():
@@ -364,7 +372,9 @@ def run_b200(args):
                    "avg_ms": upd_ms / max(upd_cnt, 1), "algorithmic_bytes": 16.0 * n_loc * m},
     }
     roofline = {"bound": "hbm", "kernel": "spmm_brb_kernel (SpMM + fused Rayleigh-quotient dots)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_DRAM_TRAFFIC_PER_LAUNCH.get((args.grid, args.stencil, m)) if world == 1 else None,
+                "traffic_source": "profiles/r01_ncu_kernels_brb.csv (ncu --set full of this command, one launch)",
                 "peak_source": peak_src, "avg_launch_ms": spmm_ms / max(spmm_cnt, 1),
                 "algorithmic_bytes_per_launch": spmm_bytes, "kernel_time_shares": shares,
                 "kernel_time_shares_source": "one extra solve after the timed region with all categories timed "

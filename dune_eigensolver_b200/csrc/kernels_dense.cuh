@@ -391,6 +391,7 @@ namespace de
     __shared__ double rowk[2][MP];
     __shared__ double colk[2][MP];
     __shared__ double dorig[MP];
+    __shared__ double dinv[MP]; // 1 / r_kk
     __shared__ double redmx[32], reddev[32];
     __shared__ int bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -456,15 +457,22 @@ namespace de
         // this warp owns row k (slot a = ka); lane kw of slot b = ka holds the pivot
         const double d = __shfl_sync(0xffffffffu, r[E == 1 ? 0 : ka][E == 1 ? 0 : ka], kw);
         const bool ok = (d > 4.0 * m * 2.220446049250313e-16 * dorig[k]) && isfinite(d);
-        const double rkk = ok ? sqrt(d) : 1.0;
-        if (!ok && lane == 0)
-          bad = k + 1;
+        // one reciprocal square root per pivot; the division and the square root of the textbook form are the
+        // longest links of the dependency chain (ncu: 800 cycles per pivot with sqrt + div, mostly in those two)
+        const double rinv = ok ? rsqrt(d) : 1.0;
+        const double rkk = ok ? d * rinv : 1.0;
+        if (lane == 0)
+        {
+          dinv[k] = rinv;
+          if (!ok)
+            bad = k + 1;
+        }
 #pragma unroll
         for (int b = 0; b < E; ++b)
         {
           const int j = lane + 32 * b;
           double v = r[E == 1 ? 0 : ka][b];
-          v = (j == k) ? rkk : (j > k ? v / rkk : 0.0);
+          v = (j == k) ? rkk : (j > k ? v * rinv : 0.0);
           r[E == 1 ? 0 : ka][b] = v;
           rowk[buf][j] = v;
         }
@@ -509,11 +517,11 @@ namespace de
       const int ka = k >> 5, kw = k & 31, buf = k & 1;
       if (warp == kw)
       {
-        const double rkk = __shfl_sync(0xffffffffu, r[E == 1 ? 0 : ka][E == 1 ? 0 : ka], kw);
+        const double rinv = dinv[k];
 #pragma unroll
         for (int b = 0; b < E; ++b)
         {
-          const double v = x[E == 1 ? 0 : ka][b] / rkk;
+          const double v = x[E == 1 ? 0 : ka][b] * rinv;
           x[E == 1 ? 0 : ka][b] = v;
           rowk[buf][lane + 32 * b] = v;
         }
