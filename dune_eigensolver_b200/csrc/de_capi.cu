@@ -33,6 +33,7 @@
 #include "kernels_spmm_blocked.cuh"
 #include "brb_format.hpp"
 #include "kernels_brb_build.cuh"
+#include "kernels_peer.cuh"
 #include "kernels_tallskinny.cuh"
 #include "kernels_trsv.cuh"
 
@@ -111,6 +112,13 @@ struct de_context
   cudaEvent_t ev_poll[2] = {nullptr, nullptr};
   double *dconv = nullptr;    // s_prev[64] | hist[dconv_cap]
   void *xfer = nullptr;       // XferEngine: pinned staging buffers and copy streams (created on first use)
+  // NVLink peer window (kernels_peer.cuh); peer_ready once every rank's window is mapped
+  bool peer_ready = false;
+  unsigned char *window = nullptr;
+  size_t window_bytes = 0, halo_cap = 0;
+  unsigned char *peer_base[de::kPeerMaxRanks] = {};
+  unsigned long long ar_epoch = 0, halo_epoch = 0;
+  int *dticket = nullptr; // [0] ticket of halo_push_kernel, [1] peer error flag
   size_t dconv_cap = 0;
   double *hsmall = nullptr;   // pinned mirror of dsmall
   int *hstatus = nullptr;     // pinned
@@ -214,9 +222,12 @@ struct de_matrix
   int *interior = nullptr, *boundary = nullptr;
   long long n_interior = 0, n_boundary = 0;
   double *send_buf = nullptr, *halo_buf = nullptr;
+  double *halo_view = nullptr; // where the kernels read halo rows of the current SpMM: halo_buf (NCCL) or the peer window
   int buf_m = 0;
   StagedRows st_all, st_interior, st_boundary;
   BrbDevice brb;
+  bool peer_halo = false;            // halo rows travel as peer stores into the neighbours' windows
+  std::vector<long long> deposit;    // [npeers] first row of this rank's rows in peer p's halo block
   int spmm_format = DE_SPMM_AUTO; // which SpMM kernel family to use (de_matrix_set_spmm_format)
 };
 
@@ -680,10 +691,31 @@ namespace
     return DE_OK;
   }
 
+  de::PeerArgs peer_args(de_context *ctx, unsigned long long epoch)
+  {
+    de::PeerArgs pa;
+    pa.rank = ctx->rank;
+    pa.nranks = ctx->nranks;
+    for (int q = 0; q < de::kPeerMaxRanks; ++q)
+      pa.base[q] = ctx->peer_base[q];
+    pa.epoch = epoch;
+    pa.done = ctx->done_ptr;
+    pa.err = ctx->dticket + 1;
+    return pa;
+  }
+
   int allreduce_sum(de_context *ctx, double *buf, size_t count)
   {
-    if (ctx->nranks > 1)
-      DE_NCCL(ctx, nccl_api().AllReduce(buf, buf, count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+    if (ctx->nranks <= 1)
+      return DE_OK;
+    if (ctx->peer_ready && count <= (size_t)de::kPeerSlotDoubles)
+    {
+      ProfScope prof(ctx, DE_PROF_SMALL);
+      de::peer_allreduce_kernel<<<1, 1024, 0, ctx->stream>>>(peer_args(ctx, ++ctx->ar_epoch), buf, (int)count);
+      DE_LAUNCH_CHECK(ctx);
+      return DE_OK;
+    }
+    DE_NCCL(ctx, nccl_api().AllReduce(buf, buf, count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
     return DE_OK;
   }
 
@@ -702,7 +734,7 @@ namespace
     a.col = A->col;
     a.val = A->val;
     a.X = X;
-    a.H = A->halo_buf;
+    a.H = A->halo_view;
     a.n_owned = A->n;
     a.ld = m;
     a.m = m;
@@ -854,7 +886,7 @@ namespace
     a.col = S.col;
     a.val = S.val;
     a.X = X;
-    a.H = A->halo_buf;
+    a.H = A->halo_view;
     a.n_owned = (int)A->n;
     a.m = m;
     a.Y = Y;
@@ -1081,7 +1113,7 @@ namespace
    *  additionally the CTA's partial of Y^T Y at partials[cta * pstride + m + i * m + j], pstride = m + m * m. */
   template <bool DOT, bool GRAM>
   int launch_spmm_brb(de_context *ctx, const de_matrix *A, int t0, int nt, const double *X, double *Y, int m, double *partials,
-                      int *grid_out)
+                      int *grid_out, int category = DE_PROF_SPMM)
   {
     *grid_out = 0;
     if (nt <= 0)
@@ -1089,7 +1121,7 @@ namespace
     const BrbDevice &B = A->brb;
     const int grid = std::min(nt, ctx->sm_count);
     const bool halo = A->n_halo > 0;
-    ProfScope prof(ctx, DE_PROF_SPMM);
+    ProfScope prof(ctx, category);
     for (int c0 = 0; c0 < m;)
     {
       const int left = (m - c0) / 8;
@@ -1101,7 +1133,7 @@ namespace
       a.blob = B.blob;
       a.ucol = B.ucol;
       a.X = X + c0;
-      a.H = A->halo_buf ? A->halo_buf + c0 : nullptr;
+      a.H = A->halo_view ? A->halo_view + c0 : nullptr;
       a.n_owned = (int)A->n;
       a.ldx = m;
       a.Y = Y + c0;
@@ -1181,30 +1213,65 @@ namespace
     }
     else
     {
-      DE_TRY(ensure_halo_buffers(ctx, A, m));
-      if (A->n_send > 0)
+      const bool peer = ctx->peer_ready && A->peer_halo && (size_t)A->n_halo * m * sizeof(double) <= ctx->halo_cap &&
+                        A->npeers <= de::kPeerMaxRanks;
+      de::PeerArgs pa{};
+      if (peer)
       {
-        const long long total = A->n_send * (m / 2);
-        const int grid = (int)std::min<long long>((total + 255) / 256, ctx->sm_count * 8);
-        ProfScope prof(ctx, DE_PROF_MISC);
-        de::pack_rows_kernel<<<grid, 256, 0, ctx->stream>>>(A->n_send, A->send_rows, m, X, A->send_buf);
-        DE_LAUNCH_CHECK(ctx);
+        // halo rows go straight into the neighbours' windows; the boundary tiles wait for this epoch's flags
+        pa = peer_args(ctx, ++ctx->halo_epoch);
+        A->halo_view = reinterpret_cast<double *>(ctx->window + de::kPeerHaloOff + (size_t)(pa.epoch & 1ull) * ctx->halo_cap);
+        if (A->n_send > 0)
+        {
+          de::HaloPushArgs h{};
+          h.npeers = A->npeers;
+          for (int p = 0; p < A->npeers; ++p)
+          {
+            h.peer_rank[p] = A->peer[p];
+            h.send_off[p] = A->send_off[p];
+            h.deposit[p] = A->deposit[p];
+          }
+          h.send_off[A->npeers] = A->n_send;
+          h.send_rows = A->send_rows;
+          h.X = X;
+          h.m = m;
+          h.halo_cap_bytes = ctx->halo_cap;
+          h.ticket = ctx->dticket;
+          const long long total = A->n_send * (m / 2);
+          const int grid = (int)std::min<long long>((total + 255) / 256, ctx->sm_count * 4);
+          ProfScope prof(ctx, DE_PROF_MISC);
+          de::halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(pa, h);
+          DE_LAUNCH_CHECK(ctx);
+        }
       }
-      DE_CUDA(ctx, cudaEventRecord(ctx->ev_pack, ctx->stream));
-      DE_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_pack, 0));
-      NcclApi &nc = nccl_api();
-      DE_NCCL(ctx, nc.GroupStart());
-      for (int p = 0; p < A->npeers; ++p)
+      else
       {
-        if (A->send_count[p] > 0)
-          DE_NCCL(ctx, nc.Send(A->send_buf + (size_t)A->send_off[p] * m, (size_t)A->send_count[p] * m, ncclDouble,
-                               A->peer[p], ctx->comm, ctx->comm_stream));
-        if (A->recv_count[p] > 0)
-          DE_NCCL(ctx, nc.Recv(A->halo_buf + (size_t)A->recv_off[p] * m, (size_t)A->recv_count[p] * m, ncclDouble,
-                               A->peer[p], ctx->comm, ctx->comm_stream));
+        DE_TRY(ensure_halo_buffers(ctx, A, m));
+        A->halo_view = A->halo_buf;
+        if (A->n_send > 0)
+        {
+          const long long total = A->n_send * (m / 2);
+          const int grid = (int)std::min<long long>((total + 255) / 256, ctx->sm_count * 8);
+          ProfScope prof(ctx, DE_PROF_MISC);
+          de::pack_rows_kernel<<<grid, 256, 0, ctx->stream>>>(A->n_send, A->send_rows, m, X, A->send_buf);
+          DE_LAUNCH_CHECK(ctx);
+        }
+        DE_CUDA(ctx, cudaEventRecord(ctx->ev_pack, ctx->stream));
+        DE_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_pack, 0));
+        NcclApi &nc = nccl_api();
+        DE_NCCL(ctx, nc.GroupStart());
+        for (int p = 0; p < A->npeers; ++p)
+        {
+          if (A->send_count[p] > 0)
+            DE_NCCL(ctx, nc.Send(A->send_buf + (size_t)A->send_off[p] * m, (size_t)A->send_count[p] * m, ncclDouble,
+                                 A->peer[p], ctx->comm, ctx->comm_stream));
+          if (A->recv_count[p] > 0)
+            DE_NCCL(ctx, nc.Recv(A->halo_buf + (size_t)A->recv_off[p] * m, (size_t)A->recv_count[p] * m, ncclDouble,
+                                 A->peer[p], ctx->comm, ctx->comm_stream));
+        }
+        DE_NCCL(ctx, nc.GroupEnd());
+        DE_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
       }
-      DE_NCCL(ctx, nc.GroupEnd());
-      DE_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
       const bool staged = staged_usable(A, m) && (A->st_interior.valid || A->n_interior == 0) &&
                           (A->st_boundary.valid || A->n_boundary == 0);
       const bool brb = brb_usable(A, m);
@@ -1220,15 +1287,26 @@ namespace
         DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_interior, X, Y, m, ctx->partials, &g1));
       else
         DE_TRY(launch_spmm_rows<DOT>(ctx, A, X, Y, m, A->interior, A->n_interior, ctx->partials, &g1));
-      DE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+      if (peer)
+      {
+        de::PeerList pl{};
+        for (int p = 0; p < A->npeers; ++p)
+          if (A->recv_count[p] > 0)
+            pl.rank[pl.n++] = A->peer[p];
+        ProfScope prof(ctx, DE_PROF_MISC);
+        de::halo_wait_kernel<<<1, 32, 0, ctx->stream>>>(pa, pl);
+        DE_LAUNCH_CHECK(ctx);
+      }
+      else
+        DE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
       if (brb)
       {
         if (gram)
           DE_TRY((launch_spmm_brb<DOT, DOT>(ctx, A, A->brb.n_interior, A->brb.ntiles - A->brb.n_interior, X, Y, m,
-                                            ctx->partials + (size_t)g1 * pstride, &g2)));
+                                            ctx->partials + (size_t)g1 * pstride, &g2, DE_PROF_SPMM_BOUNDARY)));
         else
           DE_TRY((launch_spmm_brb<DOT, false>(ctx, A, A->brb.n_interior, A->brb.ntiles - A->brb.n_interior, X, Y, m,
-                                              ctx->partials + (size_t)g1 * pstride, &g2)));
+                                              ctx->partials + (size_t)g1 * pstride, &g2, DE_PROF_SPMM_BOUNDARY)));
       }
       else if (staged)
         DE_TRY(launch_spmm_staged<DOT>(ctx, A, A->st_boundary, X, Y, m, ctx->partials + (size_t)g1 * m, &g2));
@@ -1534,7 +1612,12 @@ namespace
     if (count > 0)
       DE_CUDA(ctx, cudaMemcpyAsync(ctx->hsmall, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DE_CUDA(ctx, cudaMemcpyAsync(ctx->hstatus, ctx->dstatus, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->hflags[7] = 0;
+    if (ctx->peer_ready)
+      DE_CUDA(ctx, cudaMemcpyAsync(ctx->hflags + 7, ctx->dticket + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->hflags[7] != 0)
+      return set_error(ctx, DE_ERR_NCCL, "NVLink peer window: a neighbour rank did not arrive within 2 s");
     if (count > 0 && hdst != ctx->hsmall)
       std::memcpy(hdst, ctx->hsmall, count * sizeof(double));
     if (*ctx->hstatus != 0)
@@ -1865,6 +1948,13 @@ extern "C"
       if (e)
         cudaEventDestroy(e);
     dev_free(ctx->dconv);
+    for (int q = 0; q < de::kPeerMaxRanks; ++q)
+      if (ctx->peer_base[q] && q != ctx->rank)
+        cudaIpcCloseMemHandle(ctx->peer_base[q]);
+    if (ctx->window)
+      cudaFree(ctx->window);
+    if (ctx->dticket)
+      cudaFree(ctx->dticket);
     xfer_destroy(ctx);
     dev_cache_trim(ctx->device, ctx->stream);
     if (ctx->ev_pack)
@@ -1984,6 +2074,89 @@ extern "C"
       *rank = ctx->rank;
     if (nranks)
       *nranks = ctx->nranks;
+    return DE_OK;
+  }
+
+  int de_context_peer_window_create(de_context *ctx, int64_t halo_bytes, void *ipc_handle64)
+  {
+    if (!ctx || !ipc_handle64 || halo_bytes < 0)
+      return set_error(ctx, DE_ERR_INVALID, "de_context_peer_window_create: bad arguments");
+    if (ctx->nranks < 2 || ctx->nranks > de::kPeerMaxRanks)
+      return set_error(ctx, DE_ERR_UNSUPPORTED, "de_context_peer_window_create: needs 2..8 ranks (call de_context_init_comm first)");
+    if (ctx->window)
+      return set_error(ctx, DE_ERR_INVALID, "de_context_peer_window_create: window exists");
+    DE_TRY(bind_device(ctx));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64 bytes");
+    ctx->halo_cap = ((size_t)halo_bytes + 255) & ~(size_t)255;
+    ctx->window_bytes = de::kPeerHaloOff + 2 * ctx->halo_cap;
+    // a dedicated cudaMalloc allocation: an IPC handle exports the whole allocation
+    DE_CUDA(ctx, cudaMalloc((void **)&ctx->window, ctx->window_bytes));
+    DE_CUDA(ctx, cudaMemset(ctx->window, 0, ctx->window_bytes));
+    DE_CUDA(ctx, cudaMalloc((void **)&ctx->dticket, 2 * sizeof(int)));
+    DE_CUDA(ctx, cudaMemset(ctx->dticket, 0, 2 * sizeof(int)));
+    DE_CUDA(ctx, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    DE_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->window));
+    std::memcpy(ipc_handle64, &h, 64);
+    return DE_OK;
+  }
+
+  int de_context_peer_window_open(de_context *ctx, const void *ipc_handles)
+  {
+    if (!ctx || !ipc_handles || !ctx->window)
+      return set_error(ctx, DE_ERR_INVALID, "de_context_peer_window_open: bad arguments (create the window first)");
+    DE_TRY(bind_device(ctx));
+    for (int q = 0; q < ctx->nranks; ++q)
+    {
+      if (q == ctx->rank)
+      {
+        ctx->peer_base[q] = ctx->window;
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, (const unsigned char *)ipc_handles + 64 * (size_t)q, 64);
+      void *p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+      {
+        cudaGetLastError();
+        for (int r = 0; r < q; ++r)
+          if (r != ctx->rank && ctx->peer_base[r])
+          {
+            cudaIpcCloseMemHandle(ctx->peer_base[r]);
+            ctx->peer_base[r] = nullptr;
+          }
+        return set_error(ctx, DE_ERR_UNSUPPORTED,
+                         std::string("de_context_peer_window_open: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+      }
+      ctx->peer_base[q] = (unsigned char *)p;
+    }
+    ctx->ar_epoch = ctx->halo_epoch = 0;
+    ctx->peer_ready = true; // the caller runs a barrier before the first collective (every window must be zeroed)
+    return DE_OK;
+  }
+
+  int de_context_peer_ready(const de_context *ctx, int *ready)
+  {
+    if (!ctx || !ready)
+      return set_error(nullptr, DE_ERR_INVALID, "de_context_peer_ready: bad arguments");
+    *ready = ctx->peer_ready ? 1 : 0;
+    return DE_OK;
+  }
+
+  int de_matrix_set_peer_deposit(de_matrix *A, const int64_t *deposit_rows)
+  {
+    if (!A || (A->npeers > 0 && !deposit_rows))
+      return set_error(A ? A->ctx : nullptr, DE_ERR_INVALID, "de_matrix_set_peer_deposit: bad arguments");
+    if (!A->ctx->peer_ready)
+      return set_error(A->ctx, DE_ERR_UNSUPPORTED, "de_matrix_set_peer_deposit: the context has no peer window");
+    if (A->npeers > de::kPeerMaxRanks)
+      return set_error(A->ctx, DE_ERR_UNSUPPORTED, "de_matrix_set_peer_deposit: too many peers");
+    A->deposit.assign(deposit_rows, deposit_rows + A->npeers);
+    for (int p = 0; p < A->npeers; ++p)
+      if (A->deposit[p] < 0)
+        return set_error(A->ctx, DE_ERR_INVALID, "de_matrix_set_peer_deposit: negative offset");
+    A->peer_halo = true;
     return DE_OK;
   }
 

@@ -1,0 +1,179 @@
+// Multi-GPU data path over NVLink peer memory (one process per GPU; the windows are exchanged as CUDA IPC handles).
+//
+// Every rank owns a WINDOW in its HBM that all peers map:
+//     [0, 4 KB)            flags      ar_flag[2][8] | halo_flag[2][8] (64-bit epochs, written by the peers)
+//     [4 KB, +2*8 slots)   all-reduce slots, one per (parity, sender rank), kPeerSlotDoubles doubles each
+//     [halo_off, +2*cap)   two halo buffers (parity of the SpMM call), laid out like the matrix's halo block
+//
+//  * peer_allreduce_kernel: one-shot all-reduce of a short vector (the m Rayleigh quotients and the m x m Gram
+//    matrices, <= 33 KB): every rank stores its vector into its slot in EVERY window, releases a flag there, waits for
+//    the flags of all ranks in its own window and sums the slots in rank order -- the same order on every rank, so
+//    all ranks hold bit-identical results (the replicated Cholesky and the convergence flag depend on that).
+//    One launch, ~2 NVLink latencies; an NCCL all-reduce of the same vector costs 25-40 us and a second kernel.
+//  * halo_push_kernel: the rows of X that neighbours need are stored straight into the neighbours' halo buffers
+//    (instead of pack -> ncclSend/ncclRecv on a second stream, whose point-to-point kernel competes with the
+//    persistent SpMM kernel for SMs); the last CTA to finish releases the flags. halo_wait_kernel (one warp) is the
+//    only thing the boundary tiles wait for.
+//
+// Flow control needs no credits: consecutive SpMM calls alternate between the two halo buffers, and a rank cannot be
+// two calls ahead of a neighbour because its boundary rows need that neighbour's rows of the call in between; an
+// all-reduce is itself a barrier, so two slot sets suffice. Spins give up after ~2 s and raise an error flag.
+#pragma once
+
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+namespace de
+{
+
+  constexpr int kPeerMaxRanks = 8;
+  constexpr int kPeerSlotDoubles = 4224; // >= 64 + 64 * 64
+  constexpr size_t kPeerFlagBytes = 4096;
+  constexpr size_t kPeerArOff = kPeerFlagBytes;
+  constexpr size_t kPeerHaloOff = kPeerArOff + (size_t)2 * kPeerMaxRanks * kPeerSlotDoubles * sizeof(double);
+
+  struct PeerArgs
+  {
+    int rank, nranks;
+    unsigned char *base[kPeerMaxRanks]; // window of every rank (own: local pointer)
+    unsigned long long epoch;           // of this operation; parity = epoch & 1
+    const int *done;                    // converged driver loop: no-op (the same on every rank)
+    int *err;                           // device error flag: a peer did not arrive
+  };
+
+  __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+  {
+    asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+  }
+  __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+  {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ bool peer_wait(const unsigned long long *flag, unsigned long long epoch, int *err)
+  {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < epoch)
+    {
+      if (clock64() - t0 > 4000000000LL) // ~2 s
+      {
+        if (err)
+          *err = 1;
+        return false;
+      }
+      __nanosleep(64);
+    }
+    return true;
+  }
+
+  __device__ __forceinline__ unsigned long long *peer_ar_flag(unsigned char *base, int parity, int sender)
+  {
+    return reinterpret_cast<unsigned long long *>(base) + parity * kPeerMaxRanks + sender;
+  }
+  __device__ __forceinline__ unsigned long long *peer_halo_flag(unsigned char *base, int parity, int sender)
+  {
+    return reinterpret_cast<unsigned long long *>(base) + 2 * kPeerMaxRanks + parity * kPeerMaxRanks + sender;
+  }
+  __device__ __forceinline__ double *peer_ar_slot(unsigned char *base, int parity, int sender)
+  {
+    return reinterpret_cast<double *>(base + kPeerArOff) + (size_t)(parity * kPeerMaxRanks + sender) * kPeerSlotDoubles;
+  }
+
+  /** buf[0..len) <- sum over ranks, identical bits on every rank. One CTA of 1024 threads. */
+  __global__ void __launch_bounds__(1024) peer_allreduce_kernel(const PeerArgs pa, double *__restrict__ buf, int len)
+  {
+    if (pa.done != nullptr && *pa.done != 0)
+      return;
+    const int tid = threadIdx.x;
+    const int parity = (int)(pa.epoch & 1ull);
+    for (int q = 0; q < pa.nranks; ++q)
+    {
+      double *dst = peer_ar_slot(pa.base[q], parity, pa.rank);
+      for (int i = tid; i < len; i += 1024)
+        dst[i] = buf[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < pa.nranks)
+    {
+      st_release_sys(peer_ar_flag(pa.base[tid], parity, pa.rank), pa.epoch);
+      peer_wait(peer_ar_flag(pa.base[pa.rank], parity, tid), pa.epoch, pa.err);
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int i = tid; i < len; i += 1024)
+    {
+      double s = 0.0;
+      for (int q = 0; q < pa.nranks; ++q)
+        s += __ldcg(peer_ar_slot(pa.base[pa.rank], parity, q) + i);
+      buf[i] = s;
+    }
+  }
+
+  struct HaloPushArgs
+  {
+    int npeers;
+    int peer_rank[kPeerMaxRanks];
+    long long send_off[kPeerMaxRanks + 1]; // rows sent to peer p: send_rows[send_off[p] .. send_off[p+1])
+    long long deposit[kPeerMaxRanks];      // first row of this rank's rows in peer p's halo block
+    const int *send_rows;
+    const double *X;
+    int m;
+    size_t halo_cap_bytes;
+    int *ticket;
+  };
+
+  __global__ void __launch_bounds__(256) halo_push_kernel(const PeerArgs pa, const HaloPushArgs h)
+  {
+    if (pa.done != nullptr && *pa.done != 0)
+      return;
+    const int parity = (int)(pa.epoch & 1ull);
+    const int hp = h.m / 2;
+    const long long total = h.send_off[h.npeers] * hp;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
+    {
+      const long long s = e / hp;
+      const int c = 2 * (int)(e % hp);
+      int p = 0;
+      while (s >= h.send_off[p + 1])
+        ++p;
+      double *dst = reinterpret_cast<double *>(pa.base[h.peer_rank[p]] + kPeerHaloOff + (size_t)parity * h.halo_cap_bytes) +
+                    (size_t)(h.deposit[p] + (s - h.send_off[p])) * h.m + c;
+      *reinterpret_cast<double2 *>(dst) = __ldg(reinterpret_cast<const double2 *>(h.X + (size_t)h.send_rows[s] * h.m + c));
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int last;
+    if (threadIdx.x == 0)
+      last = (atomicAdd(h.ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (last)
+    {
+      __threadfence_system();
+      if (threadIdx.x < h.npeers)
+        st_release_sys(peer_halo_flag(pa.base[h.peer_rank[threadIdx.x]], parity, pa.rank), pa.epoch);
+      if (threadIdx.x == 0)
+        *h.ticket = 0;
+    }
+  }
+
+  struct PeerList
+  {
+    int n;
+    int rank[kPeerMaxRanks];
+  };
+
+  /** returns when the halo rows of this epoch from every listed peer have landed in this rank's window */
+  __global__ void __launch_bounds__(32) halo_wait_kernel(const PeerArgs pa, const PeerList peers)
+  {
+    if (pa.done != nullptr && *pa.done != 0)
+      return;
+    const int parity = (int)(pa.epoch & 1ull);
+    if ((int)threadIdx.x < peers.n)
+      peer_wait(peer_halo_flag(pa.base[pa.rank], parity, peers.rank[threadIdx.x]), pa.epoch, pa.err);
+    __threadfence_system();
+  }
+
+} // namespace de

@@ -68,7 +68,7 @@ class Context:
 
     def set_profiling(self, on=True, only=None):
         """per-kernel CUDA-event timers: all categories, or only those named in `only` (e.g. ["spmm"])"""
-        names = ["spmm", "gram", "update", "small", "dot", "trsv", "misc"]
+        names = ["spmm", "gram", "update", "small", "dot", "trsv", "misc", "spmm_boundary"]
         code = int(bool(on))
         if on and only:
             code = sum(2 << names.index(c) for c in only)
@@ -76,7 +76,7 @@ class Context:
 
     def profile(self, reset=False):
         """{category: (total_ms, launches)} of the per-kernel CUDA-event timers (synchronises the stream)."""
-        names = ["spmm", "gram", "update", "small", "dot", "trsv", "misc"]
+        names = ["spmm", "gram", "update", "small", "dot", "trsv", "misc", "spmm_boundary"]
         out = {}
         for c, name in enumerate(names):
             ms, cnt = C.c_double(0.0), C.c_int64(0)
@@ -84,6 +84,22 @@ class Context:
             check(capi.lib().de_context_profile(self._h, c, C.byref(ms), C.byref(cnt), int(reset and last)), self._h)
             out[name] = (ms.value, cnt.value)
         return out
+
+    def peer_window_create(self, halo_bytes):
+        """-> 64-byte CUDA IPC handle of this rank's NVLink window (include/dune_eigensolver_b200.h)"""
+        buf = (C.c_char * 64)()
+        check(capi.lib().de_context_peer_window_create(self._h, int(halo_bytes), buf), self._h)
+        return bytes(buf.raw)
+
+    def peer_window_open(self, handles):
+        """handles: the 64-byte handles of all ranks, concatenated in rank order"""
+        buf = (C.c_char * len(handles)).from_buffer_copy(bytes(handles))
+        check(capi.lib().de_context_peer_window_open(self._h, buf), self._h)
+
+    def peer_ready(self):
+        r = C.c_int(0)
+        check(capi.lib().de_context_peer_ready(self._h, C.byref(r)), self._h)
+        return bool(r.value)
 
     def init_comm(self, rank, nranks, unique_id):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
@@ -135,6 +151,10 @@ class Matrix:
                                                       len(peers), capi.i32ptr(peers), i64ptr(rc), i64ptr(so),
                                                       i64ptr(sr), C.byref(h)), ctx._h)
         return cls(ctx, _handle=h)
+
+    def set_peer_deposit(self, deposit_rows):
+        d = i64(deposit_rows)
+        check(capi.lib().de_matrix_set_peer_deposit(self._h, i64ptr(d)), self.ctx._h)
 
     def set_spmm_format(self, fmt):
         """'auto' | 'csr' | 'brb' (include/dune_eigensolver_b200.h: de_matrix_set_spmm_format)"""

@@ -3,8 +3,9 @@
 One process per GPU. The global matrix is split into contiguous 1-D row blocks (a z-slab for lexicographic 3D
 grids); each rank keeps its CSR rows with columns renumbered to [owned | halo]. torch.distributed is used ONLY
 for setup plumbing: exchanging the halo index lists and broadcasting the NCCL unique id. The data path --
-halo rows of the vector block over NVLink, all-reduce of the m and m x m reductions -- runs inside the C library
-on its own NCCL communicator.
+halo rows of the vector block over NVLink, all-reduce of the m and m x m reductions -- runs inside the C library:
+over NVLink peer memory (every rank's window is mapped into every peer through CUDA IPC handles exchanged here) and,
+where that is not available, on the library's own NCCL communicator.
 """
 import numpy as np
 
@@ -93,11 +94,34 @@ def build_distributed_matrix(ctx, rowptr, col_global, val, part, rank, dist=None
         send_offsets.append(send_offsets[-1] + len(lst))
     send_rows = np.concatenate(send_rows) if send_rows else np.zeros(0, dtype=np.int64)
     n_owned = len(rowptr) - 1
-    return Matrix.distributed(ctx, n_owned, len(halo_global), rowptr, col_local, val, peers, recv, send_offsets,
-                              send_rows)
+    dA = Matrix.distributed(ctx, n_owned, len(halo_global), rowptr, col_local, val, peers, recv, send_offsets,
+                            send_rows)
+    if ctx.peer_ready():
+        # where do my rows start in each neighbour's halo block? its halo rows are ordered by owner rank, so the
+        # offset is the number of rows it receives from ranks below mine
+        deposits = peer_deposit_offsets(recv_counts, peers, rank, dist)
+        dA.set_peer_deposit(deposits)
+    return dA
 
 
-def init_comm(ctx, dist=None):
+def peer_deposit_offsets(recv_counts, peers, rank, dist=None):
+    """all-gather every rank's recv_counts[nranks]; deposit[p] = sum_{q < rank} recv_counts_of_peer_p[q]"""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    nranks = dist.get_world_size()
+    mine = torch.tensor([int(c) for c in recv_counts], dtype=torch.int64)
+    dev = None
+    if dist.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        mine = mine.to(dev)
+    allc = [torch.zeros_like(mine) for _ in range(nranks)]
+    dist.all_gather(allc, mine)
+    allc = [t.cpu().numpy() for t in allc]
+    return np.asarray([int(allc[p][:rank].sum()) for p in peers], dtype=np.int64)
+
+
+def init_comm(ctx, dist=None, peer_window_bytes=128 << 20):
     """Create the library's NCCL communicator: rank 0 makes the unique id, torch.distributed broadcasts it."""
     import torch
     if dist is None:
@@ -114,3 +138,41 @@ def init_comm(ctx, dist=None):
         buf = buf.to(torch.device("cuda", torch.cuda.current_device()))
     dist.broadcast(buf, 0)
     ctx.init_comm(rank, nranks, bytes(buf.cpu().numpy().tobytes()))
+    if peer_window_bytes and dist.get_backend() == "nccl" and 2 <= nranks <= 8:
+        init_peer_window(ctx, dist, peer_window_bytes)
+
+
+def init_peer_window(ctx, dist, halo_bytes):
+    """NVLink fast path: create this rank's window, all-gather the CUDA IPC handles, map the peers' windows.
+    Every rank must succeed, otherwise all stay on NCCL (the decision is all-reduced)."""
+    import torch
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nranks = dist.get_world_size()
+    ok = 1
+    try:
+        handle = ctx.peer_window_create(halo_bytes)
+    except capi.DeError:
+        handle, ok = bytes(64), 0
+    mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).clone().to(dev)
+    allh = [torch.zeros_like(mine) for _ in range(nranks)]
+    dist.all_gather(allh, mine)
+    flag = torch.tensor([ok], dtype=torch.int64, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return False
+    handles = b"".join(bytes(t.cpu().numpy().tobytes()) for t in allh)
+    # opening must succeed everywhere before anyone uses the windows
+    try:
+        ctx_ok = 1
+        ctx._peer_handles = handles
+        capi.check(capi.lib().de_context_peer_window_open(ctx._h, (capi.C.c_char * len(handles)).from_buffer_copy(handles)),
+                   ctx._h)
+    except capi.DeError:
+        ctx_ok = 0
+    flag = torch.tensor([ctx_ok], dtype=torch.int64, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    if int(flag.item()) == 0 and ctx_ok:
+        raise RuntimeError("NVLink peer window: mapped on this rank but not on all ranks; cannot continue consistently")
+    return bool(int(flag.item()))

@@ -66,7 +66,8 @@ int de_context_launch_count(const de_context *ctx, int64_t *count);
 #define DE_PROF_DOT 4     /* diag_dot_kernel */
 #define DE_PROF_TRSV 5    /* permute / level / chain kernels of the factored apply */
 #define DE_PROF_MISC 6    /* layout conversion, halo pack, eigenvector extraction */
-#define DE_PROF_CATEGORIES 7
+#define DE_PROF_SPMM_BOUNDARY 7 /* boundary-row launches of a distributed SpMM (they wait for the halo rows) */
+#define DE_PROF_CATEGORIES 8
 /* enable: 0 = off, 1 = every category, otherwise a bit mask of categories shifted left by one (2 << DE_PROF_SPMM | ...) */
 int de_context_set_profiling(de_context *ctx, int enable);
 int de_context_profile(de_context *ctx, int category, double *total_ms, int64_t *launches, int reset);
@@ -78,6 +79,17 @@ int de_context_profile(de_context *ctx, int category, double *total_ms, int64_t 
 int de_comm_unique_id(void *id128);
 int de_context_init_comm(de_context *ctx, int rank, int nranks, const void *id128);
 int de_context_rank(const de_context *ctx, int *rank, int *nranks);
+
+/* Optional NVLink fast path of the multi-GPU data path (csrc/kernels_peer.cuh): every rank creates a window in its
+ * HBM (flags, all-reduce slots, two halo buffers of halo_bytes each) and receives a 64-byte CUDA IPC handle; the
+ * handles of all ranks, in rank order (nranks x 64 bytes), are passed to ..._open, which maps the peers' windows.
+ * The caller exchanges the handles (torch.distributed in parallel.py) and runs a barrier after ..._open. From then on
+ * the short all-reduces are one-shot peer-memory kernels, and matrices that were told where their rows go in the
+ * neighbours' halo blocks (de_matrix_set_peer_deposit) send halo rows as peer stores instead of ncclSend/ncclRecv.
+ * Without a window, or if the IPC mapping fails (DE_ERR_UNSUPPORTED), everything runs over NCCL. */
+int de_context_peer_window_create(de_context *ctx, int64_t halo_bytes, void *ipc_handle64);
+int de_context_peer_window_open(de_context *ctx, const void *ipc_handles);
+int de_context_peer_ready(const de_context *ctx, int *ready);
 
 /* ---- sparse matrix: replaces BCRSMatrix<FieldMatrix<double,1,1>> traversal ------------------------
  * (eigensolver.hh:32-66,208-252; kernels_cpp.hh:383-392,644-653). Header code flattens BCRS -> CSR once
@@ -93,6 +105,9 @@ int de_matrix_create_distributed(de_context *ctx, int64_t n_owned, int64_t n_hal
                                  const int64_t *rowptr, const int64_t *col_local, const double *val, int npeers,
                                  const int *peer_ranks, const int64_t *recv_counts, const int64_t *send_offsets,
                                  const int64_t *send_rows, de_matrix **out);
+/* deposit_rows[p]: the row of peer p's halo block (its [owned | halo] numbering minus n_owned) at which the rows this
+ * rank sends to peer p start. Enables peer-store halo exchange for this matrix (needs the context's peer window). */
+int de_matrix_set_peer_deposit(de_matrix *A, const int64_t *deposit_rows);
 int de_matrix_destroy(de_matrix *A);
 int de_matrix_rows(const de_matrix *A, int64_t *n_owned, int64_t *nnz);
 

@@ -269,6 +269,11 @@ int main(int argc, char **argv)
       if (np == 4)
         ms = time_it([&] { launch(de::spmm_brb_kernel<4, false, false, false>, false); }, reps);
       check(nm, ms);
+      if (np == 4)
+      {
+        ms = time_it([&] { launch(de::spmm_brb_kernel<4, false, true, false>, false); }, reps);
+        check("brb HALO variant (no halo cols)", ms);
+      }
       if (np == 1)
         ms = time_it([&] { launch(de::spmm_brb_kernel<1, true, false, false>, true); }, reps);
       if (np == 2)
