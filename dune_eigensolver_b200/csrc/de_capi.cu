@@ -34,6 +34,7 @@
 #include "brb_format.hpp"
 #include "kernels_brb_build.cuh"
 #include "kernels_peer.cuh"
+#include "kernels_tail.cuh"
 #include "kernels_tallskinny.cuh"
 #include "kernels_trsv.cuh"
 
@@ -119,6 +120,11 @@ struct de_context
   unsigned char *peer_base[de::kPeerMaxRanks] = {};
   unsigned long long ar_epoch = 0, halo_epoch = 0;
   int *dticket = nullptr; // [0] ticket of halo_push_kernel, [1] peer error flag
+  // fused tail of the NEXT partial-sum reduction (kernels_tail.cuh): set by the caller, consumed by reduce_partials
+  de::TailArgs tail{};
+  bool tail_armed = false;
+  bool tail_did_allreduce = false, tail_did_op = false; // one-shot: the following allreduce_sum / chol / convergence is skipped
+  int *dtail_ticket = nullptr;
   size_t dconv_cap = 0;
   double *hsmall = nullptr;   // pinned mirror of dsmall
   int *hstatus = nullptr;     // pinned
@@ -682,10 +688,29 @@ namespace
   }
 
   // ---- reductions -----------------------------------------------------------------------------------
+  de::PeerArgs peer_args(de_context *ctx, unsigned long long epoch);
+
   int reduce_partials(de_context *ctx, const double *partials, int nparts, int len, double *out)
   {
     dim3 block(32, 32);
     ProfScope prof(ctx, DE_PROF_SMALL);
+    const bool multi = ctx->nranks > 1;
+    if (ctx->tail_armed && ctx->dtail_ticket && (!multi || (ctx->peer_ready && len <= de::kPeerSlotDoubles)))
+    {
+      // reduce -> (all-reduce) -> Cholesky / convergence test in ONE launch
+      de::TailArgs t = ctx->tail;
+      t.do_allreduce = multi ? 1 : 0;
+      if (multi)
+        t.pa = peer_args(ctx, ++ctx->ar_epoch);
+      t.ticket = ctx->dtail_ticket;
+      ctx->tail_armed = false;
+      ctx->tail_did_allreduce = true;
+      ctx->tail_did_op = true;
+      de::reduce_tail_kernel<<<(len + 31) / 32, block, 0, ctx->stream>>>(partials, nparts, len, out, ctx->done_ptr, t);
+      DE_LAUNCH_CHECK(ctx);
+      return DE_OK;
+    }
+    ctx->tail_armed = false;
     de::reduce_partials_kernel<<<(len + 31) / 32, block, 0, ctx->stream>>>(partials, nparts, len, out, ctx->done_ptr);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
@@ -706,6 +731,11 @@ namespace
 
   int allreduce_sum(de_context *ctx, double *buf, size_t count)
   {
+    if (ctx->tail_did_allreduce)
+    {
+      ctx->tail_did_allreduce = false; // the fused tail of the reduction already did it
+      return DE_OK;
+    }
     if (ctx->nranks <= 1)
       return DE_OK;
     if (ctx->peer_ready && count <= (size_t)de::kPeerSlotDoubles)
@@ -1536,6 +1566,11 @@ namespace
   // ---- (B-)orthonormalisation: CholQR2 ------------------------------------------------------------------
   int chol_inverse(de_context *ctx, int m, const double *G, double *Rinv, double *info, int *identity_flag = nullptr)
   {
+    if (ctx->tail_did_op)
+    {
+      ctx->tail_did_op = false; // done by the fused tail of the reduction that produced G
+      return DE_OK;
+    }
     ProfScope prof(ctx, DE_PROF_SMALL);
     if (m <= 32)
       de::chol_inverse2_kernel<32><<<1, 1024, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag,
@@ -1545,6 +1580,22 @@ namespace
                                                                 const_cast<int *>(ctx->done_ptr));
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
+  }
+
+  /** the next partial-sum reduction (of a Gram matrix into G) is followed, in the same launch, by the all-reduce and by
+   *  Rinv = chol(G)^-1 -- exactly what chol_inverse(ctx, m, G, Rinv, info, identity_flag) would do afterwards */
+  void arm_chol_tail(de_context *ctx, int m, double *Rinv, double *info, int *identity_flag)
+  {
+    ctx->tail = de::TailArgs{};
+    ctx->tail.kind = de::kTailChol;
+    ctx->tail.m = m;
+    ctx->tail.Rinv = Rinv;
+    ctx->tail.status = ctx->dstatus;
+    ctx->tail.info = info;
+    ctx->tail.identity_flag = identity_flag;
+    ctx->tail.done = const_cast<int *>(ctx->done_ptr);
+    ctx->tail_armed = true;
+    ctx->tail_did_allreduce = ctx->tail_did_op = false;
   }
 
   /** X <- X R^-1 (thin QR with positive-diagonal triangular R; reference orthonormalize_blocked,
@@ -1558,7 +1609,10 @@ namespace
       // sweep 1: G = X^T X (already known if the SpMM that produced X ran its Gram epilogue) ; R1 = chol(G) ;
       // X <- X R1^-1 fused with G2 = X^T X of the result
       if (G_ready == nullptr)
+      {
+        arm_chol_tail(ctx, m, ctx->dR(), nullptr, nullptr);
         DE_TRY(gram_device(ctx, m, n, X, m, X, m, true, ctx->dG()));
+      }
       DE_TRY(chol_inverse(ctx, m, G_ready ? G_ready : ctx->dG(), ctx->dR(), nullptr, nullptr));
       de::TsArgs a{};
       a.n = n;
@@ -1568,9 +1622,12 @@ namespace
       a.Out = X;
       a.ldo = m;
       a.upper = 1;
+      // sweep 2: R2 = chol(G2) ; X <- X R2^-1, skipped on the device when G2 = I to working precision. The factor of
+      // sweep 1 is read at the start of the update kernel and overwritten by the tail of its reduction: the factor
+      // fragments are in registers long before the last CTA of the reduction runs (it is a later launch).
+      arm_chol_tail(ctx, m, ctx->dR(), nullptr, ctx->dflags);
       DE_TRY((launch_ts<true, true, true, true>(ctx, m, a, ctx->dG())));
       DE_TRY(allreduce_sum(ctx, ctx->dG(), (size_t)m * m));
-      // sweep 2: R2 = chol(G2) ; X <- X R2^-1, skipped on the device when G2 = I to working precision
       DE_TRY(chol_inverse(ctx, m, ctx->dG(), ctx->dR(), nullptr, ctx->dflags));
       return update_device<0>(ctx, m, n, X, m, ctx->dR(), X, m, 1, ctx->dflags);
     }
@@ -1903,6 +1960,8 @@ extern "C"
               cudaMalloc((void **)&ctx->dsmall, kSmall * sizeof(double)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->dstatus, sizeof(int)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->dflags, 4 * sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->dtail_ticket, sizeof(int)) == cudaSuccess &&
+              cudaMemset(ctx->dtail_ticket, 0, sizeof(int)) == cudaSuccess &&
               cudaMemset(ctx->dflags, 0, 4 * sizeof(int)) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->hsmall, kSmall * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->hstatus, sizeof(int)) == cudaSuccess &&
@@ -1937,6 +1996,7 @@ extern "C"
     dev_free(ctx->dsmall);
     dev_free(ctx->dstatus);
     dev_free(ctx->dflags);
+    dev_free(ctx->dtail_ticket);
     dev_free(ctx->stage);
     if (ctx->hsmall)
       cudaFreeHost(ctx->hsmall);
@@ -2961,9 +3021,27 @@ extern "C"
         DE_TRY(spmm_device<false>(ctx, A, Qa, Qb, m)); // Qb = A Qa (:78)
       DE_TRY(orthonormalize_device(ctx, n, m, Qb, have_gram ? ctx->dDG() + m : nullptr)); // (:81)
       // Qa = A Qb, dp = diag(Qb^T Qa) (:84-85) and, in the same pass, G = Qa^T Qa for the next orthonormalisation
+      // ... and the convergence test as the tail of the reduction of the dot-product partials
+      ctx->tail = de::TailArgs{};
+      ctx->tail.kind = de::kTailConv;
+      ctx->tail.m = m;
+      ctx->tail.k = k;
+      ctx->tail.shift = shift;
+      ctx->tail.tol = tol;
+      ctx->tail.s_prev = s_prev;
+      ctx->tail.hist = hist;
+      ctx->tail.flags = ctx->dflags;
+      ctx->tail_armed = true;
+      ctx->tail_did_allreduce = ctx->tail_did_op = false;
       DE_TRY(spmm_device<true>(ctx, A, Qb, Qa, m, kFuseGramIntoSpmm ? &have_gram : nullptr));
-      de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(k, m, shift, tol, ctx->dDP(), s_prev, hist, ctx->dflags);
-      DE_LAUNCH_CHECK(ctx);
+      if (ctx->tail_did_op)
+        ctx->tail_did_op = false;
+      else
+      {
+        de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(k, m, shift, tol, ctx->dDP(), s_prev, hist, ctx->dflags);
+        DE_LAUNCH_CHECK(ctx);
+      }
+      ctx->tail_armed = false;
       std::swap(Qa, Qb); // now Qa orthonormal, Qb = A*Qa
       have_product = true;
       ++enqueued;

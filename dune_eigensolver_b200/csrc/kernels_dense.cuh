@@ -381,20 +381,18 @@ namespace de
    *    inverse         Gauss-Jordan from the bottom: x_k /= r_kk; x_i -= r_ik x_k   (i < k), X starts as I
    *  1024 threads: element (i, j) = (w + 32 a, l + 32 b) belongs to warp w, lane l, slot (a, b). */
   template <int MP>
-  __global__ void __launch_bounds__(1024) chol_inverse2_kernel(int m, const double *__restrict__ G, double *__restrict__ Rinv,
-                                                               int *__restrict__ status, double *__restrict__ info,
-                                                               int *__restrict__ identity_flag, int *__restrict__ done)
+  __device__ __forceinline__ void chol_inverse2_body(int tid, int m, const double *__restrict__ G, double *__restrict__ Rinv,
+                                                     int *__restrict__ status, double *__restrict__ info,
+                                                     int *__restrict__ identity_flag, int *__restrict__ done)
   {
     constexpr int E = MP / 32;
-    if (done != nullptr && *done != 0)
-      return;
     __shared__ double rowk[2][MP];
     __shared__ double colk[2][MP];
     __shared__ double dorig[MP];
     __shared__ double dinv[MP]; // 1 / r_kk
     __shared__ double redmx[32], reddev[32];
     __shared__ int bad;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0)
       bad = 0;
 
@@ -409,7 +407,7 @@ namespace de
         double v = (i == j) ? 1.0 : 0.0; // identity padding
         if (i < m && j < m)
         {
-          v = (i <= j) ? G[i * m + j] : 0.0;
+          v = (i <= j) ? __ldcg(G + i * m + j) : 0.0; // L2: G may have been written by other CTAs of this launch
           if (i < j)
             mx = fmax(mx, v);
           if (i <= j)
@@ -553,6 +551,16 @@ namespace de
         if (i < m && j < m)
           Rinv[i * m + j] = (i <= j) ? x[a][b] : 0.0;
       }
+  }
+
+  template <int MP>
+  __global__ void __launch_bounds__(1024) chol_inverse2_kernel(int m, const double *__restrict__ G, double *__restrict__ Rinv,
+                                                               int *__restrict__ status, double *__restrict__ info,
+                                                               int *__restrict__ identity_flag, int *__restrict__ done)
+  {
+    if (done != nullptr && *done != 0)
+      return;
+    chol_inverse2_body<MP>(threadIdx.x, m, G, Rinv, status, info, identity_flag, done);
   }
 
 } // namespace de

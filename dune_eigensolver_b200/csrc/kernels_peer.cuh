@@ -81,18 +81,16 @@ namespace de
     return reinterpret_cast<double *>(base + kPeerArOff) + (size_t)(parity * kPeerMaxRanks + sender) * kPeerSlotDoubles;
   }
 
-  /** buf[0..len) <- sum over ranks, identical bits on every rank. One CTA of 1024 threads. */
-  __global__ void __launch_bounds__(1024) peer_allreduce_kernel(const PeerArgs pa, double *__restrict__ buf, int len)
+  /** buf[0..len) <- sum over ranks, identical bits on every rank; executed by one CTA of 1024 threads (tid).
+   *  buf may have been written by other CTAs of the same launch: it is read through L2. */
+  __device__ __forceinline__ void peer_allreduce_body(const PeerArgs &pa, int tid, double *__restrict__ buf, int len)
   {
-    if (pa.done != nullptr && *pa.done != 0)
-      return;
-    const int tid = threadIdx.x;
     const int parity = (int)(pa.epoch & 1ull);
     for (int q = 0; q < pa.nranks; ++q)
     {
       double *dst = peer_ar_slot(pa.base[q], parity, pa.rank);
       for (int i = tid; i < len; i += 1024)
-        dst[i] = buf[i];
+        dst[i] = __ldcg(buf + i);
     }
     __threadfence_system();
     __syncthreads();
@@ -110,6 +108,15 @@ namespace de
         s += __ldcg(peer_ar_slot(pa.base[pa.rank], parity, q) + i);
       buf[i] = s;
     }
+    __threadfence();
+    __syncthreads();
+  }
+
+  __global__ void __launch_bounds__(1024) peer_allreduce_kernel(const PeerArgs pa, double *__restrict__ buf, int len)
+  {
+    if (pa.done != nullptr && *pa.done != 0)
+      return;
+    peer_allreduce_body(pa, threadIdx.x, buf, len);
   }
 
   struct HaloPushArgs

@@ -485,26 +485,24 @@ namespace de
    *  s_j = dp_j - shift, distance = max_j |s_j - s_prev_j|, s_prev <- s; iteration k > 1 with distance < tol raises
    *  the `done` flag, after which every kernel of the iterations already enqueued returns at once.
    *  state: flags[1] = done, flags[2] = last completed iteration; hist[k] = distance of iteration k. One CTA of 64. */
-  __global__ void __launch_bounds__(64) convergence_kernel(int k, int m, double shift, double tol, const double *__restrict__ dp,
-                                                           double *__restrict__ s_prev, double *__restrict__ hist,
-                                                           int *__restrict__ flags)
+  __device__ __forceinline__ void convergence_body(int tid, int nthreads, int k, int m, double shift, double tol,
+                                                   const double *__restrict__ dp, double *__restrict__ s_prev,
+                                                   double *__restrict__ hist, int *__restrict__ flags)
   {
-    if (flags[1] != 0)
-      return;
     __shared__ double red[64];
-    const int j = threadIdx.x;
     double d = 0.0;
-    if (j < m)
+    if (tid < m)
     {
-      const double s = dp[j] - shift;
-      d = fabs(s - s_prev[j]);
+      const double s = __ldcg(dp + tid) - shift;
+      d = fabs(s - s_prev[tid]);
       if (!(d == d))
         d = 1.0e300; // NaN never converges
-      s_prev[j] = s;
+      s_prev[tid] = s;
     }
-    red[j] = d;
+    if (tid < 64)
+      red[tid] = d;
     __syncthreads();
-    if (j == 0)
+    if (tid == 0)
     {
       double mx = 0.0;
       for (int q = 0; q < 64; ++q)
@@ -514,6 +512,16 @@ namespace de
       if (k > 1 && mx < tol)
         flags[1] = 1;
     }
+    (void)nthreads;
+  }
+
+  __global__ void __launch_bounds__(64) convergence_kernel(int k, int m, double shift, double tol, const double *__restrict__ dp,
+                                                           double *__restrict__ s_prev, double *__restrict__ hist,
+                                                           int *__restrict__ flags)
+  {
+    if (flags[1] != 0)
+      return;
+    convergence_body(threadIdx.x, 64, k, m, shift, tol, dp, s_prev, hist, flags);
   }
 
   // ---- layout conversion at the boundary (reference MultiVector layout <-> row-major) ------------------

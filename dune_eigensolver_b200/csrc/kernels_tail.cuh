@@ -1,0 +1,92 @@
+// Partial-sum reduction with a fused TAIL: what used to be three or four dependent launches of tiny kernels after
+// every tall-skinny reduction (reduce the per-CTA partials -> all-reduce across GPUs -> Cholesky + inverse of the Gram
+// matrix, or the convergence test on the Rayleigh quotients) is one launch. Every CTA reduces its 32 outputs as before
+// (fixed order: deterministic); the CTA that finishes last -- a ticket counter tells -- then runs, with its 1024
+// threads, the one-shot peer all-reduce (kernels_peer.cuh) and the Cholesky / convergence step on the complete vector.
+// On a 27-point 100^3, m = 32 solve the small kernels were 12 % of the time on one GPU and 46 % on eight, almost all
+// of it launch and dependency latency.
+#pragma once
+
+#include "kernels_dense.cuh"
+#include "kernels_peer.cuh"
+#include "kernels_sparse.cuh"
+
+namespace de
+{
+
+  enum
+  {
+    kTailNone = 0,
+    kTailChol = 1, // out = Gram matrix (m x m): Rinv = inverse Cholesky factor
+    kTailConv = 2  // out = [dp (m) | ...]: convergence test of the driver loop
+  };
+
+  struct TailArgs
+  {
+    int kind;
+    int do_allreduce;
+    PeerArgs pa;
+    int *ticket;
+    int m;
+    // Cholesky
+    double *Rinv;
+    int *status;
+    double *info;
+    int *identity_flag;
+    int *done;
+    // convergence
+    int k;
+    double shift, tol;
+    double *s_prev, *hist;
+    int *flags;
+  };
+
+  /** blockDim = (32, 32); gridDim.x = ceil(len / 32) */
+  __global__ void __launch_bounds__(1024) reduce_tail_kernel(const double *__restrict__ partials, int nparts, int len,
+                                                             double *__restrict__ out, const int *__restrict__ done_in,
+                                                             const TailArgs t)
+  {
+    if (done_in != nullptr && *done_in != 0)
+      return;
+    __shared__ double red[32][33];
+    __shared__ int last;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int e = blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    if (e < len)
+      for (int p = threadIdx.y; p < nparts; p += 32)
+        s += partials[(size_t)p * len + e];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < len)
+    {
+      double tot = 0.0;
+#pragma unroll
+      for (int q = 0; q < 32; ++q)
+        tot += red[q][threadIdx.x];
+      out[e] = tot;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+      last = (atomicAdd(t.ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!last)
+      return;
+    if (tid == 0)
+      *t.ticket = 0;
+    __threadfence();
+    if (t.do_allreduce)
+      peer_allreduce_body(t.pa, tid, out, len);
+    if (t.kind == kTailChol)
+    {
+      if (t.m <= 32)
+        chol_inverse2_body<32>(tid, t.m, out, t.Rinv, t.status, t.info, t.identity_flag, t.done);
+      else
+        chol_inverse2_body<64>(tid, t.m, out, t.Rinv, t.status, t.info, t.identity_flag, t.done);
+    }
+    else if (t.kind == kTailConv)
+      convergence_body(tid, 1024, t.k, t.m, t.shift, t.tol, out, t.s_prev, t.hist, t.flags);
+  }
+
+} // namespace de

@@ -32,5 +32,11 @@ def test_row_partitioned_solve(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    try:  # keep the workers' output where gpurun brings it back
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "mgpu_worker_%d.log" % world), "w") as f:
+            f.write(out.stdout[-20000:] + "\n---- stderr ----\n" + out.stderr[-20000:])
+    except OSError:
+        pass
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "fails=0" in out.stdout
