@@ -1674,7 +1674,7 @@ namespace
       DE_CUDA(ctx, cudaMemcpyAsync(ctx->hflags + 7, ctx->dticket + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->hflags[7] != 0)
-      return set_error(ctx, DE_ERR_NCCL, "NVLink peer window: a neighbour rank did not arrive within 2 s");
+      return set_error(ctx, DE_ERR_NCCL, "NVLink peer window: a neighbour rank did not arrive within 30 s");
     if (count > 0 && hdst != ctx->hsmall)
       std::memcpy(hdst, ctx->hsmall, count * sizeof(double));
     if (*ctx->hstatus != 0)
@@ -2325,12 +2325,17 @@ extern "C"
       return fail(s);
     if ((s = upload_converted(ctx, &A->boundary, bd.data(), bd.size())) != DE_OK)
       return fail(s);
-    if ((s = build_staged_subset(ctx, in, rowptr, col_local, val, A->st_interior)) != DE_OK)
-      return fail(s);
-    if ((s = build_staged_subset(ctx, bd, rowptr, col_local, val, A->st_boundary)) != DE_OK)
-      return fail(s);
     if ((s = build_brb(ctx, A, n_owned, n_owned + n_halo, rowptr, col_local, val)) != DE_OK)
       return fail(s);
+    // the row-permuted CSR copies for the staged kernel are only built when the CSR family can be chosen by the AUTO
+    // policy (brb_usable); a forced DE_SPMM_CSR then still works through the row-list kernel
+    if (!(A->brb.valid && nnz >= 12 * n_owned))
+    {
+      if ((s = build_staged_subset(ctx, in, rowptr, col_local, val, A->st_interior)) != DE_OK)
+        return fail(s);
+      if ((s = build_staged_subset(ctx, bd, rowptr, col_local, val, A->st_boundary)) != DE_OK)
+        return fail(s);
+    }
     *out = A;
     return DE_OK;
   }
@@ -2549,13 +2554,26 @@ extern "C"
     *n_halo = (int64_t)ext.size();
     for (size_t h = 0; h < ext.size(); ++h)
       halo_global[h] = ext[h];
-    for (int64_t k = 0; k < nnz; ++k)
     {
-      const int64_t g = col_global[k];
-      if (g >= lo && g < hi)
-        col_local[k] = g - lo;
-      else
-        col_local[k] = n_owned + (std::lower_bound(ext.begin(), ext.end(), g) - ext.begin());
+      const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(8, nnz >> 20));
+      auto work = [&](int t)
+      {
+        const int64_t k0 = nnz * t / nth, k1 = nnz * (t + 1) / nth;
+        for (int64_t k = k0; k < k1; ++k)
+        {
+          const int64_t g = col_global[k];
+          if (g >= lo && g < hi)
+            col_local[k] = g - lo;
+          else
+            col_local[k] = n_owned + (std::lower_bound(ext.begin(), ext.end(), g) - ext.begin());
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nth; ++t)
+        th.emplace_back(work, t);
+      work(0);
+      for (auto &x : th)
+        x.join();
     }
     return DE_OK;
   }

@@ -17,7 +17,7 @@
 //
 // Flow control needs no credits: consecutive SpMM calls alternate between the two halo buffers, and a rank cannot be
 // two calls ahead of a neighbour because its boundary rows need that neighbour's rows of the call in between; an
-// all-reduce is itself a barrier, so two slot sets suffice. Spins give up after ~2 s and raise an error flag.
+// all-reduce is itself a barrier, so two slot sets suffice. Spins give up after ~30 s and raise an error flag (a neighbour that died must not hang the GPU).
 #pragma once
 
 #include <cstdint>
@@ -57,7 +57,7 @@ namespace de
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < epoch)
     {
-      if (clock64() - t0 > 4000000000LL) // ~2 s
+      if (clock64() - t0 > 60000000000LL) // ~30 s: ranks of a multi-process job can be seconds apart on the host
       {
         if (err)
           *err = 1;

@@ -47,9 +47,10 @@ def main():
         # SpMM with halo exchange + fused all-reduced dots, both kernel families (tensor-core BRB tiles / CSR rows)
         ref = orc.spmm(Aglob, Xg)
         dref = orc.diag_dot(Xg, ref)
-        fmts = ["csr", "brb"] if dA.spmm_info()["tiles"] > 0 else ["csr"]
-        for fmt in fmts:
-            dA.set_spmm_format(fmt)
+        # every rank must make the same sequence of collective calls: ranks whose local block has no BRB form (e.g.
+        # no rows at all when there are fewer grid planes than ranks) run the second round with their only kernel family
+        for fmt in ("csr", "brb"):
+            dA.set_spmm_format(fmt if (fmt == "csr" or dA.spmm_info()["tiles"] > 0) else "auto")
             dY.upload(np.zeros((r1 - r0, m)))
             dp = E.matmul_sparse_tallskinny_with_dots(dY, dA, dX)
             Yg = gather_rows(dY.download(), part)
