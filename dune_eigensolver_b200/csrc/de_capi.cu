@@ -234,6 +234,7 @@ struct de_matrix
   BrbDevice brb;
   bool peer_halo = false;            // halo rows travel as peer stores into the neighbours' windows
   std::vector<long long> deposit;    // [npeers] first row of this rank's rows in peer p's halo block
+  long long halo_rows_max = 0;       // largest halo block over ALL ranks: peer path or NCCL must be the same decision everywhere
   int spmm_format = DE_SPMM_AUTO; // which SpMM kernel family to use (de_matrix_set_spmm_format)
 };
 
@@ -1223,6 +1224,11 @@ namespace
     de_matrix *A = const_cast<de_matrix *>(Ac);
     int g1 = 0, g2 = 0;
     const bool dist = ctx->nranks > 1 && (A->n_halo > 0 || A->n_send > 0);
+    // peer-store halo exchange? decided from quantities that are equal on all ranks; the epoch advances on every rank
+    // of the job, also on one that has neither halo rows nor rows to send for this matrix
+    const bool peer_path = ctx->nranks > 1 && ctx->peer_ready && A->peer_halo &&
+                           (size_t)A->halo_rows_max * m * sizeof(double) <= ctx->halo_cap && A->npeers <= de::kPeerMaxRanks;
+    const unsigned long long halo_epoch = peer_path ? ++ctx->halo_epoch : 0ull;
     // GRAM epilogue: the caller can use G = Y^T Y (in ctx->dDG() + m); only the tensor-core kernel has it
     const bool gram = DOT && gram_out != nullptr && brb_usable(A, m) && brb_gram_epilogue(m);
     if (gram_out)
@@ -1243,13 +1249,12 @@ namespace
     }
     else
     {
-      const bool peer = ctx->peer_ready && A->peer_halo && (size_t)A->n_halo * m * sizeof(double) <= ctx->halo_cap &&
-                        A->npeers <= de::kPeerMaxRanks;
+      const bool peer = peer_path;
       de::PeerArgs pa{};
       if (peer)
       {
         // halo rows go straight into the neighbours' windows; the boundary tiles wait for this epoch's flags
-        pa = peer_args(ctx, ++ctx->halo_epoch);
+        pa = peer_args(ctx, halo_epoch);
         A->halo_view = reinterpret_cast<double *>(ctx->window + de::kPeerHaloOff + (size_t)(pa.epoch & 1ull) * ctx->halo_cap);
         if (A->n_send > 0)
         {
@@ -2204,9 +2209,9 @@ extern "C"
     return DE_OK;
   }
 
-  int de_matrix_set_peer_deposit(de_matrix *A, const int64_t *deposit_rows)
+  int de_matrix_set_peer_deposit(de_matrix *A, const int64_t *deposit_rows, int64_t max_halo_rows_all_ranks)
   {
-    if (!A || (A->npeers > 0 && !deposit_rows))
+    if (!A || (A->npeers > 0 && !deposit_rows) || max_halo_rows_all_ranks < 0)
       return set_error(A ? A->ctx : nullptr, DE_ERR_INVALID, "de_matrix_set_peer_deposit: bad arguments");
     if (!A->ctx->peer_ready)
       return set_error(A->ctx, DE_ERR_UNSUPPORTED, "de_matrix_set_peer_deposit: the context has no peer window");
@@ -2216,6 +2221,7 @@ extern "C"
     for (int p = 0; p < A->npeers; ++p)
       if (A->deposit[p] < 0)
         return set_error(A->ctx, DE_ERR_INVALID, "de_matrix_set_peer_deposit: negative offset");
+    A->halo_rows_max = std::max<long long>(max_halo_rows_all_ranks, A->n_halo);
     A->peer_halo = true;
     return DE_OK;
   }

@@ -152,9 +152,9 @@ class Matrix:
                                                       i64ptr(sr), C.byref(h)), ctx._h)
         return cls(ctx, _handle=h)
 
-    def set_peer_deposit(self, deposit_rows):
+    def set_peer_deposit(self, deposit_rows, max_halo_rows_all_ranks):
         d = i64(deposit_rows)
-        check(capi.lib().de_matrix_set_peer_deposit(self._h, i64ptr(d)), self.ctx._h)
+        check(capi.lib().de_matrix_set_peer_deposit(self._h, i64ptr(d), int(max_halo_rows_all_ranks)), self.ctx._h)
 
     def set_spmm_format(self, fmt):
         """'auto' | 'csr' | 'brb' (include/dune_eigensolver_b200.h: de_matrix_set_spmm_format)"""

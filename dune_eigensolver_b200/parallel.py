@@ -99,13 +99,14 @@ def build_distributed_matrix(ctx, rowptr, col_global, val, part, rank, dist=None
     if ctx.peer_ready():
         # where do my rows start in each neighbour's halo block? its halo rows are ordered by owner rank, so the
         # offset is the number of rows it receives from ranks below mine
-        deposits = peer_deposit_offsets(recv_counts, peers, rank, dist)
-        dA.set_peer_deposit(deposits)
+        deposits, max_halo = peer_deposit_offsets(recv_counts, peers, rank, dist)
+        dA.set_peer_deposit(deposits, max_halo)
     return dA
 
 
 def peer_deposit_offsets(recv_counts, peers, rank, dist=None):
-    """all-gather every rank's recv_counts[nranks]; deposit[p] = sum_{q < rank} recv_counts_of_peer_p[q]"""
+    """all-gather every rank's recv_counts[nranks]; deposit[p] = sum_{q < rank} recv_counts_of_peer_p[q].
+    Also returns the largest halo block (rows) over all ranks."""
     import torch
     if dist is None:
         import torch.distributed as dist
@@ -118,7 +119,8 @@ def peer_deposit_offsets(recv_counts, peers, rank, dist=None):
     allc = [torch.zeros_like(mine) for _ in range(nranks)]
     dist.all_gather(allc, mine)
     allc = [t.cpu().numpy() for t in allc]
-    return np.asarray([int(allc[p][:rank].sum()) for p in peers], dtype=np.int64)
+    return (np.asarray([int(allc[p][:rank].sum()) for p in peers], dtype=np.int64),
+            max(int(c.sum()) for c in allc))
 
 
 def init_comm(ctx, dist=None, peer_window_bytes=128 << 20):

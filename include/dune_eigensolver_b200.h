@@ -106,8 +106,10 @@ int de_matrix_create_distributed(de_context *ctx, int64_t n_owned, int64_t n_hal
                                  const int *peer_ranks, const int64_t *recv_counts, const int64_t *send_offsets,
                                  const int64_t *send_rows, de_matrix **out);
 /* deposit_rows[p]: the row of peer p's halo block (its [owned | halo] numbering minus n_owned) at which the rows this
- * rank sends to peer p start. Enables peer-store halo exchange for this matrix (needs the context's peer window). */
-int de_matrix_set_peer_deposit(de_matrix *A, const int64_t *deposit_rows);
+ * rank sends to peer p start; max_halo_rows_all_ranks: the largest halo block of this matrix over all ranks (whether the
+ * halo buffers fit the window must be the same decision on every rank). Enables peer-store halo exchange for this
+ * matrix (needs the context's peer window); every rank of the job must call it for its part of the matrix. */
+int de_matrix_set_peer_deposit(de_matrix *A, const int64_t *deposit_rows, int64_t max_halo_rows_all_ranks);
 int de_matrix_destroy(de_matrix *A);
 int de_matrix_rows(const de_matrix *A, int64_t *n_owned, int64_t *nnz);
 
