@@ -36,6 +36,7 @@
 #include "kernels_peer.cuh"
 #include "kernels_tail.cuh"
 #include "kernels_tallskinny.cuh"
+#include "kernels_tallskinny2.cuh"
 #include "kernels_trsv.cuh"
 
 // ====================================================================================================
@@ -1383,6 +1384,30 @@ namespace
   template <int M, bool DO_UPDATE, bool DO_GRAM, bool UPPER, bool SAME>
   int launch_ts_t(de_context *ctx, de::TsArgs a, double *gram_out)
   {
+    if constexpr (DO_UPDATE && M <= 32 && (!DO_GRAM || (UPPER && SAME)))
+    {
+      // block update (+ Gram of the result): the register-to-register tensor-core kernel (kernels_tallskinny2.cuh)
+      using C2 = de::Ts2Cfg<M>;
+      static bool cfg2 = false;
+      if (!cfg2)
+      {
+        DE_CUDA(ctx, cudaFuncSetAttribute(de::ts2_update_kernel<M, DO_GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)C2::SMEM));
+        cfg2 = true;
+      }
+      const long long nt2 = (a.n + C2::TR - 1) / C2::TR;
+      const int grid2 = (int)std::max<long long>(1, std::min<long long>(nt2, (long long)ctx->sm_count));
+      a.partials = ctx->partials;
+      a.done = ctx->done_ptr;
+      {
+        ProfScope prof(ctx, DE_PROF_UPDATE);
+        de::ts2_update_kernel<M, DO_GRAM><<<grid2, de::kTs2Threads, C2::SMEM, ctx->stream>>>(a);
+      }
+      DE_LAUNCH_CHECK(ctx);
+      if (DO_GRAM)
+        DE_TRY(reduce_partials(ctx, ctx->partials, grid2, M * M, gram_out));
+      return DE_OK;
+    }
     constexpr int NOPS = (DO_GRAM && !SAME) ? 2 : 1;
     using C = de::TsCfg<M, UPPER, NOPS>;
     constexpr size_t smem = de::tall_skinny_smem_bytes<M, DO_UPDATE, DO_GRAM, UPPER, SAME>();

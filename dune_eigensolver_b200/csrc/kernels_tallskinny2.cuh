@@ -1,0 +1,232 @@
+// Second-generation block update (+ Gram) kernel:  Out = X R  and, in the same pass,  G = Out^T Out.
+// This is the second sweep of CholQR2 (X <- X R1^-1 fused with the Gram matrix of the result) -- after the SpMM the
+// most expensive kernel of a StandardLargest iteration.
+//
+// ncu of the first version (tall_skinny_kernel<32,1,1,1,1>, profiles/r01_ncu_kernels_brb.csv): 136 us for 456 MB
+// (0.52 of HBM peak), 12.5 % of the warps active, 170 registers. Per 128-row tile it ran: update from shared memory ->
+// barrier -> result back into shared memory -> barrier -> coalesced write-out -> Gram from shared memory -> barrier:
+// five CTA-wide barriers and a shared-memory round trip of the whole tile, with 8 warps per SM.
+//
+// Here the product is formed TRANSPOSED on the FP64 tensor pipe,  Out^T(8 cols x 8 rows) += R^T(8 x 4) X^T(4 x 8):
+//   A operand = R^T fragment (registers for the whole kernel; a triangular factor needs 20 of 32 for M = 32),
+//   B operand = X(8 rows x 4 cols) fragment straight from the staged tile (stride M + 4 doubles: conflict-free),
+//   C         = lane (g, k) holds Out(rows 2k, 2k+1; column 8 jb + g).
+// C goes to global memory from registers (a warp store covers 4 rows x 64 contiguous bytes), and -- because rows 2kk,
+// 2kk+1 of a column sit in lane kk of the same quad -- one shuffle inside the quad turns C into the operand fragment
+// f = Out(row 4s + k, column 8 jb + g) of the Gram product G(jb, jb') += f(jb)^T f(jb'). Nothing goes back to shared
+// memory and nothing in the loop is a CTA-wide barrier: producer warps fill a ring of tile buffers with cp.async
+// copies that arrive on mbarriers, consumer warps own whole 8-row blocks (same scheme as spmm_brb_kernel).
+//
+// Bounds for M = 32: 16 n M bytes of HBM traffic (70 us on the 100^3 block) and n M^2 (update, triangular)
+// + n M^2 (Gram, symmetric) tensor flops (55 us at the measured 37 TFLOP/s).
+#pragma once
+
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+#include "kernels_spmm_blocked.cuh" // mbarrier / cp.async helpers, dmma884_sp
+#include "kernels_tallskinny.cuh"   // TsArgs
+
+namespace de
+{
+
+  constexpr int kTs2ProducerWarps = 2;
+  constexpr int kTs2ConsumerWarps = 10;
+  constexpr int kTs2Threads = 32 * (kTs2ProducerWarps + kTs2ConsumerWarps);
+  constexpr int kTs2Stages = 3;
+
+  template <int M>
+  struct Ts2Cfg
+  {
+    static constexpr int NB = M / 8;                           // 8-column blocks
+    static constexpr int KS = M / 4;                           // k steps of the update
+    static constexpr int LDT = M + 4;                          // staged row stride (doubles)
+    static constexpr int TR = 8 * kTs2ConsumerWarps * (M == 32 ? 2 : (M == 16 ? 4 : 8)); // rows per tile
+    static constexpr int NBLK = TR / 8;                        // 8-row blocks per tile
+    static constexpr int NT = NB * (NB + 1) / 2;               // Gram tiles jb <= jb'
+    static constexpr size_t STAGE_BYTES = (size_t)TR * LDT * sizeof(double);
+    static constexpr size_t SMEM = 128 + kTs2Stages * STAGE_BYTES;
+  };
+
+  /** a.X (n x M, ld a.ldx) -> a.Out (may alias X), a.R row-major M x M (a.upper: upper triangular);
+   *  DO_GRAM: per-CTA partial of Out^T Out at a.partials[cta * M * M + i * M + j] (full symmetric matrix). */
+  template <int M, bool DO_GRAM>
+  __global__ void __launch_bounds__(kTs2Threads, 1) ts2_update_kernel(const TsArgs a)
+  {
+    using C = Ts2Cfg<M>;
+    constexpr int NPW = kTs2ProducerWarps, NCW = kTs2ConsumerWarps;
+    extern __shared__ __align__(128) unsigned char dyn2[];
+    if (a.skip_flag != nullptr && *a.skip_flag != 0)
+      return;
+    if (a.done != nullptr && *a.done != 0)
+      return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned bar0 = smem_u32(dyn2); // full[s] at +8 s, empty[s] at +8 (kTs2Stages + s)
+    double *tiles = reinterpret_cast<double *>(dyn2 + 128);
+    if (tid == 0)
+    {
+      for (int s = 0; s < kTs2Stages; ++s)
+      {
+        mbar_init(bar0 + 8 * s, 32 * NPW);
+        mbar_init(bar0 + 8 * (kTs2Stages + s), NCW);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long ntiles = (a.n + C::TR - 1) / C::TR;
+    double gacc[DO_GRAM ? C::NT : 1][2];
+#pragma unroll
+    for (int i = 0; i < (DO_GRAM ? C::NT : 1); ++i)
+      gacc[i][0] = gacc[i][1] = 0.0;
+
+    if (warp < NPW)
+    {
+      // ---------------- producers: rows of the tile -> staged rows (zero fill past the end of the block) ----------
+      constexpr int CPR = M / 2;
+      const int ptid = warp * 32 + lane;
+      int s = 0, use = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
+      {
+        if (use > 0)
+          mbar_wait(bar0 + 8 * (kTs2Stages + s), (unsigned)((use - 1) & 1));
+        double *dst = tiles + (size_t)s * C::TR * C::LDT;
+        const long long r0 = t * C::TR;
+#pragma unroll 4
+        for (int e = ptid; e < C::TR * CPR; e += 32 * NPW)
+        {
+          const int r = e / CPR, c = 2 * (e % CPR);
+          const bool in = r0 + r < a.n;
+          const long long row = in ? r0 + r : 0;
+          cp_async16(dst + r * C::LDT + c, a.X + (size_t)row * a.ldx + c, in);
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar0 + 8 * s) : "memory");
+        if (++s == kTs2Stages)
+        {
+          s = 0;
+          ++use;
+        }
+      }
+    }
+    else
+    {
+      // ---------------- consumers ----------------
+      const int cw = warp - NPW;
+      const int g = lane >> 2, k = lane & 3;
+      // R^T fragments: A(i = g, kk = k) of (ks, jb) = R(4 ks + k, 8 jb + g)
+      double rfrag[C::KS][C::NB];
+#pragma unroll
+      for (int ks = 0; ks < C::KS; ++ks)
+#pragma unroll
+        for (int jb = 0; jb < C::NB; ++jb)
+          rfrag[ks][jb] = (!a.upper || ks <= 2 * jb + 1) ? __ldg(a.R + (4 * ks + k) * M + 8 * jb + g) : 0.0;
+
+      int s = 0, use = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
+      {
+        mbar_wait(bar0 + 8 * s, (unsigned)(use & 1));
+        const double *Xs = tiles + (size_t)s * C::TR * C::LDT;
+        const long long r0 = t * C::TR;
+        for (int rb = cw; rb < C::NBLK; rb += NCW)
+        {
+          // B(kk = k, n = g) of step ks = X(row 8 rb + g, column 4 ks + k)
+          const double *xr = Xs + (rb * 8 + g) * C::LDT + k;
+          double c[C::NB][2];
+#pragma unroll
+          for (int jb = 0; jb < C::NB; ++jb)
+            c[jb][0] = c[jb][1] = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < C::KS; ++ks)
+          {
+            const double xv = xr[4 * ks];
+#pragma unroll
+            for (int jb = 0; jb < C::NB; ++jb)
+              if (!a.upper || ks <= 2 * jb + 1) // triangular factor: column block jb only sees k < 8 jb + 8 (uniform)
+                dmma884_sp(c[jb][0], c[jb][1], rfrag[ks][jb], xv);
+          }
+          // c[jb] = Out(rows 8 rb + 2k, + 2k + 1; column 8 jb + g)
+          const long long row0 = r0 + rb * 8 + 2 * k;
+#pragma unroll
+          for (int jb = 0; jb < C::NB; ++jb)
+          {
+            if (row0 < a.n)
+              a.Out[(size_t)row0 * a.ldo + 8 * jb + g] = c[jb][0];
+            if (row0 + 1 < a.n)
+              a.Out[(size_t)(row0 + 1) * a.ldo + 8 * jb + g] = c[jb][1];
+          }
+          if (DO_GRAM)
+          {
+            // rows past the end of the block were staged as zeros: they add nothing
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+            {
+              const int src = (lane & ~3) | (2 * sl + (k >> 1));
+              double f[C::NB];
+#pragma unroll
+              for (int jb = 0; jb < C::NB; ++jb)
+              {
+                const double v0 = __shfl_sync(0xffffffffu, c[jb][0], src);
+                const double v1 = __shfl_sync(0xffffffffu, c[jb][1], src);
+                f[jb] = (k & 1) ? v1 : v0; // Out(row 4 sl + k, column 8 jb + g)
+              }
+              int ti = 0;
+#pragma unroll
+              for (int bi = 0; bi < C::NB; ++bi)
+#pragma unroll
+                for (int bj = bi; bj < C::NB; ++bj)
+                {
+                  dmma884_sp(gacc[ti][0], gacc[ti][1], f[bi], f[bj]); // D(i = g, j = 2k, 2k+1) of tile (bi, bj)
+                  ++ti;
+                }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0)
+          mbar_arrive(bar0 + 8 * (kTs2Stages + s));
+        if (++s == kTs2Stages)
+        {
+          s = 0;
+          ++use;
+        }
+      }
+    }
+
+    if (DO_GRAM)
+    {
+      // fold the consumer warps in fixed order into one M x M matrix, mirror the strict lower block triangle
+      __syncthreads();
+      double *G = tiles;
+      const int g = lane >> 2, k = lane & 3;
+      for (int turn = 0; turn < NCW; ++turn)
+      {
+        if (warp - NPW == turn)
+        {
+          int ti = 0;
+#pragma unroll
+          for (int bi = 0; bi < C::NB; ++bi)
+#pragma unroll
+            for (int bj = bi; bj < C::NB; ++bj)
+            {
+#pragma unroll
+              for (int e = 0; e < 2; ++e)
+              {
+                const int gi = 8 * bi + g, gj = 8 * bj + 2 * k + e;
+                G[gi * M + gj] = gacc[ti][e] + (turn == 0 ? 0.0 : G[gi * M + gj]);
+              }
+              ++ti;
+            }
+        }
+        __syncthreads();
+      }
+      double *outp = a.partials + (size_t)blockIdx.x * M * M;
+      for (int e = tid; e < M * M; e += kTs2Threads)
+      {
+        const int i = e / M, j = e % M;
+        outp[e] = ((i >> 3) <= (j >> 3)) ? G[e] : G[j * M + i];
+      }
+    }
+  }
+
+} // namespace de
