@@ -1408,6 +1408,27 @@ namespace
         DE_TRY(reduce_partials(ctx, ctx->partials, grid2, M * M, gram_out));
       return DE_OK;
     }
+    if constexpr (!DO_UPDATE && DO_GRAM && UPPER && SAME)
+    {
+      // G = X^T X of one block: warp-specialised tensor-core kernel (kernels_tallskinny2.cuh)
+      using C3 = de::Tg2Cfg<M>;
+      static bool cfg3 = false;
+      if (!cfg3)
+      {
+        DE_CUDA(ctx, cudaFuncSetAttribute(de::ts2_gram_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3::SMEM));
+        cfg3 = true;
+      }
+      const long long nt3 = (a.n + C3::TR - 1) / C3::TR;
+      const int grid3 = (int)std::max<long long>(1, std::min<long long>(nt3, (long long)ctx->sm_count));
+      a.partials = ctx->partials;
+      a.done = ctx->done_ptr;
+      {
+        ProfScope prof(ctx, DE_PROF_GRAM);
+        de::ts2_gram_kernel<M><<<grid3, de::kTg2Threads, C3::SMEM, ctx->stream>>>(a);
+      }
+      DE_LAUNCH_CHECK(ctx);
+      return reduce_partials(ctx, ctx->partials, grid3, M * M, gram_out);
+    }
     constexpr int NOPS = (DO_GRAM && !SAME) ? 2 : 1;
     using C = de::TsCfg<M, UPPER, NOPS>;
     constexpr size_t smem = de::tall_skinny_smem_bytes<M, DO_UPDATE, DO_GRAM, UPPER, SAME>();
@@ -2812,7 +2833,8 @@ extern "C"
       return set_error(ctx, DE_ERR_INVALID, "dot_products_blocked: number of columns does not match"); // :64
     DE_TRY(bind_device(ctx));
     DE_TRY(reset_status(ctx));
-    DE_TRY(gram_device(ctx, X->m, X->n, X->d, X->m, Y->d, Y->m, false, ctx->dG()));
+    // X^T X is symmetric: only the upper block triangle is computed (and mirrored) when both operands are the same block
+    DE_TRY(gram_device(ctx, X->m, X->n, X->d, X->m, Y->d, Y->m, X->d == Y->d, ctx->dG()));
     return fetch_small(ctx, ctx->dG(), G_host, (size_t)X->m * X->m);
   }
 

@@ -444,6 +444,22 @@ namespace de
         info[0] = (m > 1) ? t : 0.0;
       if (identity_flag != nullptr)
         identity_flag[0] = (u <= 1.0e-14) ? 1 : 0;
+      bad = (identity_flag != nullptr && u <= 1.0e-14) ? -1 : 0; // -1: G = I to working precision, nothing to factor
+    }
+    __syncthreads();
+    if (bad == -1)
+    {
+      // the update that would use the factor skips itself on the same flag; leave Rinv = I for any other reader
+#pragma unroll
+      for (int a = 0; a < E; ++a)
+#pragma unroll
+        for (int b = 0; b < E; ++b)
+        {
+          const int i = warp + 32 * a, j = lane + 32 * b;
+          if (i < m && j < m)
+            Rinv[i * m + j] = (i == j) ? 1.0 : 0.0;
+        }
+      return;
     }
 
     // ---- factorisation ----

@@ -230,3 +230,165 @@ namespace de
   }
 
 } // namespace de
+
+namespace de
+{
+  // ------------------------------------------------------------------------------------------------------------
+  // Gram matrix of one block, G = X^T X (upper block triangle computed, mirrored on output), M = 8/16/32/64.
+  // Same ring of staged tiles and the same producer warps as ts2_update_kernel. A consumer warp takes 4-row slabs; the
+  // operand fragment of column block jb, f(jb) = X(row 4 s + k, column 8 jb + g), is ONE conflict-free 64-bit shared load
+  // (it serves as A and as B operand). At M = 64 the 36 tiles of the upper triangle (72 accumulator registers each way)
+  // are split over two tile groups: warps 2w and 2w+1 work on the same slabs with half of the tiles each.
+  // The first version ran 8 warps per SM with a CTA barrier per tile: 0.15 of HBM peak at M = 64 (DMMA latency-bound).
+  // ------------------------------------------------------------------------------------------------------------
+  constexpr int kTg2ConsumerWarps = 12;
+  constexpr int kTg2Threads = 32 * (kTs2ProducerWarps + kTg2ConsumerWarps);
+
+  template <int M>
+  struct Tg2Cfg
+  {
+    static constexpr int NB = M / 8;
+    static constexpr int LDT = M + 4;
+    static constexpr int TG = (M == 64) ? 2 : 1;                       // tile groups
+    static constexpr int SW = kTg2ConsumerWarps / TG;                  // slab workers per tile group
+    static constexpr int TR = (M == 64) ? 96 : (M == 32 ? 192 : (M == 16 ? 384 : 768)); // rows per tile (multiple of 4 SW)
+    static constexpr int NT = NB * (NB + 1) / 2;
+    static constexpr int NTW = (NT + TG - 1) / TG;                     // tiles per warp
+    static constexpr size_t STAGE_BYTES = (size_t)TR * LDT * sizeof(double);
+    static constexpr size_t SMEM = 128 + kTs2Stages * STAGE_BYTES;
+  };
+
+  template <int M>
+  __global__ void __launch_bounds__(kTg2Threads, 1) ts2_gram_kernel(const TsArgs a)
+  {
+    using C = Tg2Cfg<M>;
+    constexpr int NPW = kTs2ProducerWarps, NCW = kTg2ConsumerWarps;
+    extern __shared__ __align__(128) unsigned char dyn3[];
+    if (a.done != nullptr && *a.done != 0)
+      return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned bar0 = smem_u32(dyn3);
+    double *tiles = reinterpret_cast<double *>(dyn3 + 128);
+    if (tid == 0)
+    {
+      for (int s = 0; s < kTs2Stages; ++s)
+      {
+        mbar_init(bar0 + 8 * s, 32 * NPW);
+        mbar_init(bar0 + 8 * (kTs2Stages + s), NCW);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long ntiles = (a.n + C::TR - 1) / C::TR;
+    double gacc[C::NTW][2];
+#pragma unroll
+    for (int i = 0; i < C::NTW; ++i)
+      gacc[i][0] = gacc[i][1] = 0.0;
+    const int cw = warp - NPW;
+    const int tgi = cw % C::TG, swi = cw / C::TG;
+
+    if (warp < NPW)
+    {
+      constexpr int CPR = M / 2;
+      const int ptid = warp * 32 + lane;
+      int s = 0, use = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
+      {
+        if (use > 0)
+          mbar_wait(bar0 + 8 * (kTs2Stages + s), (unsigned)((use - 1) & 1));
+        double *dst = tiles + (size_t)s * C::TR * C::LDT;
+        const long long r0 = t * C::TR;
+#pragma unroll 4
+        for (int e = ptid; e < C::TR * CPR; e += 32 * NPW)
+        {
+          const int r = e / CPR, c = 2 * (e % CPR);
+          const bool in = r0 + r < a.n;
+          const long long row = in ? r0 + r : 0;
+          cp_async16(dst + r * C::LDT + c, a.X + (size_t)row * a.ldx + c, in);
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar0 + 8 * s) : "memory");
+        if (++s == kTs2Stages)
+        {
+          s = 0;
+          ++use;
+        }
+      }
+    }
+    else
+    {
+      const int g = lane >> 2, k = lane & 3;
+      int s = 0, use = 0;
+      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
+      {
+        mbar_wait(bar0 + 8 * s, (unsigned)(use & 1));
+        const double *Xs = tiles + (size_t)s * C::TR * C::LDT;
+#pragma unroll 2
+        for (int slab = swi; slab < C::TR / 4; slab += C::SW)
+        {
+          const double *xs = Xs + (slab * 4 + k) * C::LDT + g;
+          double f[C::NB];
+#pragma unroll
+          for (int jb = 0; jb < C::NB; ++jb)
+            f[jb] = xs[8 * jb];
+          int idx = 0;
+#pragma unroll
+          for (int bi = 0; bi < C::NB; ++bi)
+#pragma unroll
+            for (int bj = bi; bj < C::NB; ++bj)
+            {
+              if (idx % C::TG == tgi) // warp-uniform; idx is a compile-time constant after unrolling
+                dmma884_sp(gacc[idx / C::TG][0], gacc[idx / C::TG][1], f[bi], f[bj]);
+              ++idx;
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+          mbar_arrive(bar0 + 8 * (kTs2Stages + s));
+        if (++s == kTs2Stages)
+        {
+          s = 0;
+          ++use;
+        }
+      }
+    }
+
+    // fold the slab workers in fixed order, mirror, emit the CTA partial
+    __syncthreads();
+    double *G = tiles;
+    {
+      const int g = lane >> 2, k = lane & 3;
+      for (int turn = 0; turn < C::SW; ++turn)
+      {
+        if (warp >= NPW && swi == turn)
+        {
+          int idx = 0;
+#pragma unroll
+          for (int bi = 0; bi < C::NB; ++bi)
+#pragma unroll
+            for (int bj = bi; bj < C::NB; ++bj)
+            {
+              if (idx % C::TG == tgi)
+              {
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                {
+                  const int gi = 8 * bi + g, gj = 8 * bj + 2 * k + e;
+                  G[gi * M + gj] = gacc[idx / C::TG][e] + (turn == 0 ? 0.0 : G[gi * M + gj]);
+                }
+              }
+              ++idx;
+            }
+        }
+        __syncthreads();
+      }
+    }
+    double *outp = a.partials + (size_t)blockIdx.x * M * M;
+    for (int e = tid; e < M * M; e += kTg2Threads)
+    {
+      const int i = e / M, j = e % M;
+      outp[e] = ((i >> 3) <= (j >> 3)) ? G[e] : G[j * M + i];
+    }
+  }
+
+} // namespace de
