@@ -474,9 +474,9 @@ namespace
 
   // ---- host <-> device transfers of caller (pageable) memory -------------------------------------------------
   // A plain cudaMemcpy from pageable memory is staged by the driver through one pinned buffer on one thread
-  // (~10 GB/s); here kXferThreads workers convert / copy 8 MB chunks into their own pinned buffers and issue
+  // (~10 GB/s); here kXferThreads (8) workers convert / copy 8 MB chunks into their own pinned buffers and issue
   // asynchronous copies on their own streams, so the PCIe link and several host cores work at the same time.
-  constexpr int kXferThreads = 4;
+  constexpr int kXferThreads = 8;
   constexpr size_t kXferChunk = (size_t)8 << 20; // bytes per pinned buffer
 
   struct XferEngine
