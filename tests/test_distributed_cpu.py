@@ -58,6 +58,20 @@ def _worker(rank, world, port, shape, kind, ret):
             r.wait()
         for p, b in bufs.items():
             halo[offs[p]:offs[p + 1]] = b.numpy()
+        # --- the NVLink peer path deposits rows at offsets every sender computes itself (parallel.peer_deposit_offsets,
+        # csrc/kernels_peer.cuh halo_push_kernel): emulate the stores and compare with the halo block built above
+        peers = sorted(set(send_lists.keys()) | {p for p in range(world) if recv_counts[p] > 0})
+        deposits, max_halo = P.peer_deposit_offsets(recv_counts, peers, rank, dist)
+        msgs = [(rank, p, int(deposits[i]), np.ascontiguousarray(X[send_lists[p]])) for i, p in enumerate(peers)
+                if p in send_lists]
+        allmsgs = [None] * world
+        dist.all_gather_object(allmsgs, msgs)
+        halo_peer = np.full((len(halo_global), m), np.nan)
+        for lst in allmsgs:
+            for src, dst, off, rows in lst:
+                if dst == rank:
+                    halo_peer[off:off + len(rows)] = rows
+        peer_ok = bool(np.array_equal(halo_peer, halo)) and max_halo >= len(halo_global)
         import scipy.sparse as sp
 
         Aloc = sp.csr_matrix((v, col_local, rp), shape=(n_owned, n_owned + len(halo_global)))
@@ -68,26 +82,27 @@ def _worker(rank, world, port, shape, kind, ret):
         G = torch.from_numpy(X.T @ X)
         dist.all_reduce(G)
         gerr = np.abs(G.numpy() - Xglob.T @ Xglob).max()
-        ret[rank] = (float(err), float(gerr), int(len(halo_global)), [int(c) for c in recv_counts])
+        ret[rank] = (float(err), float(gerr), int(len(halo_global)), [int(c) for c in recv_counts], peer_ok)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shape,kind", [((6, 5, 8), "fd"), ((5, 4, 6), "q1")])
-def test_row_partition_halo_exchange_gloo(shape, kind):
+@pytest.mark.parametrize("shape,kind,world", [((6, 5, 8), "fd", 2), ((5, 4, 6), "q1", 2), ((4, 5, 7), "q1", 3)])
+def test_row_partition_halo_exchange_gloo(shape, kind, world):
     import torch.multiprocessing as mp
 
-    world = 2
     port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, shape, kind, ret), nprocs=world, join=True)
     plane = int(np.prod(shape[:-1]))
     for rank in range(world):
-        err, gerr, nhalo, recv = ret[rank]
+        err, gerr, nhalo, recv, peer_ok = ret[rank]
         assert err < 1e-12 and gerr < 1e-10
-        assert nhalo == plane                      # a z-slab needs exactly one neighbouring plane
-        assert recv[1 - rank] == plane and recv[rank] == 0
+        assert peer_ok                              # peer-store deposit offsets reproduce the halo block layout
+        neighbours = [p for p in (rank - 1, rank + 1) if 0 <= p < world]
+        assert nhalo == plane * len(neighbours)     # a z-slab needs one plane per neighbouring slab
+        assert all(recv[p] == plane for p in neighbours) and recv[rank] == 0
 
 
 def test_partition_rows():
