@@ -1384,7 +1384,19 @@ namespace
   template <int M, bool DO_UPDATE, bool DO_GRAM, bool UPPER, bool SAME>
   int launch_ts_t(de_context *ctx, de::TsArgs a, double *gram_out)
   {
-    if constexpr (DO_UPDATE && M <= 32 && (!DO_GRAM || (UPPER && SAME)))
+    if constexpr (DO_UPDATE && M == 64 && DO_GRAM && UPPER && SAME)
+    {
+      // no fused kernel at this width: block update, then the Gram matrix of the result (two passes, both on the
+      // warp-specialised kernels; the one-pass first-generation kernel at M = 64 is slower than the two together)
+      de::TsArgs u = a;
+      DE_TRY((launch_ts_t<M, true, false, false, true>(ctx, u, nullptr)));
+      de::TsArgs g = a;
+      g.X = a.Out;
+      g.ldx = a.ldo;
+      g.skip_flag = nullptr;
+      return launch_ts_t<M, false, true, true, true>(ctx, g, gram_out);
+    }
+    if constexpr (DO_UPDATE && (M <= 32 || !DO_GRAM) && (!DO_GRAM || (UPPER && SAME)))
     {
       // block update (+ Gram of the result): the register-to-register tensor-core kernel (kernels_tallskinny2.cuh)
       using C2 = de::Ts2Cfg<M>;

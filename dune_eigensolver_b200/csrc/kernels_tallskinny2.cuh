@@ -42,19 +42,24 @@ namespace de
     static constexpr int NB = M / 8;                           // 8-column blocks
     static constexpr int KS = M / 4;                           // k steps of the update
     static constexpr int LDT = M + 4;                          // staged row stride (doubles)
-    static constexpr int TR = 8 * kTs2ConsumerWarps * (M == 32 ? 2 : (M == 16 ? 4 : 8)); // rows per tile
+    static constexpr bool RSMEM = (M == 64);                    // factor fragments from shared memory instead of registers
+    static constexpr int TR = 8 * kTs2ConsumerWarps * (M == 64 ? 1 : (M == 32 ? 2 : (M == 16 ? 4 : 8))); // rows per tile
     static constexpr int NBLK = TR / 8;                        // 8-row blocks per tile
     static constexpr int NT = NB * (NB + 1) / 2;               // Gram tiles jb <= jb'
     static constexpr size_t STAGE_BYTES = (size_t)TR * LDT * sizeof(double);
-    static constexpr size_t SMEM = 128 + kTs2Stages * STAGE_BYTES;
+    static constexpr size_t RBYTES = RSMEM ? (size_t)M * LDT * sizeof(double) : 0; // staged factor, row stride LDT
+    static constexpr size_t SMEM = 128 + RBYTES + kTs2Stages * STAGE_BYTES;
   };
 
   /** a.X (n x M, ld a.ldx) -> a.Out (may alias X), a.R row-major M x M (a.upper: upper triangular);
-   *  DO_GRAM: per-CTA partial of Out^T Out at a.partials[cta * M * M + i * M + j] (full symmetric matrix). */
+   *  DO_GRAM: per-CTA partial of Out^T Out at a.partials[cta * M * M + i * M + j] (full symmetric matrix).
+   *  M = 64: the 128 factor fragments do not fit the register file next to the accumulators; the factor is staged in
+   *  shared memory (row stride M + 4: the fragment load of a half warp is conflict-free) and DO_GRAM is not offered. */
   template <int M, bool DO_GRAM>
   __global__ void __launch_bounds__(kTs2Threads, 1) ts2_update_kernel(const TsArgs a)
   {
     using C = Ts2Cfg<M>;
+    static_assert(!(C::RSMEM && DO_GRAM), "no fused Gram at M = 64");
     constexpr int NPW = kTs2ProducerWarps, NCW = kTs2ConsumerWarps;
     extern __shared__ __align__(128) unsigned char dyn2[];
     if (a.skip_flag != nullptr && *a.skip_flag != 0)
@@ -63,7 +68,8 @@ namespace de
       return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned bar0 = smem_u32(dyn2); // full[s] at +8 s, empty[s] at +8 (kTs2Stages + s)
-    double *tiles = reinterpret_cast<double *>(dyn2 + 128);
+    double *Rs = reinterpret_cast<double *>(dyn2 + 128);                  // RSMEM: M x LDT
+    double *tiles = reinterpret_cast<double *>(dyn2 + 128 + C::RBYTES);
     if (tid == 0)
     {
       for (int s = 0; s < kTs2Stages; ++s)
@@ -73,6 +79,9 @@ namespace de
       }
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    if (C::RSMEM)
+      for (int e = tid; e < M * M; e += kTs2Threads)
+        Rs[(e / M) * C::LDT + e % M] = __ldg(a.R + e);
     __syncthreads();
 
     const long long ntiles = (a.n + C::TR - 1) / C::TR;
@@ -115,12 +124,16 @@ namespace de
       const int cw = warp - NPW;
       const int g = lane >> 2, k = lane & 3;
       // R^T fragments: A(i = g, kk = k) of (ks, jb) = R(4 ks + k, 8 jb + g)
-      double rfrag[C::KS][C::NB];
+      double rfrag[C::RSMEM ? 1 : C::KS][C::RSMEM ? 1 : C::NB];
+      if (!C::RSMEM)
+      {
 #pragma unroll
-      for (int ks = 0; ks < C::KS; ++ks)
+        for (int ks = 0; ks < (C::RSMEM ? 1 : C::KS); ++ks)
 #pragma unroll
-        for (int jb = 0; jb < C::NB; ++jb)
-          rfrag[ks][jb] = (!a.upper || ks <= 2 * jb + 1) ? __ldg(a.R + (4 * ks + k) * M + 8 * jb + g) : 0.0;
+          for (int jb = 0; jb < (C::RSMEM ? 1 : C::NB); ++jb)
+            rfrag[ks][jb] = (!a.upper || ks <= 2 * jb + 1) ? __ldg(a.R + (4 * ks + k) * M + 8 * jb + g) : 0.0;
+      }
+      const double *rs = Rs + k * C::LDT + g; // RSMEM: fragment (ks, jb) = rs[4 ks LDT + 8 jb]
 
       int s = 0, use = 0;
       for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
@@ -143,7 +156,7 @@ namespace de
 #pragma unroll
             for (int jb = 0; jb < C::NB; ++jb)
               if (!a.upper || ks <= 2 * jb + 1) // triangular factor: column block jb only sees k < 8 jb + 8 (uniform)
-                dmma884_sp(c[jb][0], c[jb][1], rfrag[ks][jb], xv);
+                dmma884_sp(c[jb][0], c[jb][1], C::RSMEM ? rs[4 * ks * C::LDT + 8 * jb] : rfrag[C::RSMEM ? 0 : ks][C::RSMEM ? 0 : jb], xv);
           }
           // c[jb] = Out(rows 8 rb + 2k, + 2k + 1; column 8 jb + g)
           const long long row0 = r0 + rb * 8 + 2 * k;
