@@ -123,8 +123,8 @@ struct de_context
   int *dticket = nullptr; // [0] ticket of halo_push_kernel, [1] peer error flag
   // fused tail of the NEXT partial-sum reduction (kernels_tail.cuh): set by the caller, consumed by reduce_partials
   de::TailArgs tail{};
-  bool tail_armed = false;
-  bool tail_did_allreduce = false, tail_did_op = false; // one-shot: the following allreduce_sum / chol / convergence is skipped
+  mutable bool tail_armed = false; // cleared by any error return (set_error), so a failed call cannot leave it behind
+  mutable bool tail_did_allreduce = false, tail_did_op = false; // one-shot: the following allreduce_sum / chol / convergence is skipped
   int *dtail_ticket = nullptr;
   size_t dconv_cap = 0;
   double *hsmall = nullptr;   // pinned mirror of dsmall
@@ -277,7 +277,10 @@ namespace
   {
     g_thread_error = msg;
     if (ctx)
+    {
       ctx->err = msg;
+      ctx->tail_armed = ctx->tail_did_allreduce = ctx->tail_did_op = false;
+    }
     return code;
   }
 

@@ -248,133 +248,11 @@ namespace de
   // ------------------------------------------------------------------------------------------------
   // m x m Cholesky + inverse of the triangular factor (one CTA; replicated on every GPU of a multi-GPU run)
   // ------------------------------------------------------------------------------------------------
-  /** G = R^T R (R upper, positive diagonal), Rinv = R^-1 (upper). Only the upper triangle of G is read.
-   *  This is the L D L^T / U = L^-T D^-1/2 construction of kernels_cpp.hh:247-291, :468-512 for the whole block.
-   *  status[0] (sticky) = 1 + index of the first pivot that is non-finite or not above 4 m eps G(k,k); untouched on success.
-   *  info[0] (optional) = largest strict-upper entry of G (the `norm` diagnostic of kernels_cpp.hh:464-466).
-   *  identity_flag[0] (optional) = 1 if max |G - I| <= 1e-14: lets the second CholQR sweep's update skip itself. */
-  __global__ void __launch_bounds__(256) chol_inverse_kernel(int m, const double *__restrict__ G,
-                                                             double *__restrict__ Rinv, int *__restrict__ status,
-                                                             double *__restrict__ info,
-                                                             int *__restrict__ identity_flag,
-                                                             int *__restrict__ done = nullptr)
-  {
-    // `done`: a converged driver loop turns the launch into a no-op; a failed factorisation raises it so that the
-    // iterations already enqueued do not run on garbage
-    if (done != nullptr && *done != 0)
-      return;
-    // upper triangle + diagonal: R ; strict lower triangle: (R^-1)^T ; dinv: diagonal of R^-1
-    __shared__ double A[DE_KERNEL_MAX_M][DE_KERNEL_MAX_M + 1];
-    __shared__ double dinv[DE_KERNEL_MAX_M];
-    __shared__ double dorig[DE_KERNEL_MAX_M]; // diagonal of G: a pivot below ~m*eps of it means rank deficiency
-    __shared__ int bad;
-    __shared__ double red[256];
-    const int tid = threadIdx.x;
-    if (tid == 0)
-      bad = 0;
-    double mx = -1.0e300, dev = 0.0; // dev: max |G - I| over the upper triangle
-    for (int e = tid; e < m * m; e += blockDim.x)
-    {
-      const int i = e / m, j = e % m;
-      const double v = (i <= j) ? G[i * m + j] : 0.0;
-      A[i][j] = v;
-      if (i == j)
-        dorig[i] = v;
-      if (i < j)
-        mx = fmax(mx, v);
-      if (i <= j)
-        dev = fmax(dev, fabs(v - (i == j ? 1.0 : 0.0)));
-    }
-    if (identity_flag != nullptr)
-    {
-      // G equals I to working precision: the factor is I and the following update would change nothing
-      red[tid] = dev;
-      __syncthreads();
-      if (tid == 0)
-      {
-        double t = 0.0;
-        for (int q = 0; q < (int)blockDim.x; ++q)
-          t = fmax(t, red[q]);
-        identity_flag[0] = (t <= 1.0e-14) ? 1 : 0; // also false for NaN
-      }
-      __syncthreads();
-    }
-    red[tid] = mx;
-    __syncthreads();
-    if (info != nullptr && tid == 0)
-    {
-      double t = -1.0e300;
-      for (int q = 0; q < (int)blockDim.x; ++q)
-        t = fmax(t, red[q]);
-      info[0] = (m > 1) ? t : 0.0;
-    }
-
-    // right-looking Cholesky on the upper triangle; every thread sees the same pivot, so control flow is uniform
-    for (int k = 0; k < m; ++k)
-    {
-      const double d = A[k][k];
-      if (!(d > 4.0 * m * 2.220446049250313e-16 * dorig[k]) || !isfinite(d))
-      {
-        if (tid == 0)
-          bad = k + 1;
-        break;
-      }
-      const double rkk = sqrt(d);
-      __syncthreads(); // everybody has read A[k][k]
-      for (int j = k + tid; j < m; j += blockDim.x)
-        A[k][j] = (j == k) ? rkk : A[k][j] / rkk;
-      __syncthreads();
-      const int w = m - k - 1;
-      for (int e = tid; e < w * w; e += blockDim.x)
-      {
-        const int i = k + 1 + e / w, j = k + 1 + e % w;
-        if (i <= j)
-          A[i][j] = fma(-A[k][i], A[k][j], A[i][j]);
-      }
-      __syncthreads();
-    }
-    __syncthreads();
-    if (bad != 0)
-    {
-      if (tid == 0)
-      {
-        status[0] = bad; // sticky: success never clears an earlier failure; the host resets it per driver call
-        if (done != nullptr)
-          *done = 1;
-      }
-      // leave Rinv = identity so that downstream kernels stay finite; the host reports the failure
-      for (int e = tid; e < m * m; e += blockDim.x)
-        Rinv[e] = (e / m == e % m) ? 1.0 : 0.0;
-      return;
-    }
-    // back substitution, one column of R^-1 per thread: R * Ri(:,j) = e_j ; Ri(i,j) is kept at A[j][i], i < j
-    for (int j = tid; j < m; j += blockDim.x)
-    {
-      const double dj = 1.0 / A[j][j];
-      dinv[j] = dj;
-      for (int i = j - 1; i >= 0; --i)
-      {
-        double s = A[i][j] * dj;
-        for (int k = i + 1; k < j; ++k)
-          s = fma(A[i][k], A[j][k], s);
-        A[j][i] = -s / A[i][i];
-      }
-    }
-    __syncthreads();
-    for (int e = tid; e < m * m; e += blockDim.x)
-    {
-      const int i = e / m, j = e % m;
-      Rinv[e] = (i < j) ? A[j][i] : (i == j ? dinv[i] : 0.0);
-    }
-  }
-
-
-  /** Second-generation Cholesky + triangular inverse of the (all-reduced) Gram matrix, same contract as
-   *  chol_inverse_kernel: Rinv = R^-1 with G = R^T R, R upper triangular with positive diagonal; a pivot
+  /** Cholesky + triangular inverse of the (all-reduced) Gram matrix: Rinv = R^-1 with G = R^T R, R upper triangular with positive diagonal; a pivot
    *  <= 4 m eps G_kk reports rank deficiency (status = k + 1, Rinv = I, `done` raised).
-   *  ncu (profiles/r01_ncu_launches_brb.csv) had the first version at 30 us per call, 13 % of a StandardLargest
-   *  iteration: integer divisions in the trailing update, three CTA barriers per pivot and a 32-thread back
-   *  substitution. Here the matrix is padded with the identity to MP x MP (MP = 32 or 64), every thread keeps its
+   *  ncu (profiles/r01_ncu_launches_brb.csv) had the first version (a shared-memory right-looking factorisation, kept in
+   *  the history) at 30 us per call, 13 % of a StandardLargest iteration: integer divisions in the trailing update, three
+   *  CTA barriers per pivot and a 32-thread back substitution. Here the matrix is padded with the identity to MP x MP (MP = 32 or 64), every thread keeps its
    *  (MP/32)^2 elements in registers, row k lives in ONE warp (its pivot is a warp shuffle away), and both phases are
    *  rank-1 updates with ONE barrier per pivot:
    *    factorisation   scaled row k -> shared; barrier; a_ij -= r_ki r_kj          (i > k)
