@@ -248,7 +248,13 @@ namespace de
   // ------------------------------------------------------------------------------------------------
   // m x m Cholesky + inverse of the triangular factor (one CTA; replicated on every GPU of a multi-GPU run)
   // ------------------------------------------------------------------------------------------------
-  /** Cholesky + triangular inverse of the (all-reduced) Gram matrix: Rinv = R^-1 with G = R^T R, R upper triangular with positive diagonal; a pivot
+  /** G = R^T R (R upper, positive diagonal), Rinv = R^-1 (upper); only the upper triangle of G is read. This is the
+   *  L D L^T / U = L^-T D^-1/2 construction of the reference (kernels_cpp.hh:247-291, :468-512) for the whole block.
+   *  status[0] (sticky) = 1 + index of the first pivot that is non-finite or not above 4 m eps G(k,k); untouched on success.
+   *  info[0] (optional) = largest strict-upper entry of G (the `norm` the reference's B-orthonormalisation returns,
+   *  kernels_cpp.hh:464-466); identity_flag[0] (optional) = 1 iff max |G - I| <= 1e-14 over the upper triangle, in which
+   *  case nothing is factored (Rinv = I).
+   *  Cholesky + triangular inverse of the (all-reduced) Gram matrix: Rinv = R^-1 with G = R^T R, R upper triangular with positive diagonal; a pivot
    *  <= 4 m eps G_kk reports rank deficiency (status = k + 1, Rinv = I, `done` raised).
    *  ncu (profiles/r01_ncu_launches_brb.csv) had the first version (a shared-memory right-looking factorisation, kept in
    *  the history) at 30 us per call, 13 % of a StandardLargest iteration: integer divisions in the trailing update, three
