@@ -1416,7 +1416,7 @@ namespace
       a.done = ctx->done_ptr;
       {
         ProfScope prof(ctx, DE_PROF_UPDATE);
-        de::ts2_update_kernel<M, DO_GRAM><<<grid2, de::kTs2Threads, C2::SMEM, ctx->stream>>>(a);
+        de::ts2_update_kernel<M, DO_GRAM><<<grid2, C2::THREADS, C2::SMEM, ctx->stream>>>(a);
       }
       DE_LAUNCH_CHECK(ctx);
       if (DO_GRAM)

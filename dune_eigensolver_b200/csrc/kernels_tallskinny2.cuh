@@ -8,7 +8,8 @@
 // five CTA-wide barriers and a shared-memory round trip of the whole tile, with 8 warps per SM.
 //
 // Here the product is formed TRANSPOSED on the FP64 tensor pipe,  Out^T(8 cols x 8 rows) += R^T(8 x 4) X^T(4 x 8):
-//   A operand = R^T fragment (registers for the whole kernel; a triangular factor needs 20 of 32 for M = 32),
+//   A operand = R^T fragment (registers for the whole kernel; a triangular factor needs 20 of 32 for M = 32. Reading them
+//               from shared memory instead frees 40 registers and allows 12 consumer warps, but measured no faster),
 //   B operand = X(8 rows x 4 cols) fragment straight from the staged tile (stride M + 4 doubles: conflict-free),
 //   C         = lane (g, k) holds Out(rows 2k, 2k+1; column 8 jb + g).
 // C goes to global memory from registers (a warp store covers 4 rows x 64 contiguous bytes), and -- because rows 2kk,
@@ -32,8 +33,6 @@ namespace de
 {
 
   constexpr int kTs2ProducerWarps = 2;
-  constexpr int kTs2ConsumerWarps = 10;
-  constexpr int kTs2Threads = 32 * (kTs2ProducerWarps + kTs2ConsumerWarps);
   constexpr int kTs2Stages = 3;
 
   template <int M>
@@ -43,7 +42,9 @@ namespace de
     static constexpr int KS = M / 4;                           // k steps of the update
     static constexpr int LDT = M + 4;                          // staged row stride (doubles)
     static constexpr bool RSMEM = (M == 64);                    // factor fragments from shared memory instead of registers
-    static constexpr int TR = 8 * kTs2ConsumerWarps * (M == 64 ? 1 : (M == 32 ? 2 : (M == 16 ? 4 : 8))); // rows per tile
+    static constexpr int NCW = (M >= 32) ? 10 : 12;             // consumer warps (M >= 32: up to 167 registers per thread)
+    static constexpr int THREADS = 32 * (kTs2ProducerWarps + NCW);
+    static constexpr int TR = 8 * NCW * (M == 64 ? 1 : (M == 32 ? 2 : (M == 16 ? 4 : 8))); // rows per tile
     static constexpr int NBLK = TR / 8;                        // 8-row blocks per tile
     static constexpr int NT = NB * (NB + 1) / 2;               // Gram tiles jb <= jb'
     static constexpr size_t STAGE_BYTES = (size_t)TR * LDT * sizeof(double);
@@ -56,11 +57,11 @@ namespace de
    *  M = 64: the 128 factor fragments do not fit the register file next to the accumulators; the factor is staged in
    *  shared memory (row stride M + 4: the fragment load of a half warp is conflict-free) and DO_GRAM is not offered. */
   template <int M, bool DO_GRAM>
-  __global__ void __launch_bounds__(kTs2Threads, 1) ts2_update_kernel(const TsArgs a)
+  __global__ void __launch_bounds__(Ts2Cfg<M>::THREADS, 1) ts2_update_kernel(const TsArgs a)
   {
     using C = Ts2Cfg<M>;
-    static_assert(!(C::RSMEM && DO_GRAM), "no fused Gram at M = 64");
-    constexpr int NPW = kTs2ProducerWarps, NCW = kTs2ConsumerWarps;
+    static_assert(!(M == 64 && DO_GRAM), "no fused Gram at M = 64");
+    constexpr int NPW = kTs2ProducerWarps, NCW = C::NCW;
     extern __shared__ __align__(128) unsigned char dyn2[];
     if (a.skip_flag != nullptr && *a.skip_flag != 0)
       return;
@@ -80,7 +81,7 @@ namespace de
       asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (C::RSMEM)
-      for (int e = tid; e < M * M; e += kTs2Threads)
+      for (int e = tid; e < M * M; e += C::THREADS)
         Rs[(e / M) * C::LDT + e % M] = __ldg(a.R + e);
     __syncthreads();
 
@@ -234,7 +235,7 @@ namespace de
         __syncthreads();
       }
       double *outp = a.partials + (size_t)blockIdx.x * M * M;
-      for (int e = tid; e < M * M; e += kTs2Threads)
+      for (int e = tid; e < M * M; e += C::THREADS)
       {
         const int i = e / M, j = e % M;
         outp[e] = ((i >> 3) <= (j >> 3)) ? G[e] : G[j * M + i];
