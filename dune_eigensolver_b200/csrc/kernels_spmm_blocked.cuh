@@ -152,9 +152,9 @@ namespace de
   }
 
 
-  constexpr int kBrbProducerWarps = 2;
+  constexpr int kBrbProducerWarps = 4;      // measured: 2 producer warps starve the pipeline (0.210 ms), 4: 0.181 ms, 8: 0.183 ms
   constexpr int kBrbConsumerWarps = 12;     // plain / DOT variants
-  constexpr int kBrbConsumerWarpsGram = 10; // GRAM variants carry 40 more accumulator registers per thread
+  constexpr int kBrbConsumerWarpsGram = 8;  // GRAM variants carry 40 more accumulator registers per thread (168 in all)
   constexpr int brb_threads(bool gram) { return 32 * (kBrbProducerWarps + (gram ? kBrbConsumerWarpsGram : kBrbConsumerWarps)); }
   constexpr int kBrbMaxStages = 4;
   constexpr int kBrbBarrierBytes = 128; // mbarriers in front of the stage buffers
@@ -324,6 +324,18 @@ namespace de
         for (int blk = cw; blk < nb; blk += NCW)
         {
           const int s0 = blkstep[blk], s1 = blkstep[blk + 1];
+          if (DOT && !GRAM)
+          {
+            // the X row of the dot epilogue: start it towards L1 now, it is needed after the step loop
+            const long long prow = (long long)blkrows[8 * blk + g];
+            if (prow >= 0 && prow < a.n)
+            {
+              const double *xr = a.X + (size_t)prow * a.ldx + 2 * k * NP;
+              asm volatile("prefetch.global.L1 [%0];\n" ::"l"(xr));
+              if (NP >= 2)
+                asm volatile("prefetch.global.L1 [%0];\n" ::"l"(xr + NP));
+            }
+          }
           double c[NP][2];
 #pragma unroll
           for (int p = 0; p < NP; ++p)
