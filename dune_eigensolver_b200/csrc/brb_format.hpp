@@ -8,6 +8,8 @@
 //                   [0..3]  nb (row blocks), ns (steps), nv (values), nu (union rows)
 //                   blkstep[nb+1]            first step of each row block (tile-relative)
 //                   blkrows[8 nb]            output row of each block row (-1: empty slot)
+//                   blkself[8 nb] (uint16)   tile-local id of the column equal to that row (its own X row is then in the staged
+//                                            tile: the dot-product epilogue reads it from shared memory), 0xffff if absent
 //                   pad to 4 words
 //                   step[ns] x 4 words       lc0 | lc1 << 16, lc2 | lc3 << 16, pattern mask, first value (tile-relative)
 //                   val[nv] doubles          packed values: step-major, ascending pattern bit (bit = 4 * block row + step column)
@@ -116,9 +118,16 @@ namespace de
         while (blob.size() % 4)
           blob.push_back(0);
         const size_t w0 = blob.size();
-        blob.resize(w0 + 4 + (nb + 1) + 8 * nb, 0);
+        blob.resize(w0 + 4 + (nb + 1) + 8 * nb + 4 * nb, 0);
         for (int q = 0; q < 8 * nb; ++q)
           blob[w0 + 4 + (nb + 1) + q] = rows[q];
+        for (int q = 0; q < 8 * nb; ++q)
+        {
+          const int r = rows[q];
+          const unsigned self = (r >= 0 && (size_t)r < stamp.size() && stamp[r] == tag) ? (unsigned)lid[r] : 0xffffu;
+          int &w = blob[w0 + 4 + (nb + 1) + 8 * nb + q / 2];
+          w = (int)((unsigned)w | (self << (16 * (q & 1))));
+        }
         while (blob.size() % 4)
           blob.push_back(0);
 

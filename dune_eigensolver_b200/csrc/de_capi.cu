@@ -1044,7 +1044,7 @@ namespace
           ok = false;
           break;
         }
-        const size_t words = (((size_t)4 + (nb + 1) + 8 * (size_t)nb + 3) & ~(size_t)3) + 4 * (size_t)f.x + (((size_t)2 * f.y + 3) & ~(size_t)3);
+        const size_t words = (((size_t)4 + (nb + 1) + 12 * (size_t)nb + 3) & ~(size_t)3) + 4 * (size_t)f.x + (((size_t)2 * f.y + 3) & ~(size_t)3);
         const int len16 = (int)(words / 4);
         place[t] = make_int4((int)blob16, len16, (int)ucols, f.z);
         blob16 += (size_t)len16;
@@ -2467,7 +2467,8 @@ extern "C"
       const int *h = &F.blob[(size_t)d.blob16 * 4];
       const int nb = h[0], ns = h[1];
       const int *blkstep = h + 4, *blkrows = blkstep + nb + 1;
-      const int o_step = (4 + (nb + 1) + 8 * nb + 3) & ~3;
+      const int o_step = (4 + (nb + 1) + 8 * nb + 4 * nb + 3) & ~3;
+      const unsigned short *self = reinterpret_cast<const unsigned short *>(blkrows + 8 * nb);
       const int *st = h + o_step;
       const double *v = reinterpret_cast<const double *>(h + o_step + 4 * ns);
       if (d.nu != h[3] || (size_t)d.len16 * 4 < (size_t)o_step + 4 * (size_t)ns + 2 * (size_t)h[2])
@@ -2476,7 +2477,13 @@ extern "C"
       {
         for (int g = 0; g < 8; ++g)
           if (blkrows[8 * b + g] >= 0)
+          {
             seen[blkrows[8 * b + g]]++;
+            // the recorded position of the row's own column must hold exactly that column
+            const unsigned sl = self[8 * b + g];
+            if (sl != 0xffffu && ((int)sl >= d.nu || F.ucol[(size_t)d.ucol0 + sl] != blkrows[8 * b + g]))
+              return set_error(nullptr, DE_ERR_INVALID, "de_brb_format_check: wrong self column id");
+          }
         for (int q = blkstep[b]; q < blkstep[b + 1]; ++q)
         {
           const unsigned lc[4] = {(unsigned)st[4 * q] & 0xffffu, (unsigned)st[4 * q] >> 16, (unsigned)st[4 * q + 1] & 0xffffu,

@@ -243,7 +243,7 @@ namespace de
     const int4 pl = a.place[t];
     int *hdr = a.blob + 4 * (size_t)pl.x;
     const int ns = S.blk_ns[nb], nv = S.blk_nv[nb];
-    const int o_step = (4 + (nb + 1) + 8 * nb + 3) & ~3;
+    const int o_step = (4 + (nb + 1) + 8 * nb + 4 * nb + 3) & ~3;
     int *steps = hdr + o_step;
     double *vals = reinterpret_cast<double *>(hdr + o_step + 4 * ns);
     if (tid == 0)
@@ -257,6 +257,24 @@ namespace de
       hdr[4 + b] = S.blk_ns[b];
     for (int q = tid; q < 8 * nb; q += kBldThreads)
       hdr[4 + (nb + 1) + q] = trows[q];
+    for (int q2 = tid; q2 < 4 * nb; q2 += kBldThreads)
+    {
+      // tile-local id of each row's own column (0xffff: not among the tile's columns), two per word
+      unsigned w = 0;
+      for (int h = 0; h < 2; ++h)
+      {
+        const int r = trows[2 * q2 + h];
+        unsigned self = 0xffffu;
+        if (r >= 0 && nu > 0)
+        {
+          const int l = brb_lid(S.ulist, nu, r);
+          if (S.ulist[l] == r)
+            self = (unsigned)l;
+        }
+        w |= self << (16 * h);
+      }
+      hdr[4 + (nb + 1) + 8 * nb + q2] = (int)w;
+    }
     for (int i = tid; i < nu; i += kBldThreads)
       a.ucol[pl.z + i] = S.ulist[i];
 

@@ -316,7 +316,8 @@ namespace de
         const int nb = hdr[0];
         const int *blkstep = hdr + 4;
         const int *blkrows = blkstep + nb + 1;
-        const int o_step = (4 + (nb + 1) + 8 * nb + 3) & ~3;
+        const unsigned short *blkself = reinterpret_cast<const unsigned short *>(blkrows + 8 * nb);
+        const int o_step = (4 + (nb + 1) + 8 * nb + 4 * nb + 3) & ~3;
         const int4 *steps = reinterpret_cast<const int4 *>(hdr + o_step);
         const double *sval = reinterpret_cast<const double *>(hdr + o_step + 4 * hdr[1]);
         const double *xs = reinterpret_cast<const double *>(base + (size_t)a.blob_cap16 * 16);
@@ -324,18 +325,6 @@ namespace de
         for (int blk = cw; blk < nb; blk += NCW)
         {
           const int s0 = blkstep[blk], s1 = blkstep[blk + 1];
-          if (DOT && !GRAM)
-          {
-            // the X row of the dot epilogue: start it towards L1 now, it is needed after the step loop
-            const long long prow = (long long)blkrows[8 * blk + g];
-            if (prow >= 0 && prow < a.n)
-            {
-              const double *xr = a.X + (size_t)prow * a.ldx + 2 * k * NP;
-              asm volatile("prefetch.global.L1 [%0];\n" ::"l"(xr));
-              if (NP >= 2)
-                asm volatile("prefetch.global.L1 [%0];\n" ::"l"(xr + NP));
-            }
-          }
           double c[NP][2];
 #pragma unroll
           for (int p = 0; p < NP; ++p)
@@ -377,10 +366,26 @@ namespace de
               stg_row<NP>(yr + NP, hi);
               if (DOT)
               {
+                // X(row, :) -- from the staged tile when the row's own column is among the tile's columns (any matrix with
+                // a stored diagonal), else from global memory
                 double zl[NP], zh[NP];
-                const double *xr = a.X + (size_t)row * a.ldx + 2 * k * NP;
-                ldg_row_if<NP>(zl, xr, true);
-                ldg_row_if<NP>(zh, xr + NP, true);
+                const unsigned self = blkself[8 * blk + g];
+                if (self != 0xffffu)
+                {
+                  const double *zr = xs + self * LDR + 2 * k * NP;
+#pragma unroll
+                  for (int p = 0; p < NP; ++p)
+                  {
+                    zl[p] = zr[p];
+                    zh[p] = zr[NP + p];
+                  }
+                }
+                else
+                {
+                  const double *xr = a.X + (size_t)row * a.ldx + 2 * k * NP;
+                  ldg_row_if<NP>(zl, xr, true);
+                  ldg_row_if<NP>(zh, xr + NP, true);
+                }
 #pragma unroll
                 for (int p = 0; p < NP; ++p)
                 {
