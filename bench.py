@@ -41,10 +41,10 @@ sys.path.insert(0, ROOT)
 ITERATIONS_TO_CONVERGENCE = {(100, "q1", 32, 2e-3): 41}
 
 # DRAM traffic of ONE launch of the dominant kernel, from the committed ncu --set full capture of this very command
-# (profiles/r01_ncu_kernels_brb.csv: dram__bytes_read.sum + dram__bytes_write.sum of spmm_brb_kernel<4,1,0,0>):
-# 515.4 MB + 231.1 MB. It is BELOW the algorithmic bytes (833.6 MB, counted for CSR: 12 B per nonzero) because the
+# (profiles/r01_ncu_kernels_final.csv: dram__bytes_read.sum + dram__bytes_write.sum of spmm_brb_kernel<4,1,0,0>):
+# 517.4 MB + 230.7 MB. It is BELOW the algorithmic bytes (833.6 MB, counted for CSR: 12 B per nonzero) because the
 # BRB stream is 9.4 B per nonzero; no byte is read twice.
-NCU_DRAM_TRAFFIC_PER_LAUNCH = {(100, "q1", 32): 746.5e6}
+NCU_DRAM_TRAFFIC_PER_LAUNCH = {(100, "q1", 32): 748.1e6}
 
 
 def parse():
@@ -407,7 +407,7 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": "spmm_brb_kernel (SpMM + fused Rayleigh-quotient dots)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_TRAFFIC_PER_LAUNCH.get((args.grid, args.stencil, m)) if world == 1 else None,
-                "traffic_source": "profiles/r01_ncu_kernels_brb.csv (ncu --set full of this command, one launch)",
+                "traffic_source": "profiles/r01_ncu_kernels_final.csv (ncu --set full of this command, one launch)",
                 "peak_source": peak_src, "avg_launch_ms": spmm_ms / max(spmm_cnt, 1),
                 "algorithmic_bytes_per_launch": spmm_bytes, "kernel_time_shares": shares,
                 "kernel_time_shares_source": "one extra solve after the timed region with all categories timed "
