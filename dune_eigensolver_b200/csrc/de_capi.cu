@@ -1715,8 +1715,10 @@ namespace
     DE_TRY(spmm_device<false>(ctx, B, X, BX, m));
     for (int sweep = 0; sweep < 2; ++sweep)
     {
+      double *info = (want_info && sweep == 0) ? ctx->dInfo() : nullptr;
+      arm_chol_tail(ctx, m, ctx->dR(), info, nullptr); // reduce -> all-reduce -> Cholesky in one launch (kernels_tail.cuh)
       DE_TRY(gram_device(ctx, m, n, X, m, BX, m, true, ctx->dG()));
-      DE_TRY(chol_inverse(ctx, m, ctx->dG(), ctx->dR(), (want_info && sweep == 0) ? ctx->dInfo() : nullptr));
+      DE_TRY(chol_inverse(ctx, m, ctx->dG(), ctx->dR(), info));
       DE_TRY(update_device<0>(ctx, m, n, X, m, ctx->dR(), X, m, 1));
       DE_TRY(update_device<0>(ctx, m, n, BX, m, ctx->dR(), BX, m, 1));
     }
