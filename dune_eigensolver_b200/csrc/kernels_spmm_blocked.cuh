@@ -183,7 +183,11 @@ namespace de
   /** bytes of dynamic shared memory for a pass of 8 NP columns */
   inline size_t spmm_brb_smem_bytes(int np, int blob_cap16, int xs_cap, int stages)
   {
-    return (size_t)kBrbBarrierBytes + (size_t)stages * ((size_t)blob_cap16 * 16 + (size_t)xs_cap * (8 * np + 4) * sizeof(double));
+    const size_t ring = (size_t)stages * ((size_t)blob_cap16 * 16 + (size_t)xs_cap * (8 * np + 4) * sizeof(double));
+    // the stage buffers double as scratch of the final reductions (consumer warps x M dot partials, M x M Gram): tiny
+    // matrices have tiles smaller than that
+    const size_t scratch = ((size_t)kBrbConsumerWarps * 8 * np + (size_t)64 * np * np) * sizeof(double);
+    return (size_t)kBrbBarrierBytes + (ring > scratch ? ring : scratch);
   }
 
   /** Y(:, 0 : 8 NP) = A X(:, 0 : 8 NP) for the tiles of one launch (+ per-CTA partials of diag(X^T Y) when DOT).

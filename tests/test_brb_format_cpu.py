@@ -142,3 +142,34 @@ def test_local_block_of_a_distributed_matrix_separates_boundary_tiles():
 def test_empty_matrix():
     d = check((np.array([0]), np.array([], dtype=np.int64), np.array([])))
     assert d["ok"] == 0
+
+
+@pytest.mark.parametrize("n", [1, 5, 8, 9, 63, 65])
+def test_tiny_matrices(n):
+    """fewer rows than one row block / than the grid detector looks at: consecutive-row tiles, partly empty blocks"""
+    rp, ci, v = [0], [], []
+    for i in range(n):
+        for j in (i - 1, i, i + 1):
+            if 0 <= j < n:
+                ci.append(j)
+                v.append(2.0 if j == i else -1.0)
+        rp.append(len(ci))
+    d = check((np.array(rp), np.array(ci), np.array(v)))
+    assert d["ok"] == 1 and d["diff"] <= 1e-14 * d["scale"], d
+    assert d["blocks"] == (n + 7) // 8
+
+
+def test_matrix_without_diagonal_entries():
+    """rows whose own column is absent: the dot epilogue's self-column id is 0xffff (checked by de_brb_format_check)"""
+    n = 200
+    rp, ci, v = [0], [], []
+    for i in range(n):
+        for j in ((i + 1) % n, (i + 7) % n):
+            ci.append(j)
+            v.append(1.0 + 0.1 * j)
+        order = np.argsort(ci[-2:])
+        ci[-2:] = [ci[-2:][k] for k in order]
+        v[-2:] = [v[-2:][k] for k in order]
+        rp.append(len(ci))
+    d = check((np.array(rp), np.array(ci), np.array(v)))
+    assert d["ok"] == 1 and d["diff"] <= 1e-13 * d["scale"], d

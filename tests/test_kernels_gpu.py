@@ -65,6 +65,35 @@ BRB_MATS = {
 }
 
 
+def _tridiag(n, diagonal=True):
+    rp, ci, v = [0], [], []
+    for i in range(n):
+        for j in (i - 1, i, i + 1):
+            if 0 <= j < n and (diagonal or j != i):
+                ci.append(j)
+                v.append(2.0 if j == i else -1.0 - 0.01 * j)
+        rp.append(len(ci))
+    return np.array(rp), np.array(ci), np.array(v)
+
+
+@pytest.mark.parametrize("n", [1, 5, 9, 70])
+@pytest.mark.parametrize("diagonal", [True, False])
+def test_spmm_tiny_and_diagonal_free_matrices(ctx, oracle, n, diagonal):
+    """partly empty row blocks; rows without their own column (the dot epilogue then reads X from global memory)"""
+    A = _tridiag(n, diagonal)
+    if len(A[1]) == 0:
+        pytest.skip("empty matrix")
+    m = 16
+    X = rnd(n, m, n)
+    dA, dX, dY = E.Matrix(ctx, A), E.MultiVector.from_array(ctx, X), E.MultiVector(ctx, n, m)
+    ref = oracle.spmm(A, X)
+    for fmt in (["brb"] if dA.spmm_info()["tiles"] > 0 else []) + ["csr"]:
+        dA.set_spmm_format(fmt)
+        dp = E.matmul_sparse_tallskinny_with_dots(dY, dA, dX)
+        assert np.abs(dY.download() - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max()), fmt
+        assert np.abs(dp - oracle.diag_dot(X, ref)).max() <= 1e-12 * max(1.0, (np.abs(X) * np.abs(ref)).sum(0).max()), fmt
+
+
 def _random_csr(n, per_row, seed):
     rng = np.random.default_rng(seed)
     rp, ci, v = [0], [], []
