@@ -264,6 +264,10 @@ struct de_factor
   double *rowscale = nullptr;
   double *W = nullptr;
   int W_m = 0;
+  // the two triangular sweeps (hundreds of dependent launches on the fixed work block W) captured once per width
+  cudaGraphExec_t sweep_graph = nullptr;
+  int sweep_graph_m = 0;
+  long long sweep_graph_nodes = 0;
 };
 
 struct de_host_factor
@@ -1868,6 +1872,12 @@ namespace
     if (F->W)
       dev_free(F->W);
     F->W = nullptr;
+    if (F->sweep_graph) // captured on the old work block
+    {
+      cudaGraphExecDestroy(F->sweep_graph);
+      F->sweep_graph = nullptr;
+      F->sweep_graph_m = 0;
+    }
     DE_TRY(dev_alloc(ctx, &F->W, (size_t)F->n * m));
     F->W_m = m;
     return DE_OK;
@@ -1887,8 +1897,49 @@ namespace
       de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->P, F->rowscale, X, F->W, 0);
     }
     DE_LAUNCH_CHECK(ctx);
-    DE_TRY(run_schedule(ctx, F->L, F->W, m));
-    DE_TRY(run_schedule(ctx, F->U, F->W, m));
+    // forward sweep over the levels of L, backward sweep over the levels of U: a fixed sequence of launches on the
+    // fixed block W -> a CUDA graph, replayed with one call (per-launch CPU cost and front-end latency dominate these
+    // sweeps for 2D problems: hundreds of levels of a few hundred rows). With per-kernel timers on, launch one by one.
+    bool replayed = false;
+    if (!ctx->profiling)
+    {
+      if (F->sweep_graph == nullptr || F->sweep_graph_m != m)
+      {
+        if (F->sweep_graph)
+          cudaGraphExecDestroy(F->sweep_graph);
+        F->sweep_graph = nullptr;
+        F->sweep_graph_m = 0;
+        cudaGraph_t graph = nullptr;
+        const long long before = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess)
+        {
+          const int s1 = run_schedule(ctx, F->L, F->W, m);
+          const int s2 = (s1 == DE_OK) ? run_schedule(ctx, F->U, F->W, m) : s1;
+          const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+          F->sweep_graph_nodes = ctx->launches - before;
+          ctx->launches = before; // counted again at every replay
+          if (s2 == DE_OK && ce == cudaSuccess && graph != nullptr &&
+              cudaGraphInstantiate(&F->sweep_graph, graph, 0) == cudaSuccess)
+            F->sweep_graph_m = m;
+          else
+            F->sweep_graph = nullptr;
+          if (graph)
+            cudaGraphDestroy(graph);
+          cudaGetLastError();
+        }
+      }
+      if (F->sweep_graph != nullptr && F->sweep_graph_m == m)
+      {
+        DE_CUDA(ctx, cudaGraphLaunch(F->sweep_graph, ctx->stream));
+        ctx->launches += F->sweep_graph_nodes;
+        replayed = true;
+      }
+    }
+    if (!replayed)
+    {
+      DE_TRY(run_schedule(ctx, F->L, F->W, m));
+      DE_TRY(run_schedule(ctx, F->U, F->W, m));
+    }
     {
       ProfScope prof(ctx, DE_PROF_TRSV);
       de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->Q, nullptr, F->W, Y, 1);
@@ -3027,6 +3078,8 @@ extern "C"
     cudaSetDevice(F->ctx->device);
     free_schedule(F->L);
     free_schedule(F->U);
+    if (F->sweep_graph)
+      cudaGraphExecDestroy(F->sweep_graph);
     dev_free(F->P);
     dev_free(F->Q);
     dev_free(F->rowscale);

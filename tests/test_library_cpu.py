@@ -133,3 +133,22 @@ def test_generators_row_ranges_and_symmetry():
     np.testing.assert_allclose(sl.eigh(K, Mm, eigvals_only=True), M.eigenvalues_q1_pencil((4, 4, 4)), atol=1e-11)
     np.testing.assert_allclose(np.linalg.eigvalsh(M.to_scipy(M.laplacian_fd((5, 4, 3))).toarray()),
                                M.eigenvalues_laplacian_fd((5, 4, 3)), atol=1e-12)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path: one replica of the reference solve per host core) prints
+    ONE JSON line with the contract's keys; run here on a small grid with a bounded sample"""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "12", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample-iters", "2"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "time-to-m-eigenpairs" and d["unit"] == "s"
+    assert d["higher_is_better"] is False and d["value"] > 0
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
