@@ -358,6 +358,24 @@ namespace
 
   bool valid_cols(int m) { return m > 0 && m % 8 == 0 && m <= DE_MAX_COLS; }
 
+  /** launch with programmatic stream serialization: the kernel's CTAs may be scheduled while the preceding kernel of the
+   *  stream drains; the kernel itself waits for that kernel's completion in pdl_prologue() (kernels_sparse.cuh) */
+  template <class... KArgs, class... Args>
+  cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+  }
+
   // ---- device memory: a caching allocator ------------------------------------------------------------------
   // cudaMalloc / cudaFree take driver-wide locks; on the shared B200 boxes single calls were seen to stall for
   // 0.3-1 s (a 256 MB block allocated and freed per solve made one step in ten take 800 ms instead of 28). Blocks
@@ -715,7 +733,8 @@ namespace
       ctx->tail_armed = false;
       ctx->tail_did_allreduce = true;
       ctx->tail_did_op = true;
-      de::reduce_tail_kernel<<<(len + 31) / 32, block, 0, ctx->stream>>>(partials, nparts, len, out, ctx->done_ptr, t);
+      DE_CUDA(ctx, launch_pdl(de::reduce_tail_kernel, dim3((len + 31) / 32), block, 0, ctx->stream, partials, nparts, len, out,
+                              ctx->done_ptr, t));
       DE_LAUNCH_CHECK(ctx);
       return DE_OK;
     }
@@ -1132,7 +1151,7 @@ namespace
       cfg = true;
     }
     const size_t smem = de::spmm_brb_smem_bytes(NP, a.blob_cap16, a.xs_cap, a.stages);
-    de::spmm_brb_kernel<NP, DOT, HALO, GRAM><<<grid, de::brb_threads(GRAM), smem, ctx->stream>>>(a);
+    DE_CUDA(ctx, launch_pdl(de::spmm_brb_kernel<NP, DOT, HALO, GRAM>, dim3(grid), dim3(de::brb_threads(GRAM)), smem, ctx->stream, a));
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -1420,7 +1439,7 @@ namespace
       a.done = ctx->done_ptr;
       {
         ProfScope prof(ctx, DE_PROF_UPDATE);
-        de::ts2_update_kernel<M, DO_GRAM><<<grid2, C2::THREADS, C2::SMEM, ctx->stream>>>(a);
+        DE_CUDA(ctx, launch_pdl(de::ts2_update_kernel<M, DO_GRAM>, dim3(grid2), dim3(C2::THREADS), C2::SMEM, ctx->stream, a));
       }
       DE_LAUNCH_CHECK(ctx);
       if (DO_GRAM)
@@ -1443,7 +1462,7 @@ namespace
       a.done = ctx->done_ptr;
       {
         ProfScope prof(ctx, DE_PROF_GRAM);
-        de::ts2_gram_kernel<M><<<grid3, de::kTg2Threads, C3::SMEM, ctx->stream>>>(a);
+        DE_CUDA(ctx, launch_pdl(de::ts2_gram_kernel<M>, dim3(grid3), dim3(de::kTg2Threads), C3::SMEM, ctx->stream, a));
       }
       DE_LAUNCH_CHECK(ctx);
       return reduce_partials(ctx, ctx->partials, grid3, M * M, gram_out);

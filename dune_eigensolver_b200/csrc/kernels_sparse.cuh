@@ -14,6 +14,17 @@
 namespace de
 {
 
+  /** Programmatic dependent launch (kernels of the asynchronous driver loop are launched with
+   *  cudaLaunchAttributeProgrammaticStreamSerialization): wait until the preceding kernel of the stream has completed
+   *  and its writes are visible -- everything this kernel reads comes from it -- then allow the NEXT kernel's CTAs to be
+   *  scheduled as SMs become free (they block in their own prologue). Only launch latency is overlapped; without the
+   *  launch attribute both instructions do nothing. */
+  __device__ __forceinline__ void pdl_prologue()
+  {
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+  }
+
   __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
   __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
   __device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }

@@ -205,6 +205,7 @@ namespace de
     constexpr int M = 8 * NP;
     constexpr int LDR = M + 4; // staged row stride (doubles): see lds_frag
     extern __shared__ __align__(128) unsigned char dynq[];
+    pdl_prologue();
     if (a.done != nullptr && *a.done != 0)
       return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -46,6 +46,7 @@ namespace de
                                                              double *__restrict__ out, const int *__restrict__ done_in,
                                                              const TailArgs t)
   {
+    pdl_prologue();
     if (done_in != nullptr && *done_in != 0)
       return;
     __shared__ double red[32][33];

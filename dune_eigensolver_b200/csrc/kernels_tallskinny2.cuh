@@ -63,6 +63,7 @@ namespace de
     static_assert(!(M == 64 && DO_GRAM), "no fused Gram at M = 64");
     constexpr int NPW = kTs2ProducerWarps, NCW = C::NCW;
     extern __shared__ __align__(128) unsigned char dyn2[];
+    pdl_prologue();
     if (a.skip_flag != nullptr && *a.skip_flag != 0)
       return;
     if (a.done != nullptr && *a.done != 0)
@@ -278,6 +279,7 @@ namespace de
     using C = Tg2Cfg<M>;
     constexpr int NPW = kTs2ProducerWarps, NCW = kTg2ConsumerWarps;
     extern __shared__ __align__(128) unsigned char dyn3[];
+    pdl_prologue();
     if (a.done != nullptr && *a.done != 0)
       return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
