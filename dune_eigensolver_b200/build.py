@@ -16,7 +16,8 @@ METIS = "/usr/local/cuda/targets/x86_64-linux/lib/libmetis_static.a"
 
 SOURCES = ["de_capi.cu"]
 HEADERS = ["kernels_sparse.cuh", "kernels_dense.cuh", "kernels_trsv.cuh", "kernels_tallskinny.cuh",
-           "kernels_spmm_blocked.cuh", "brb_format.hpp",
+           "kernels_spmm_blocked.cuh", "brb_format.hpp", "kernels_tallskinny2.cuh", "kernels_tail.cuh", "kernels_peer.cuh",
+           "kernels_brb_build.cuh", "kernels_lobpcg.cuh", "lobpcg_core.hpp", "host_eig.hpp",
            os.path.join("..", "..", "include", "dune_eigensolver_b200.h"),
            os.path.join("..", "..", "include", "dune", "eigensolver", "sparse_lu.hh")]
 

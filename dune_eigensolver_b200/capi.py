@@ -76,6 +76,11 @@ SIGNATURES = {
     "de_standard_inverse": [_vp, _vp, _vp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip],
     "de_generalized_inverse": [_vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int,
                                _ip, _dp],
+    "de_standard_lobpcg": [_vp, _vp, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip],
+    "de_generalized_lobpcg": [_vp, _vp, _vp, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip],
+    "de_lobpcg_mv": [_vp, _vp, _vp, _vp, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _dp, _dp, C.c_int, _ip, _ip, _ip],
+    "de_host_sym_eig": [C.c_int, _dp, _dp, _dp],
+    "de_host_sym_gen_eig": [C.c_int, _dp, _dp, _dp, _dp, _dp],
     "de_start_block": [C.c_int64, C.c_int, C.c_uint, _dp],
     "de_host_factorize": [C.c_int64, _i64p, _i64p, _dp, C.c_int, C.c_int, _vpp],
     "de_host_factor_arrays": [_vp, _i64p, _i64p, _i64p, C.POINTER(_lp), C.POINTER(_lp), C.POINTER(_dp),

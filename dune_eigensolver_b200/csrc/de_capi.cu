@@ -38,6 +38,8 @@
 #include "kernels_tallskinny.cuh"
 #include "kernels_tallskinny2.cuh"
 #include "kernels_trsv.cuh"
+#include "kernels_lobpcg.cuh"
+#include "lobpcg_core.hpp"
 
 // ====================================================================================================
 // error plumbing
@@ -2040,6 +2042,213 @@ namespace
 
   inline int padded_cols(int nev) { return (nev / 8 + std::min(nev % 8, 1)) * 8; } // eigensolver.hh:43
 
+  // ---- LOBPCG: device implementation of the Ops interface of lobpcg_core.hpp ----------------------------------
+  template <int M>
+  int launch_lincomb_t(de_context *ctx, long long n, int ns, const double *const *S, const double *C, double *out,
+                       double *out2)
+  {
+    using K = de::LinCfg<M>;
+    static bool configured = false; // per instantiation; same attribute for every device of this process
+    if (!configured)
+    {
+      DE_CUDA(ctx, cudaFuncSetAttribute(de::lincomb_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)K::SMEM_BYTES));
+      configured = true;
+    }
+    const long long ntiles = (n + K::TR - 1) / K::TR;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (size_t)(200 * 1024) / K::SMEM_BYTES));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * per_sm));
+    ProfScope prof(ctx, DE_PROF_UPDATE);
+    de::lincomb_kernel<M><<<grid, K::THREADS, K::SMEM_BYTES, ctx->stream>>>(n, ns, S[0], ns > 1 ? S[1] : nullptr,
+                                                                           ns > 2 ? S[2] : nullptr, C, out, out2);
+    DE_LAUNCH_CHECK(ctx);
+    return DE_OK;
+  }
+
+  int lincomb_device(de_context *ctx, int m, long long n, int ns, const double *const *S, const double *C, double *out,
+                     double *out2)
+  {
+    switch (m)
+    {
+    case 8:
+      return launch_lincomb_t<8>(ctx, n, ns, S, C, out, out2);
+    case 16:
+      return launch_lincomb_t<16>(ctx, n, ns, S, C, out, out2);
+    case 24:
+      return launch_lincomb_t<24>(ctx, n, ns, S, C, out, out2);
+    case 32:
+      return launch_lincomb_t<32>(ctx, n, ns, S, C, out, out2);
+    case 40:
+      return launch_lincomb_t<40>(ctx, n, ns, S, C, out, out2);
+    case 48:
+      return launch_lincomb_t<48>(ctx, n, ns, S, C, out, out2);
+    case 56:
+      return launch_lincomb_t<56>(ctx, n, ns, S, C, out, out2);
+    case 64:
+      return launch_lincomb_t<64>(ctx, n, ns, S, C, out, out2);
+    }
+    return set_error(ctx, DE_ERR_UNSUPPORTED, "lincomb: column count must be a multiple of 8 in [8,64]");
+  }
+
+  struct LobpcgDeviceOps
+  {
+    using Blk = double *;
+    de_context *ctx = nullptr;
+    const de_matrix *A = nullptr, *B = nullptr;
+    const de_factor *T = nullptr; // optional preconditioner: W <- T^-1 W (factored apply, kernels_trsv.cuh)
+    long long n = 0;
+    int m = 0;
+    ScopedBlocks blocks;
+    double *dcoef = nullptr;  // 3 m^2 coefficients | m Ritz values
+    double *dgrams = nullptr; // 12 m^2
+    double *scratch = nullptr; // a block for the preconditioner's output
+
+    int init()
+    {
+      DE_TRY(blocks.alloc(ctx, &dcoef, (size_t)3 * m * m + m));
+      DE_TRY(blocks.alloc(ctx, &dgrams, (size_t)12 * m * m));
+      if (T)
+        DE_TRY(blocks.alloc(ctx, &scratch, (size_t)n * m));
+      return DE_OK;
+    }
+    int alloc(Blk *b) { return blocks.alloc(ctx, b, (size_t)n * m); }
+    /** wait for the stream; surfaces the sticky Cholesky status and the peer-window error flag */
+    int sync_check() { return fetch_small(ctx, nullptr, nullptr, 0); }
+    int orthonormalize(Blk X, Blk BX)
+    {
+      DE_TRY(reset_status(ctx));
+      if (B)
+        DE_TRY(b_orthonormalize_device(ctx, B, n, m, X, BX, false));
+      else
+        DE_TRY(orthonormalize_device(ctx, n, m, X));
+      return sync_check();
+    }
+    int apply_A(Blk Y, Blk X) { return spmm_device<false>(ctx, A, X, Y, m); }
+    int apply_B(Blk Y, Blk X) { return spmm_device<false>(ctx, B, X, Y, m); }
+    int residual(Blk W, Blk AX, Blk BX, const double *theta, double *norm2)
+    {
+      double *dtheta = dcoef + (size_t)3 * m * m;
+      DE_CUDA(ctx, cudaMemcpyAsync(dtheta, theta, sizeof(double) * m, cudaMemcpyHostToDevice, ctx->stream));
+      const long long pairs = n * m / 2;
+      const int grid = (int)std::max<long long>(1, std::min<long long>((pairs + 255) / 256, (long long)ctx->sm_count * 8));
+      {
+        ProfScope prof(ctx, DE_PROF_MISC);
+        de::residual_kernel<<<grid, 256, 0, ctx->stream>>>(pairs, m, AX, BX, dtheta, W);
+      }
+      DE_LAUNCH_CHECK(ctx);
+      DE_TRY(diag_dot_device(ctx, n, m, W, W, ctx->dDP()));
+      return fetch_small(ctx, ctx->dDP(), norm2, m);
+    }
+    int precondition(Blk W)
+    {
+      if (!T)
+        return DE_OK;
+      DE_TRY(factor_apply_device(ctx, T, W, scratch, m)); // W is clobbered (scratch of the sweeps)
+      DE_CUDA(ctx, cudaMemcpyAsync(W, scratch, sizeof(double) * (size_t)n * m, cudaMemcpyDeviceToDevice, ctx->stream));
+      return DE_OK;
+    }
+    int project(Blk W, Blk X, Blk BX)
+    {
+      DE_TRY(gram_device(ctx, m, n, BX, m, W, m, false, ctx->dG()));
+      return update_device<1>(ctx, m, n, X, m, ctx->dG(), W, m, 0); // W -= X G
+    }
+    int grams(int count, const Blk *L, const Blk *R, const char *sym, double *out)
+    {
+      for (int g = 0; g < count; ++g)
+        DE_TRY(gram_device(ctx, m, n, L[g], m, R[g], m, sym[g] != 0, dgrams + (size_t)g * m * m));
+      DE_CUDA(ctx, cudaMemcpyAsync(out, dgrams, sizeof(double) * (size_t)count * m * m, cudaMemcpyDeviceToHost,
+                                   ctx->stream));
+      return sync_check();
+    }
+    int rotate(Blk X, const double *C)
+    {
+      DE_CUDA(ctx, cudaMemcpyAsync(dcoef, C, sizeof(double) * (size_t)m * m, cudaMemcpyHostToDevice, ctx->stream));
+      const double *S[1] = {X};
+      return lincomb_device(ctx, m, n, 1, S, dcoef, X, nullptr);
+    }
+    int lincomb(int ns, const Blk *S, const double *C, Blk out, Blk out2)
+    {
+      DE_CUDA(ctx, cudaMemcpyAsync(dcoef, C, sizeof(double) * (size_t)ns * m * m, cudaMemcpyHostToDevice, ctx->stream));
+      const double *src[3] = {S[0], ns > 1 ? S[1] : nullptr, ns > 2 ? S[2] : nullptr};
+      return lincomb_device(ctx, m, n, ns, src, dcoef, out, out2);
+    }
+  };
+
+  /** LOBPCG on the device block X (n x m, start block on entry, Ritz vectors on return) */
+  int lobpcg_device(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *T, bool largest, double tol,
+                    int maxiter, int nev, int m, double *X, de::LobpcgResult &res, int verbose)
+  {
+    LobpcgDeviceOps ops;
+    ops.ctx = ctx;
+    ops.A = A;
+    ops.B = B;
+    ops.T = T;
+    ops.n = A->n;
+    ops.m = m;
+    DE_TRY(ops.init());
+    de::LobpcgParams prm;
+    prm.m = m;
+    prm.nev = nev;
+    prm.tol = tol;
+    prm.maxiter = maxiter;
+    prm.verbose = verbose;
+    prm.has_B = B != nullptr;
+    prm.largest = largest;
+    prm.name = B ? "GeneralizedLOBPCG" : "StandardLOBPCG";
+    const int rc = de::lobpcg_run(ops, prm, X, res);
+    if (rc == de::kLobpcgRitzFailed)
+      return set_error(ctx, DE_ERR_SINGULAR,
+                       "LOBPCG: the Rayleigh-Ritz problem on [X W] is numerically singular (or residuals are not finite)");
+    if (rc != DE_OK)
+      return rc;
+    return ops.sync_check();
+  }
+
+  int lobpcg_check_args(de_context *ctx, const char *who, const de_matrix *A, const de_matrix *B, const de_factor *T,
+                        int nev, int m)
+  {
+    if (!valid_cols(m))
+      return set_error(ctx, DE_ERR_UNSUPPORTED, std::string(who) + ": nev exceeds DE_MAX_COLS (64)");
+    if (nev <= 0 || nev > m)
+      return set_error(ctx, DE_ERR_INVALID, std::string(who) + ": nev must be in [1, number of columns]");
+    if ((B && B->n != A->n) || (T && T->n != A->n))
+      return set_error(ctx, DE_ERR_INVALID, std::string(who) + ": A, B and the preconditioner must have the same size");
+    if (T && ctx->nranks > 1)
+      return set_error(ctx, DE_ERR_UNSUPPORTED, std::string(who) + ": the factored preconditioner is single-GPU");
+    return DE_OK;
+  }
+
+  int lobpcg_driver(de_context *ctx, const char *who, const de_matrix *A, const de_matrix *B, const de_factor *T,
+                    double tol, int maxiter, int nev, const double *start_panel8, double *eval, double *evec, int verbose,
+                    int *iterations)
+  {
+    if (!ctx || !A || !start_panel8 || !eval || !evec || nev <= 0)
+      return set_error(ctx, DE_ERR_INVALID, std::string(who) + ": bad arguments");
+    const int m = padded_cols(nev);
+    DE_TRY(lobpcg_check_args(ctx, who, A, B, T, nev, m));
+    DE_TRY(bind_device(ctx));
+    const long long n = A->n;
+    ScopedBlocks blk;
+    double *X;
+    DE_TRY(blk.alloc(ctx, &X, (size_t)n * m));
+    DE_TRY(upload_panel8_device(ctx, n, m, start_panel8, X));
+    de::LobpcgResult res;
+    const auto t0 = std::chrono::steady_clock::now();
+    DE_TRY(lobpcg_device(ctx, A, B, T, false, tol, maxiter, nev, m, X, res, verbose));
+    if (iterations)
+      *iterations = res.iterations;
+    if (verbose > 0) // one summary line in the style of eigensolver.hh:345-350
+    {
+      double worst = 0.0;
+      for (int j = 0; j < nev; ++j)
+        worst = std::max(worst, res.resnorm[j] / std::max(std::abs(res.theta[j]), std::numeric_limits<double>::min()));
+      std::printf("%s:  time_total=%g iterations=%d restarts=%d relres=%g\n", who,
+                  std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), res.iterations,
+                  res.restarts, worst);
+    }
+    return copy_out(ctx, n, m, nev, X, res.theta, eval, evec);
+  }
+
 } // namespace
 
 // ====================================================================================================
@@ -3431,6 +3640,67 @@ extern "C"
     if (relerror_out)
       *relerror_out = relerror;
     return copy_out(ctx, n, m, nev, Q1, ra2, eval, evec);
+  }
+
+
+  // ---- LOBPCG drivers (new; no reference counterpart) ----------------------------------------
+  int de_standard_lobpcg(de_context *ctx, const de_matrix *A, double tol, int maxiter, int nev,
+                         const double *start_panel8, double *eval, double *evec, int verbose, int *iterations)
+  {
+    return lobpcg_driver(ctx, "StandardLOBPCG", A, nullptr, nullptr, tol, maxiter, nev, start_panel8, eval, evec, verbose,
+                         iterations);
+  }
+
+  int de_generalized_lobpcg(de_context *ctx, const de_matrix *A, const de_matrix *B, double tol, int maxiter, int nev,
+                            const double *start_panel8, double *eval, double *evec, int verbose, int *iterations)
+  {
+    if (!B)
+      return set_error(ctx, DE_ERR_INVALID, "GeneralizedLOBPCG: bad arguments");
+    return lobpcg_driver(ctx, "GeneralizedLOBPCG", A, B, nullptr, tol, maxiter, nev, start_panel8, eval, evec, verbose,
+                         iterations);
+  }
+
+  int de_lobpcg_mv(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *T, int largest, double tol,
+                   int maxiter, int nev, de_mv *Q, double *eval_m, double *resnorm_m, int verbose, int *iterations,
+                   int *restarts, int *converged)
+  {
+    if (!ctx || !A || !Q || !eval_m)
+      return set_error(ctx, DE_ERR_INVALID, "de_lobpcg_mv: bad arguments");
+    if (Q->n != A->n)
+      return set_error(ctx, DE_ERR_INVALID, "de_lobpcg_mv: the block does not match the matrix");
+    DE_TRY(lobpcg_check_args(ctx, "de_lobpcg_mv", A, B, T, nev, Q->m));
+    DE_TRY(bind_device(ctx));
+    de::LobpcgResult res;
+    DE_TRY(lobpcg_device(ctx, A, B, T, largest != 0, tol, maxiter, nev, Q->m, Q->d, res, verbose));
+    for (int j = 0; j < Q->m; ++j)
+    {
+      eval_m[j] = res.theta[j];
+      if (resnorm_m)
+        resnorm_m[j] = res.resnorm[j];
+    }
+    if (iterations)
+      *iterations = res.iterations;
+    if (restarts)
+      *restarts = res.restarts;
+    if (converged)
+      *converged = res.converged ? 1 : 0;
+    return DE_OK;
+  }
+
+  int de_host_sym_eig(int n, const double *A, double *w, double *V)
+  {
+    if (n < 0 || (n > 0 && (!A || !w || !V)))
+      return set_error(nullptr, DE_ERR_INVALID, "de_host_sym_eig: bad arguments");
+    return de::hosteig::sym_eig(n, A, w, V) == 0 ? DE_OK
+                                                  : set_error(nullptr, DE_ERR_SINGULAR, "de_host_sym_eig: QL iteration failed");
+  }
+
+  int de_host_sym_gen_eig(int n, const double *GA, const double *GB, double *w, double *C, double *min_pivot)
+  {
+    if (n < 0 || (n > 0 && (!GA || !GB || !w || !C)))
+      return set_error(nullptr, DE_ERR_INVALID, "de_host_sym_gen_eig: bad arguments");
+    const int rc = de::hosteig::sym_gen_eig(n, GA, GB, w, C, 0.0, min_pivot);
+    return rc == 0 ? DE_OK : set_error(nullptr, DE_ERR_SINGULAR, "de_host_sym_gen_eig: GB is not positive definite");
   }
 
   // ---- host-side helpers ---------------------------------------------------------------------------------------

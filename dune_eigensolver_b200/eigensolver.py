@@ -510,3 +510,72 @@ def GeneralizedInverse(ctx, inA, B, shift, reg, tol, maxiter, nev, verbose=0, se
     if verbose > 0:  # the reference's summary line (eigensolver.hh:344-350)
         print("GeneralizedInverse:  time_factorization=%g iterations=%d relerror=%g" % (t_fact, it.value, rel.value))
     return Result(ev, V, it.value, rel.value, t_fact)
+
+
+# ---- LOBPCG drivers (new: the reference has none; SURVEY.md §8f rank 1, BASELINE.json configs[1]) ----------------
+def StandardLOBPCG(ctx, A, tol, maxiter, nev, verbose=0, seed=123, start=None):
+    """nev smallest eigenpairs of A x = lambda x without a factorisation. Parameter shape of the reference's drivers
+    (eigensolver.hh:28-29): same start block, m = nev rounded up to 8, eval / evec as in StandardLargest.
+    Convergence: ||A x - theta x||_2 <= tol |theta| for every wanted pair."""
+    rp, ci, v = A if isinstance(A, tuple) else (A.indptr, A.indices, A.data)
+    n = len(rp) - 1
+    if start is None:
+        start = start_block(n, padded_cols(nev), seed)
+    dA = Matrix(ctx, (rp, ci, v))
+    try:
+        ev, V, it = np.zeros(nev), np.zeros((nev, n)), C.c_int(0)
+        check(capi.lib().de_standard_lobpcg(ctx._h, dA._h, tol, maxiter, nev, dptr(f64(start)), dptr(ev), dptr(V),
+                                            verbose, C.byref(it)), ctx._h)
+    finally:
+        dA.close()
+    return Result(ev, V, it.value)
+
+
+def GeneralizedLOBPCG(ctx, A, B, tol, maxiter, nev, verbose=0, seed=123, start=None):
+    """nev smallest eigenpairs of A x = lambda B x (B symmetric positive definite) without a factorisation; the
+    eigenvectors are B-orthonormal like GeneralizedInverse's (eigensolver.hh:204-351)."""
+    rpa, cia, va = A if isinstance(A, tuple) else (A.indptr, A.indices, A.data)
+    rpb, cib, vb = B if isinstance(B, tuple) else (B.indptr, B.indices, B.data)
+    n = len(rpa) - 1
+    if start is None:
+        start = start_block(n, padded_cols(nev), seed)
+    dA, dB = Matrix(ctx, (rpa, cia, va)), Matrix(ctx, (rpb, cib, vb))
+    try:
+        ev, V, it = np.zeros(nev), np.zeros((nev, n)), C.c_int(0)
+        check(capi.lib().de_generalized_lobpcg(ctx._h, dA._h, dB._h, tol, maxiter, nev, dptr(f64(start)), dptr(ev),
+                                               dptr(V), verbose, C.byref(it)), ctx._h)
+    finally:
+        dA.close()
+        dB.close()
+    return Result(ev, V, it.value)
+
+
+def lobpcg_mv(ctx, dA, Q, tol, maxiter, nev=None, dB=None, dT=None, largest=False, verbose=0):
+    """Device-resident LOBPCG with all options (de_lobpcg_mv): Q holds the start block on entry and the m Ritz vectors
+    on return; dB: mass matrix or None; dT: a Factor used as preconditioner or None.
+    Returns (eval[m], resnorm[m], iterations, restarts, converged)."""
+    nev = Q.m if nev is None else nev
+    ev, rn = np.zeros(Q.m), np.zeros(Q.m)
+    it, rs, cv = C.c_int(0), C.c_int(0), C.c_int(0)
+    check(capi.lib().de_lobpcg_mv(ctx._h, dA._h, dB._h if dB is not None else None, dT._h if dT is not None else None,
+                                  1 if largest else 0, tol, maxiter, nev, Q._h, dptr(ev), dptr(rn), verbose,
+                                  C.byref(it), C.byref(rs), C.byref(cv)), ctx._h)
+    return ev, rn, it.value, rs.value, bool(cv.value)
+
+
+def host_sym_eig(A):
+    """(w ascending, V with eigenvector j in column j) of a dense symmetric matrix -- the host Rayleigh-Ritz solver."""
+    A = f64(A)
+    n = A.shape[0]
+    w, V = np.zeros(n), np.zeros((n, n))
+    check(capi.lib().de_host_sym_eig(n, dptr(A), dptr(w), dptr(V)))
+    return w, V
+
+
+def host_sym_gen_eig(GA, GB):
+    """(w ascending, C with C^T GB C = I, smallest scaled Cholesky pivot) of GA c = w GB c."""
+    GA, GB = f64(GA), f64(GB)
+    n = GA.shape[0]
+    w, Cm, piv = np.zeros(n), np.zeros((n, n)), C.c_double(0.0)
+    check(capi.lib().de_host_sym_gen_eig(n, dptr(GA), dptr(GB), dptr(w), dptr(Cm), C.byref(piv)))
+    return w, Cm, piv.value

@@ -236,6 +236,35 @@ int de_generalized_inverse(de_context *ctx, const de_matrix *A, const de_matrix 
                            double tol, int maxiter, int nev, const double *start_panel8, double *eval, double *evec,
                            int verbose, int *iterations, double *relerror);
 
+/* ---- LOBPCG drivers -------------------------------------------------------------------------------------
+ * NEW: the reference has no LOBPCG (its drivers are eigensolver.hh:28-112, :116-198, :204-351); BASELINE.json names
+ * StandardLOBPCG for the 3D configurations, SURVEY.md §8f ranks it first among the adjacent components. Parameter
+ * shape of the reference's free functions: start block filled like eigensolver.hh:50-55 (de_start_block), m = nev
+ * rounded up to a multiple of 8 (eigensolver.hh:43), eval / evec caller-allocated (nev values, nev vectors of length
+ * n). Computes the nev SMALLEST eigenpairs of A x = lambda x (A x = lambda B x, B symmetric positive definite) without
+ * any factorisation. Convergence: ||A x_j - theta_j B x_j||_2 <= tol * |theta_j| for every j < nev, with x_j
+ * B-normalised; like the reference's drivers the loop falls through silently at maxiter. *iterations = number of
+ * basis updates. The Rayleigh-Ritz problem (3m x 3m) is solved on the host (csrc/host_eig.hpp); every n x m operation
+ * is a device kernel (csrc/lobpcg_core.hpp lists them). Iteration counts are parity-unpinned (no reference
+ * implementation); converged eigenpairs are checked against analytic spectra / the reference's drivers. */
+int de_standard_lobpcg(de_context *ctx, const de_matrix *A, double tol, int maxiter, int nev,
+                       const double *start_panel8, double *eval, double *evec, int verbose, int *iterations);
+int de_generalized_lobpcg(de_context *ctx, const de_matrix *A, const de_matrix *B, double tol, int maxiter, int nev,
+                          const double *start_panel8, double *eval, double *evec, int verbose, int *iterations);
+/* device-resident variant with all options: B may be NULL (standard problem); T, if not NULL, is a factorisation used
+ * as preconditioner W <- T^-1 W (e.g. of A + shift*B; single GPU only); largest != 0 selects the largest eigenvalues.
+ * Q: start block on entry, all m Ritz vectors on return; eval_m / resnorm_m (may be NULL): m Ritz values and residual
+ * norms; restarts / converged may be NULL. Works on a row-partitioned matrix (n = owned rows; reductions all-reduced). */
+int de_lobpcg_mv(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *T, int largest, double tol,
+                 int maxiter, int nev, de_mv *Q, double *eval_m, double *resnorm_m, int verbose, int *iterations,
+                 int *restarts, int *converged);
+/* Host-only (no GPU): the dense symmetric eigensolvers of the Rayleigh-Ritz step. A = V diag(w) V^T (w ascending,
+ * eigenvector j in column j of the row-major V); GA c = w GB c with C^T GB C = I, *min_pivot (may be NULL) = smallest
+ * Cholesky pivot of the unit-diagonal-scaled GB. DE_ERR_SINGULAR if GB is not positive definite. */
+int de_host_sym_eig(int n, const double *A, double *w, double *V);
+int de_host_sym_gen_eig(int n, const double *GA, const double *GB, double *w, double *C, double *min_pivot);
+
+
 /* ---- host-side helpers (no GPU) -------------------------------------------------------------------*/
 /* the reference's start block: std::mt19937{seed} + std::normal_distribution<double>{0,1}, filled
  * panel -> row -> column-in-panel (eigensolver.hh:50-55, :138-143, :232-237) */

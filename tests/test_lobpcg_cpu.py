@@ -1,0 +1,126 @@
+"""LOBPCG drivers, CPU side (no GPU): the host Rayleigh-Ritz solver against numpy / scipy, and the orchestration
+template of csrc/lobpcg_core.hpp -- the same code the library runs with its device kernels -- instantiated with plain
+host loops (tests/cpp/lobpcg_host_test.cc, test infrastructure) against analytic spectra.
+
+The reference has no LOBPCG, so there is no reference vector to pin iteration counts to: what is
+checked is the converged eigenpairs."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from dune_eigensolver_b200 import eigensolver as E, matrices as M
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "lobpcg_host_test.cc")
+EXE = os.path.join(ROOT, "tests", "cpp", "lobpcg_host_test")
+CORE = [os.path.join(ROOT, "dune_eigensolver_b200", "csrc", f) for f in ("lobpcg_core.hpp", "host_eig.hpp")]
+
+
+def build_exe():
+    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(f) for f in [SRC] + CORE):
+        return EXE
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++17", "-O2", SRC, "-o", EXE], check=True, capture_output=True, text=True)
+    return EXE
+
+
+def run(*args):
+    out = subprocess.run([build_exe(), *[str(a) for a in args]], capture_output=True, text=True, timeout=300)
+    vals = {}
+    for line in out.stdout.splitlines():
+        k, _, rest = line.partition(" ")
+        vals[k] = rest
+    return out.returncode, vals, out.stdout
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 8, 24, 96, 192])
+def test_host_sym_eig_matches_numpy(n):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    A = A + A.T
+    w, V = E.host_sym_eig(A)
+    assert np.abs(w - np.linalg.eigvalsh(A)).max() <= 1e-13 * max(1.0, np.abs(A).max() * n)
+    assert np.abs(V.T @ V - np.eye(n)).max() <= 1e-13
+    assert np.abs(A @ V - V * w).max() <= 1e-12 * max(1.0, np.abs(w).max())
+
+
+def test_host_sym_eig_degenerate():
+    for A in (np.eye(7), np.zeros((5, 5)), np.diag([3.0, 1, 2, 2, 2, 5])):
+        w, V = E.host_sym_eig(A)
+        assert np.allclose(w, np.sort(np.diag(A)))
+        assert np.abs(V.T @ V - np.eye(len(w))).max() <= 1e-14
+
+
+@pytest.mark.parametrize("n", [2, 16, 48, 96, 192])
+def test_host_sym_gen_eig_matches_scipy(n):
+    import scipy.linalg as sl
+
+    rng = np.random.default_rng(100 + n)
+    A = rng.standard_normal((n, n))
+    A = A + A.T
+    Bm = rng.standard_normal((n, n + 3))
+    Bm = Bm @ Bm.T + 0.1 * np.eye(n)
+    D = np.diag(10.0 ** rng.uniform(-6, 2, n))  # badly scaled basis vectors: the unit-diagonal scaling must cope
+    Bm = D @ Bm @ D
+    A = D @ A @ D
+    w, C, piv = E.host_sym_gen_eig(A, Bm)
+    wr = sl.eigh(A, Bm, eigvals_only=True)
+    assert np.abs(w - wr).max() <= 1e-11 * np.abs(wr).max()
+    assert np.abs(C.T @ Bm @ C - np.eye(n)).max() <= 1e-11
+    assert 0.0 < piv <= 1.0
+
+
+def test_host_sym_gen_eig_rejects_indefinite():
+    GA = np.eye(4)
+    GB = np.diag([1.0, 1.0, -1.0, 1.0])
+    with pytest.raises(E.DeError) as e:
+        E.host_sym_gen_eig(GA, GB)
+    assert e.value.status == E.capi.DE_ERR_SINGULAR
+    v = np.ones((4, 1))
+    with pytest.raises(E.DeError):
+        E.host_sym_gen_eig(GA, v @ v.T)  # rank one
+
+
+@pytest.mark.parametrize("N,nev,tol", [(20, 8, 1e-8), (24, 32, 1e-10), (40, 24, 1e-6)])
+def test_lobpcg_orchestration_standard_vs_analytic(N, nev, tol):
+    """2D Dirichlet Laplacian of the reference (src/dune-eigensolver.cc:98-103) against its analytic spectrum
+    (:437-446): eigenvalue error of a Ritz pair is <= residual^2 / gap, far below tol * lambda here."""
+    rc, vals, text = run(N, nev, tol, 0, 0)
+    assert rc == 0, text
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    an = M.eigenvalues_laplace_dirichlet_2d(N)[:nev]
+    assert np.abs(ev - an).max() <= 10 * tol * np.abs(an).max()
+    assert float(vals["maxres"]) <= tol and float(vals["orth"]) <= 1e-12
+
+
+def test_lobpcg_orchestration_largest():
+    rc, vals, text = run(20, 8, 1e-8, 0, 1)
+    assert rc == 0, text
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    an = M.eigenvalues_laplace_dirichlet_2d(20)[::-1][:8]
+    assert np.abs(ev - an).max() <= 1e-7
+
+
+@pytest.mark.parametrize("N,nev,tol", [(16, 12, 1e-9), (30, 16, 1e-12)])
+def test_lobpcg_orchestration_generalized(N, nev, tol):
+    """A x = lambda B x with the 5-point Laplacian and an SPD matrix on the same pattern: both are polynomials in the
+    1D second-difference matrices, so the pencil's spectrum is analytic."""
+    rc, vals, text = run(N, nev, tol, 1, 0)
+    assert rc == 0, text
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    c = np.cos(np.pi * np.arange(1, N + 1) / (N + 1.0))
+    lam = (4.0 - 2.0 * (c[:, None] + c[None, :])) / (4.0 + 1.0 * (c[:, None] + c[None, :]))
+    an = np.sort(lam.reshape(-1))[:nev]
+    assert np.abs(ev - an).max() <= 10 * tol * np.abs(an).max()
+    assert float(vals["maxres"]) <= tol and float(vals["orth"]) <= 1e-12
+
+
+def test_lobpcg_orchestration_restarts_when_basis_is_singular():
+    """3 m = 192 columns in a 144-dimensional space: S^T B S is singular every iteration, the Rayleigh-Ritz step falls
+    back to [X W] each time and the iteration still converges."""
+    rc, vals, text = run(12, 64, 1e-8, 1, 0)
+    assert rc == 0, text
+    assert int(vals["restarts"]) >= int(vals["iterations"]) - 2
+    assert float(vals["maxres"]) <= 1e-8

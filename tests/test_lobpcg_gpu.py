@@ -1,0 +1,124 @@
+"""LOBPCG drivers on the GPU (BASELINE.json configs[1] names StandardLOBPCG).
+
+The reference has no LOBPCG, so iteration counts are parity-unpinned. What is pinned: the converged eigenpairs --
+against analytic spectra, against the reference's own drivers (oracle: StandardLargest / GeneralizedInverse at tight
+tolerance) and through the north_star's criteria: eigenvalues within 1e-10 relative where the tolerance allows it,
+residuals ||A x - lambda B x|| under the requested tolerance, (B-)orthonormal eigenvectors."""
+import numpy as np
+import pytest
+
+from dune_eigensolver_b200 import eigensolver as E, matrices as M
+
+pytestmark = pytest.mark.gpu
+
+
+def check_pairs(A, B, lam, V, tol):
+    As = M.to_scipy(A)
+    Bs = None if B is None else M.to_scipy(B)
+    X = V.T
+    BX = X if Bs is None else Bs @ X
+    R = As @ X - BX * lam
+    rel = np.linalg.norm(R, axis=0) / np.abs(lam)
+    assert rel.max() <= 1.05 * tol, rel
+    G = X.T @ BX
+    assert np.abs(G - np.eye(len(lam))).max() <= 1e-10
+
+
+@pytest.mark.parametrize("N,nev,tol", [(20, 8, 1e-8), (30, 16, 1e-9), (30, 20, 1e-6), (30, 32, 1e-10), (30, 40, 1e-6),
+                                        (30, 48, 1e-6), (30, 56, 1e-6), (30, 64, 1e-7), (17, 3, 1e-8)])
+def test_standard_lobpcg_2d_analytic(ctx, N, nev, tol):
+    """every block width 8..64 (each is its own instantiation of the combination / projection kernels) on the
+    reference's 2D Laplacian against its analytic spectrum (src/dune-eigensolver.cc:437-446)"""
+    A = M.laplacian_dirichlet_2d(N)
+    r = E.StandardLOBPCG(ctx, A, tol, 2000, nev)
+    an = M.eigenvalues_laplace_dirichlet_2d(N)[:nev]
+    assert r.iterations < 2000
+    assert np.abs(r.eval - an).max() <= max(1e-10, 1000 * tol * tol) * np.abs(an).max()
+    assert np.all(np.diff(r.eval) >= -1e-12)  # ascending
+    check_pairs(A, None, r.eval, r.evec, tol)
+
+
+def test_standard_lobpcg_3d_q1_and_fd(ctx):
+    for A, an in ((M.q1_stiffness((16, 16, 16)), M.eigenvalues_q1_stiffness((16, 16, 16))),
+                  (M.laplacian_fd((40, 36, 32)), M.eigenvalues_laplacian_fd((40, 36, 32)))):
+        r = E.StandardLOBPCG(ctx, A, 1e-8, 2000, 12)
+        assert np.abs(r.eval - an[:12]).max() <= 1e-10 * np.abs(an[:12]).max()
+        check_pairs(A, None, r.eval, r.evec, 1e-8)
+
+
+def test_generalized_lobpcg_q1_pencil(ctx):
+    """stiffness + consistent mass (configs[2] of BASELINE.json, small): analytic pencil spectrum"""
+    shape = (14, 12, 10)
+    A, B = M.q1_stiffness(shape), M.q1_mass(shape)
+    r = E.GeneralizedLOBPCG(ctx, A, B, 1e-8, 2000, 10)
+    an = M.eigenvalues_q1_pencil(shape)[:10]
+    assert np.abs(r.eval - an).max() <= 1e-10 * np.abs(an).max()
+    check_pairs(A, B, r.eval, r.evec, 1e-8)
+
+
+def test_generalized_lobpcg_matches_reference_generalized_inverse(ctx, oracle):
+    """same pencil through the reference's GeneralizedInverse (eigensolver.hh:204-351, compiled oracle) at tight
+    tolerance: eigenvalues within 1e-10 relative (north_star), eigenvectors equal up to sign where simple"""
+    N = 18
+    A, B = M.q1_stiffness((N, N)), M.q1_mass((N, N))
+    ev, V, it = oracle.generalized_inverse(A, B, 1e-3, 0.0, 1e-13, 4000, 8)
+    r = E.GeneralizedLOBPCG(ctx, A, B, 1e-9, 2000, 8)
+    order = np.argsort(ev)
+    assert np.abs(r.eval - ev[order]).max() <= 1e-10 * np.abs(ev).max()
+    x_ref, x = V[order[0]], r.evec[0]  # the smallest eigenvalue is simple
+    Bs = M.to_scipy(B)
+    assert abs(abs(x_ref @ (Bs @ x)) - 1.0) <= 1e-8
+
+
+def test_lobpcg_mv_largest_matches_reference_standard_largest(ctx, oracle):
+    N, nev = 20, 8
+    A = M.laplacian_dirichlet_2d(N)
+    ev, V, k = oracle.standard_largest((A[0].copy(), A[1].copy(), A[2].copy()), 0.0, 1e-12, 4000, nev)
+    dA = E.Matrix(ctx, A)
+    Q = E.MultiVector(ctx, N * N, 8)
+    Q.upload_panels(E.start_block(N * N, 8, 123))
+    lam, rn, it, restarts, conv = E.lobpcg_mv(ctx, dA, Q, 1e-9, 2000, nev=nev, largest=True)
+    assert conv and it < 2000
+    an = M.eigenvalues_laplace_dirichlet_2d(N)[::-1][:nev]
+    assert np.abs(lam - an).max() <= 1e-10 * an.max()  # descending, like the reference's largest-first order
+    assert np.abs(np.sort(lam) - np.sort(ev)).max() <= 5e-8  # the reference itself is only this close to the spectrum
+    assert np.all(rn[:nev] <= 1e-9 * np.abs(lam[:nev]) * 1.0001)
+    X = Q.download()
+    assert np.abs(X.T @ X - np.eye(8)).max() <= 1e-12
+    Q.close()
+    dA.close()
+
+
+def test_lobpcg_mv_factored_preconditioner_and_maxiter(ctx):
+    """T = factorisation of A + 0.05 I as preconditioner (the factored apply of kernels_cpp.hh:660-755 reused):
+    far fewer iterations than without; maxiter is honoured silently like the reference's loops (eigensolver.hh:191)"""
+    N, nev = 24, 8
+    A = M.laplacian_dirichlet_2d(N)
+    sh = (A[0].copy(), A[1].copy(), A[2].copy())
+    E._add_to_diagonal(np.asarray(sh[0]), np.asarray(sh[1]), sh[2], 0.05)
+    hF = E.HostFactorization(sh, 1)
+    dA, dF = E.Matrix(ctx, A), E.Factor(ctx, hF)
+    an = M.eigenvalues_laplace_dirichlet_2d(N)[:nev]
+    Q = E.MultiVector(ctx, N * N, 8)
+    Q.upload_panels(E.start_block(N * N, 8, 123))
+    lam0, _, it0, _, conv0 = E.lobpcg_mv(ctx, dA, Q, 1e-9, 2000, nev=nev)
+    Q.upload_panels(E.start_block(N * N, 8, 123))
+    lam1, _, it1, _, conv1 = E.lobpcg_mv(ctx, dA, Q, 1e-9, 2000, nev=nev, dT=dF)
+    assert conv0 and conv1
+    assert np.abs(lam0 - an).max() <= 1e-10 and np.abs(lam1 - an).max() <= 1e-10
+    assert it1 * 3 < it0
+    Q.upload_panels(E.start_block(N * N, 8, 123))
+    _, _, it2, _, conv2 = E.lobpcg_mv(ctx, dA, Q, 1e-12, 3, nev=nev)
+    assert it2 == 3 and not conv2
+    for h in (Q, dA, dF, hF):
+        h.close()
+
+
+def test_lobpcg_argument_errors(ctx):
+    A = M.laplacian_dirichlet_2d(12)
+    with pytest.raises(E.DeError) as e:
+        E.StandardLOBPCG(ctx, A, 1e-6, 10, 65)
+    assert e.value.status == E.capi.DE_ERR_UNSUPPORTED
+    with pytest.raises(E.DeError) as e:
+        E.GeneralizedLOBPCG(ctx, A, M.laplacian_dirichlet_2d(10), 1e-6, 10, 8, start=E.start_block(144, 8))
+    assert e.value.status == E.capi.DE_ERR_INVALID
