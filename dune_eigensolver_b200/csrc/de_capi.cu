@@ -2101,14 +2101,11 @@ namespace
     ScopedBlocks blocks;
     double *dcoef = nullptr;  // 3 m^2 coefficients | m Ritz values
     double *dgrams = nullptr; // 12 m^2
-    double *scratch = nullptr; // a block for the preconditioner's output
 
     int init()
     {
       DE_TRY(blocks.alloc(ctx, &dcoef, (size_t)3 * m * m + m));
       DE_TRY(blocks.alloc(ctx, &dgrams, (size_t)12 * m * m));
-      if (T)
-        DE_TRY(blocks.alloc(ctx, &scratch, (size_t)n * m));
       return DE_OK;
     }
     int alloc(Blk *b) { return blocks.alloc(ctx, b, (size_t)n * m); }
@@ -2143,9 +2140,8 @@ namespace
     {
       if (!T)
         return DE_OK;
-      DE_TRY(factor_apply_device(ctx, T, W, scratch, m)); // W is clobbered (scratch of the sweeps)
-      DE_CUDA(ctx, cudaMemcpyAsync(W, scratch, sizeof(double) * (size_t)n * m, cudaMemcpyDeviceToDevice, ctx->stream));
-      return DE_OK;
+      // in place: the apply permutes W into the factor's own work block before anything is written back
+      return factor_apply_device(ctx, T, W, W, m);
     }
     int project(Blk W, Blk X, Blk BX)
     {

@@ -177,4 +177,56 @@ void GeneralizedInverse(const ISTLM &inA, const ISTLM &B, double shift, double r
               << " iterations=" << iterations << " relerror=" << relerror << std::endl;
 }
 
+/** \brief nev smallest eigenpairs of A x = lambda x by LOBPCG -- NEW: the reference has no LOBPCG driver (its three
+ *  are eigensolver.hh:28-112, :116-198, :204-351); BASELINE.json names StandardLOBPCG for the 3D configurations, where
+ *  smallest eigenpairs are out of reach of StandardInverse without a factorisation. Parameter shape of the reference's
+ *  Standard* drivers minus the shift: same start block (seed), m = nev rounded up to 8, eval / evec pre-sized by the
+ *  caller, A is not modified. Stops when ||A x - theta x||_2 <= tol |theta| for all nev pairs, or silently at maxiter. */
+template <typename ISTLM, typename VEC>
+void StandardLOBPCG(const ISTLM &A, double tol, int maxiter, int nev, std::vector<double> &eval, std::vector<VEC> &evec,
+                    int verbose = 0, unsigned int seed = 123)
+{
+  de_b200::require_square_blocks<ISTLM>("StandardLOBPCG");
+  de_b200::require_scalar_blocks<ISTLM>("matmul_sparse_tallskinny_blocked");
+  const std::size_t n = A.N();
+  const std::size_t m = de_b200::padded_columns(nev, 8);
+  MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
+  auto &ctx = de_b200::Context::thread_default();
+  de_b200::DeviceMatrix dA(ctx, A);
+  std::vector<double> values(nev), vectors((std::size_t)nev * n);
+  int iterations = 0;
+  de_b200::check(de_standard_lobpcg(ctx.get(), dA.get(), tol, maxiter, nev, start.data(), values.data(), vectors.data(),
+                                    verbose, &iterations),
+                 ctx.get());
+  de_b200::scatter_results(nev, n, values, vectors, eval, evec);
+}
+
+/** \brief nev smallest eigenpairs of A x = lambda B x (B symmetric positive definite) by LOBPCG; B-orthonormal
+ *  eigenvectors, eval / evec resized like GeneralizedInverse does (reference eigensolver.hh:328-341). NEW, see above. */
+template <typename ISTLM, typename VEC>
+void GeneralizedLOBPCG(const ISTLM &A, const ISTLM &B, double tol, int maxiter, int nev, std::vector<double> &eval,
+                       std::vector<VEC> &evec, int verbose = 0, unsigned int seed = 123)
+{
+  de_b200::require_square_blocks<ISTLM>("GeneralizedLOBPCG");
+  de_b200::require_scalar_blocks<ISTLM>("B_orthonormalize_blocked");
+  const std::size_t n = A.N();
+  const std::size_t m = de_b200::padded_columns(nev, 8);
+  MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
+  auto &ctx = de_b200::Context::thread_default();
+  de_b200::DeviceMatrix dA(ctx, A), dB(ctx, B);
+  std::vector<double> values(nev), vectors((std::size_t)nev * n);
+  int iterations = 0;
+  de_b200::check(de_generalized_lobpcg(ctx.get(), dA.get(), dB.get(), tol, maxiter, nev, start.data(), values.data(),
+                                       vectors.data(), verbose, &iterations),
+                 ctx.get());
+  if (eval.size() != (std::size_t)nev)
+    eval.resize(nev);
+  if (evec.size() != (std::size_t)nev)
+    evec.resize(nev);
+  for (int j = 0; j < nev; ++j)
+    if (evec[j].size() != n)
+      evec[j].resize(n);
+  de_b200::scatter_results(nev, n, values, vectors, eval, evec);
+}
+
 #endif

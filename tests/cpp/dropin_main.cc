@@ -84,6 +84,11 @@ int main(int argc, char **argv)
       eval = ev;
       evec = V;
     }
+    else if (mode == "lobpcg")
+    {
+      Matrix A = laplacian(N, "dirichlet", 0);
+      StandardLOBPCG(A, tol, 4000, nev, eval, evec, 0, 123);
+    }
     else if (mode == "kernels")
     {
       Matrix A = laplacian(N, "dirichlet", 0);

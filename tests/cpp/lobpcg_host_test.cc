@@ -81,7 +81,54 @@ struct HostOps
         G[(size_t)a * m + b] = s;
       }
   }
+  /** CholQR2 with the pivot test of the device kernel (chol_inverse2_kernel, kernels_dense.cuh: a pivot that is not
+   *  above 4 m eps G_kk reports rank deficiency), so that the orchestration sees the same failures on the CPU as on
+   *  the GPU; set `mgs` for modified Gram-Schmidt instead. */
+  bool mgs = false;
   int orthonormalize(Blk X, Blk BX)
+  {
+    if (mgs)
+      return orthonormalize_mgs(X, BX);
+    std::vector<double> G((size_t)m * m), R((size_t)m * m), T((size_t)n * m);
+    for (int sweep = 0; sweep < 2; ++sweep)
+    {
+      if (B)
+        B->apply(X, BX, m);
+      gram(X, B ? BX : X, G.data());
+      // G = R^T R, R upper triangular
+      std::fill(R.begin(), R.end(), 0.0);
+      for (int k = 0; k < m; ++k)
+      {
+        double d = G[(size_t)k * m + k];
+        for (int q = 0; q < k; ++q)
+          d -= R[(size_t)q * m + k] * R[(size_t)q * m + k];
+        if (!(d > 4.0 * m * 2.220446049250313e-16 * G[(size_t)k * m + k]))
+          return 5;
+        R[(size_t)k * m + k] = std::sqrt(d);
+        for (int j = k + 1; j < m; ++j)
+        {
+          double v = G[(size_t)k * m + j];
+          for (int q = 0; q < k; ++q)
+            v -= R[(size_t)q * m + k] * R[(size_t)q * m + j];
+          R[(size_t)k * m + j] = v / R[(size_t)k * m + k];
+        }
+      }
+      // X <- X R^-1 : forward substitution per row
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < m; ++j)
+        {
+          double v = X[(size_t)i * m + j];
+          for (int q = 0; q < j; ++q)
+            v -= T[(size_t)i * m + q] * R[(size_t)q * m + j];
+          T[(size_t)i * m + j] = v / R[(size_t)j * m + j];
+        }
+      std::copy(T.begin(), T.end(), X);
+    }
+    if (B)
+      B->apply(X, BX, m);
+    return 0;
+  }
+  int orthonormalize_mgs(Blk X, Blk BX)
   {
     // modified Gram-Schmidt in the B inner product, twice
     std::vector<double> bx((size_t)n);

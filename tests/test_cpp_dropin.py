@@ -84,3 +84,14 @@ def test_dropin_kernels(oracle):
     assert np.abs(dp - ref).max() <= 1e-12 * np.abs(ref).max()
     assert float(vals["ortho_defect"]) < 1e-13
     assert "number of cols must be a multiple of block size" in vals["caught"]
+
+
+@pytest.mark.gpu
+def test_dropin_standard_lobpcg_analytic():
+    """StandardLOBPCG through the C++ header template (new driver, reference parameter shape) against the analytic
+    spectrum of the reference's Laplacian (src/dune-eigensolver.cc:437-446)"""
+    rc, vals, text = run("lobpcg", 20, 8, 1e-9)
+    assert rc == 0, text
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    an = M.eigenvalues_laplace_dirichlet_2d(20)[:8]
+    assert np.abs(ev - an).max() <= 1e-10 * an.max()

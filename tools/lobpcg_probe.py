@@ -1,0 +1,97 @@
+"""StandardLOBPCG on one B200: time-to-nev-smallest-eigenpairs of a 3D Laplacian (BASELINE.json configs[1]:
+"3D Q1 Laplace 100^3, 32 eigenpairs via StandardLOBPCG on 1 B200"), printed as ONE JSON line.
+
+    python tools/lobpcg_probe.py [--grid 100] [--stencil q1|fd] [--nev 32] [--tol 2e-3] [--steps 3] [--verify]
+
+The reference has no LOBPCG and its shift-invert drivers cannot reach the smallest eigenpairs of this matrix without a
+3D factorisation, so there is no reference arm for this number; what pins the result is the analytic spectrum of the
+matrix (matrices.eigenvalues_q1_stiffness) and, with --verify, residuals recomputed on the host with scipy.
+bench.py runs this as a child process and attaches the line as its "lobpcg" object.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", type=int, default=100)
+    ap.add_argument("--stencil", default="q1", choices=["q1", "fd"])
+    ap.add_argument("--nev", type=int, default=32)
+    ap.add_argument("--tol", type=float, default=2e-3)
+    ap.add_argument("--maxiter", type=int, default=4000)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--verbose", type=int, default=0)
+    args = ap.parse_args()
+
+    from dune_eigensolver_b200 import eigensolver as E, matrices as M
+
+    shape = (args.grid,) * 3
+    n = args.grid ** 3
+    m = E.padded_cols(args.nev)
+    A = M.q1_stiffness(shape) if args.stencil == "q1" else M.laplacian_fd(shape)
+    analytic = (M.eigenvalues_q1_stiffness(shape) if args.stencil == "q1" else M.eigenvalues_laplacian_fd(shape))[:m]
+    ctx = E.Context(0)
+    dA = E.Matrix(ctx, A)
+    start = E.start_block(n, m, 123)
+    Q = E.MultiVector(ctx, n, m)
+
+    def solve():
+        Q.upload_panels(start)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        out = E.lobpcg_mv(ctx, dA, Q, args.tol, args.maxiter, nev=args.nev, verbose=args.verbose)
+        ctx.synchronize()
+        return time.perf_counter() - t0, out
+
+    solve()  # warm-up (kernel attributes, allocator cache)
+    times, out = [], None
+    for _ in range(args.steps):
+        t, out = solve()
+        times.append(t)
+    lam, rn, it, restarts, conv = out
+    # one more solve with every kernel category timed: where the time goes
+    ctx.profile(reset=True)
+    ctx.set_profiling(True)
+    t_prof, _ = solve()
+    prof = ctx.profile(reset=True)
+    ctx.set_profiling(False)
+    kernel_ms = sum(v[0] for v in prof.values())
+    line = {
+        "driver": "StandardLOBPCG (de_lobpcg_mv, blocks resident in HBM)",
+        "workload": "3D %s Laplace %d^3 (n=%d), %d smallest eigenpairs, m=%d, relative residual tol=%g, seed=123" %
+                    ("Q1 27-point FE stiffness" if args.stencil == "q1" else "7-point FD", args.grid, n, args.nev, m,
+                     args.tol),
+        "seconds": float(np.median(times)), "seconds_all": [round(t, 5) for t in times],
+        "iterations": it, "restarts": restarts, "converged": conv, "ms_per_iteration": 1e3 * float(np.median(times)) / max(it, 1),
+        "max_rel_residual": float((rn[:args.nev] / np.abs(lam[:args.nev])).max()),
+        "max_rel_eigenvalue_error_vs_analytic": float((np.abs(lam[:args.nev] - analytic[:args.nev]) / analytic[:args.nev]).max()),
+        "eigenvalues_head": [float(x) for x in lam[:4]],
+        "kernel_ms_per_solve": {k: round(v[0], 3) for k, v in prof.items() if v[1] > 0},
+        "kernel_launches_per_solve": {k: int(v[1]) for k, v in prof.items() if v[1] > 0},
+        "host_share": max(0.0, 1.0 - kernel_ms * 1e-3 / t_prof) if t_prof > 0 else None,
+        "reference_arm": None,
+        "note": "no reference arm: the reference has no LOBPCG and no factorisation-free route to these eigenpairs",
+    }
+    if args.verify:
+        import scipy.sparse as sp
+
+        As = sp.csr_matrix((A[2], A[1], A[0]), shape=(n, n))
+        X = Q.download_rowmajor()[:, :args.nev]
+        R = As @ X - X * lam[:args.nev]
+        line["verified_max_rel_residual"] = float((np.linalg.norm(R, axis=0) / np.abs(lam[:args.nev])).max())
+        line["verified_orthonormality_defect"] = float(np.abs(X.T @ X - np.eye(args.nev)).max())
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
