@@ -2,7 +2,7 @@
 // solver (host_eig.hpp): the same template the library instantiates with its device kernels is instantiated here with
 // plain host loops. TEST INFRASTRUCTURE ONLY -- nothing in the library links or calls this.
 //
-// usage: lobpcg_host_test N nev tol generalized(0|1) largest(0|1)
+// usage: lobpcg_host_test N nev tol generalized(0|1) largest(0|1) [verbose] [mgs(0|1)]
 // prints "iterations k", "restarts r", "eval ...", "maxres ...", "orth ..." ; exit code 0 if converged.
 #include <cmath>
 #include <cstdio>
@@ -261,6 +261,7 @@ int main(int argc, char **argv)
   ops.A = &A;
   ops.B = generalized ? &B : nullptr;
   ops.n = A.n;
+  ops.mgs = argc > 7 && std::atoi(argv[7]) != 0;
   ops.m = (nev / 8 + (nev % 8 ? 1 : 0)) * 8;
 
   de::LobpcgParams prm;

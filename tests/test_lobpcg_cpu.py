@@ -120,7 +120,15 @@ def test_lobpcg_orchestration_generalized(N, nev, tol):
 def test_lobpcg_orchestration_restarts_when_basis_is_singular():
     """3 m = 192 columns in a 144-dimensional space: S^T B S is singular every iteration, the Rayleigh-Ritz step falls
     back to [X W] each time and the iteration still converges."""
-    rc, vals, text = run(12, 64, 1e-8, 1, 0)
+    rc, vals, text = run(12, 64, 1e-8, 1, 0, 0, 1)  # Gram-Schmidt orthonormalisation of W
     assert rc == 0, text
     assert int(vals["restarts"]) >= int(vals["iterations"]) - 2
     assert float(vals["maxres"]) <= 1e-8
+
+
+def test_lobpcg_orchestration_passes_rank_deficiency_through():
+    """same problem with the CholQR2 of the device path (its pivot test included): 64 residual columns squeezed into
+    the 80-dimensional complement of X are numerically dependent -- the error code of the orthonormalisation must
+    come back unchanged (DE_ERR_SINGULAR = 5 on the device) instead of NaNs"""
+    rc, vals, text = run(12, 64, 1e-8, 1, 0)
+    assert rc == 1 and int(vals["rc"]) == 5, text
