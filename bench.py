@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--cpu-sample-iters", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-lobpcg", action="store_true", help="skip the StandardLOBPCG leg (the \"lobpcg\" object)")
     return ap.parse_args()
 
 
@@ -444,9 +445,30 @@ def run_b200(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "eigenvalues_head": [float(x) for x in ev[:4]], "step_ms": [round(x, 3) for x in step_ms],
     }
+    if world == 1 and not args.no_lobpcg:
+        line["lobpcg"] = lobpcg_leg(args)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def lobpcg_leg(args):
+    """BASELINE.json configs[1] names StandardLOBPCG; the reference has none, so the headline above
+    stays on the driver the reference arm can run and this object reports the new driver next to it: the nev SMALLEST
+    eigenpairs of the same matrix. Runs tools/lobpcg_probe.py as a child process (after everything else was measured)
+    so that no failure in the new driver can cost the main line."""
+    import subprocess
+
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "lobpcg_probe.py"), "--grid", str(args.grid), "--stencil",
+           args.stencil, "--nev", str(args.nev), "--tol", str(args.tol), "--maxiter", str(args.maxiter)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        for ln in reversed(out.stdout.splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": "rc %d: %s" % (out.returncode, (out.stderr or out.stdout)[-400:])}
+    except Exception as e:  # timeout, missing file
+        return {"error": repr(e)[:400]}
 
 
 def main():
