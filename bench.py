@@ -465,7 +465,7 @@ def lobpcg_leg(args):
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
         for ln in reversed(out.stdout.splitlines()):
             if ln.startswith("{"):
-                return json.loads(ln)
+                return json.loads(ln)  # one degree requested -> one line
         return {"error": "rc %d: %s" % (out.returncode, (out.stderr or out.stdout)[-400:])}
     except Exception as e:  # timeout, missing file
         return {"error": repr(e)[:400]}

@@ -2127,10 +2127,9 @@ namespace
       double *dtheta = dcoef + (size_t)3 * m * m;
       DE_CUDA(ctx, cudaMemcpyAsync(dtheta, theta, sizeof(double) * m, cudaMemcpyHostToDevice, ctx->stream));
       const long long pairs = n * m / 2;
-      const int grid = (int)std::max<long long>(1, std::min<long long>((pairs + 255) / 256, (long long)ctx->sm_count * 8));
       {
         ProfScope prof(ctx, DE_PROF_MISC);
-        de::residual_kernel<<<grid, 256, 0, ctx->stream>>>(pairs, m, AX, BX, dtheta, W);
+        de::residual_kernel<<<elementwise_grid(pairs), 256, 0, ctx->stream>>>(pairs, m, AX, BX, dtheta, W);
       }
       DE_LAUNCH_CHECK(ctx);
       DE_TRY(diag_dot_device(ctx, n, m, W, W, ctx->dDP()));
@@ -2142,6 +2141,45 @@ namespace
         return DE_OK;
       // in place: the apply permutes W into the factor's own work block before anything is written back
       return factor_apply_device(ctx, T, W, W, m);
+    }
+    int elementwise_grid(long long pairs) const
+    {
+      return (int)std::max<long long>(1, std::min<long long>((pairs + 255) / 256, (long long)ctx->sm_count * 8));
+    }
+    /** Gershgorin bound over all ranks' rows. The all-reduce of this library sums, so every rank deposits its local
+     *  maximum in its own slot of a zeroed vector and the maximum is taken on the host. */
+    int spectral_bound(double *b)
+    {
+      const int nr = std::max(1, ctx->nranks);
+      double *slots = ctx->dDP(); // nr <= 64 doubles of scratch
+      DE_CUDA(ctx, cudaMemsetAsync(slots, 0, sizeof(double) * nr, ctx->stream));
+      {
+        ProfScope prof(ctx, DE_PROF_MISC);
+        de::gershgorin_kernel<<<elementwise_grid(A->n), 256, 0, ctx->stream>>>(
+            A->n, A->rowptr, A->val, reinterpret_cast<unsigned long long *>(slots + ctx->rank));
+      }
+      DE_LAUNCH_CHECK(ctx);
+      DE_TRY(allreduce_sum(ctx, slots, nr));
+      std::vector<double> h(nr, 0.0);
+      DE_TRY(fetch_small(ctx, slots, h.data(), nr));
+      *b = *std::max_element(h.begin(), h.end());
+      return DE_OK;
+    }
+    int cheb_start(Blk Z, Blk Zold, Blk R, double s)
+    {
+      const long long pairs = n * m / 2;
+      ProfScope prof(ctx, DE_PROF_MISC);
+      de::cheb_start_kernel<<<elementwise_grid(pairs), 256, 0, ctx->stream>>>(pairs, s, R, Z, Zold);
+      DE_LAUNCH_CHECK(ctx);
+      return DE_OK;
+    }
+    int cheb_step(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta)
+    {
+      const long long pairs = n * m / 2;
+      ProfScope prof(ctx, DE_PROF_MISC);
+      de::cheb_step_kernel<<<elementwise_grid(pairs), 256, 0, ctx->stream>>>(pairs, alpha, beta, Z, R, AZ, Zold);
+      DE_LAUNCH_CHECK(ctx);
+      return DE_OK;
     }
     int project(Blk W, Blk X, Blk BX)
     {
@@ -2171,8 +2209,9 @@ namespace
   };
 
   /** LOBPCG on the device block X (n x m, start block on entry, Ritz vectors on return) */
-  int lobpcg_device(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *T, bool largest, double tol,
-                    int maxiter, int nev, int m, double *X, de::LobpcgResult &res, int verbose)
+  int lobpcg_device(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *T, bool largest,
+                    int cheb_degree, double tol, int maxiter, int nev, int m, double *X, de::LobpcgResult &res,
+                    int verbose)
   {
     LobpcgDeviceOps ops;
     ops.ctx = ctx;
@@ -2181,6 +2220,7 @@ namespace
     ops.T = T;
     ops.n = A->n;
     ops.m = m;
+    DE_TRY(reset_status(ctx));
     DE_TRY(ops.init());
     de::LobpcgParams prm;
     prm.m = m;
@@ -2190,6 +2230,7 @@ namespace
     prm.verbose = verbose;
     prm.has_B = B != nullptr;
     prm.largest = largest;
+    prm.cheb_degree = (T || largest) ? 0 : std::max(0, cheb_degree); // a factored preconditioner takes precedence
     prm.name = B ? "GeneralizedLOBPCG" : "StandardLOBPCG";
     const int rc = de::lobpcg_run(ops, prm, X, res);
     if (rc == de::kLobpcgRitzFailed)
@@ -2230,7 +2271,7 @@ namespace
     DE_TRY(upload_panel8_device(ctx, n, m, start_panel8, X));
     de::LobpcgResult res;
     const auto t0 = std::chrono::steady_clock::now();
-    DE_TRY(lobpcg_device(ctx, A, B, T, false, tol, maxiter, nev, m, X, res, verbose));
+    DE_TRY(lobpcg_device(ctx, A, B, T, false, DE_LOBPCG_DEFAULT_CHEB_DEGREE, tol, maxiter, nev, m, X, res, verbose));
     if (iterations)
       *iterations = res.iterations;
     if (verbose > 0) // one summary line in the style of eigensolver.hh:345-350
@@ -3656,8 +3697,8 @@ extern "C"
                          iterations);
   }
 
-  int de_lobpcg_mv(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *T, int largest, double tol,
-                   int maxiter, int nev, de_mv *Q, double *eval_m, double *resnorm_m, int verbose, int *iterations,
+  int de_lobpcg_mv(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *T, int largest,
+                   int cheb_degree, double tol, int maxiter, int nev, de_mv *Q, double *eval_m, double *resnorm_m, int verbose, int *iterations,
                    int *restarts, int *converged)
   {
     if (!ctx || !A || !Q || !eval_m)
@@ -3667,7 +3708,7 @@ extern "C"
     DE_TRY(lobpcg_check_args(ctx, "de_lobpcg_mv", A, B, T, nev, Q->m));
     DE_TRY(bind_device(ctx));
     de::LobpcgResult res;
-    DE_TRY(lobpcg_device(ctx, A, B, T, largest != 0, tol, maxiter, nev, Q->m, Q->d, res, verbose));
+    DE_TRY(lobpcg_device(ctx, A, B, T, largest != 0, cheb_degree, tol, maxiter, nev, Q->m, Q->d, res, verbose));
     for (int j = 0; j < Q->m; ++j)
     {
       eval_m[j] = res.theta[j];

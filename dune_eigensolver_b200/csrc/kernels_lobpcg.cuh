@@ -1,6 +1,8 @@
 // Kernels of the LOBPCG drivers (lobpcg_core.hpp) that the subspace-iteration path did not need:
 //   lincomb_kernel   X <- X Cx + W Cw + P Cp  and  P <- W Cw + P Cp  in ONE pass over the three blocks
 //   residual_kernel  W = A X - B X diag(theta)
+//   cheb_start_kernel / cheb_step_kernel / gershgorin_kernel   the Chebyshev polynomial preconditioner (three-term
+//                    recurrence between two SpMMs: 40*n*m bytes per step, pure streaming) and its spectral bound
 // Everything else of an LOBPCG iteration (SpMM, Gram, CholQR2, projection) reuses the kernels of the reference path.
 // No reference counterpart: normallytangent/dune-eigensolver has no LOBPCG; the closest relatives are
 // its block update V <- V U (kernels_cpp.hh:293-305) and projection Q_j -= Q_k S (:335-348).
@@ -137,6 +139,56 @@ namespace de
       const double t0 = __ldg(theta + c), t1 = __ldg(theta + c + 1);
       st2(W + 2 * e, make_double2(fma(-t0, b.x, a.x), fma(-t1, b.y, a.y)));
     }
+  }
+
+  /** Z = s R ; Zold = 0  (first Chebyshev iterate z_1 = r / theta, z_0 = 0) */
+  __global__ void __launch_bounds__(256)
+      cheb_start_kernel(long long pairs, double s, const double *__restrict__ R, double *__restrict__ Z,
+                        double *__restrict__ Zold)
+  {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < pairs; e += stride)
+    {
+      const double2 r = ld2(R + 2 * e);
+      st2(Z + 2 * e, make_double2(s * r.x, s * r.y));
+      st2(Zold + 2 * e, make_double2(0.0, 0.0));
+    }
+  }
+
+  /** Zold <- Z + alpha (Z - Zold) + beta (R - AZ): the next Chebyshev iterate overwrites the one before the current */
+  __global__ void __launch_bounds__(256)
+      cheb_step_kernel(long long pairs, double alpha, double beta, const double *__restrict__ Z,
+                       const double *__restrict__ R, const double *__restrict__ AZ, double *__restrict__ Zold)
+  {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < pairs; e += stride)
+    {
+      const double2 z = ld2(Z + 2 * e), zo = ld2(Zold + 2 * e), r = ld2(R + 2 * e), a = ld2(AZ + 2 * e);
+      st2(Zold + 2 * e, make_double2(z.x + alpha * (z.x - zo.x) + beta * (r.x - a.x),
+                                     z.y + alpha * (z.y - zo.y) + beta * (r.y - a.y)));
+    }
+  }
+
+  /** out[0] = max(out[0], max_i sum_k |a_ik|) over this rank's rows: Gershgorin bound of the spectrum of a symmetric
+   *  matrix. Non-negative doubles compare like their bit patterns, so the maximum is an integer atomicMax. */
+  __global__ void __launch_bounds__(256)
+      gershgorin_kernel(long long n, const int *__restrict__ rowptr, const double *__restrict__ val,
+                        unsigned long long *out)
+  {
+    double best = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+      double sum = 0.0;
+      for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
+        sum += fabs(val[k]);
+      best = fmax(best, sum);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best > 0.0)
+      atomicMax(out, (unsigned long long)__double_as_longlong(best));
   }
 
 } // namespace de

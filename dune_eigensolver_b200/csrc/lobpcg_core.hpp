@@ -27,6 +27,10 @@
 //   int apply_B(Blk Y, Blk X);                         Y = B X (only called for a generalized problem)
 //   int residual(Blk W, Blk AX, Blk BX, const double *theta, double *norm2);   W = AX - BX diag(theta), column norms^2
 //   int precondition(Blk W);                           W <- T^-1 W (no-op without a preconditioner)
+//   int spectral_bound(double *b);                     an upper bound of the spectrum of A (Gershgorin); Chebyshev only
+//   int cheb_start(Blk Z, Blk Zold, Blk R, double s);  Z = s R ; Zold = 0
+//   int cheb_step(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta);
+//                                                      Zold <- Z + alpha (Z - Zold) + beta (R - AZ)   (the next iterate)
 //   int project(Blk W, Blk X, Blk BX);                 W <- W - X (BX^T W)
 //   int grams(int count, const Blk *L, const Blk *R, const char *sym, double *out);   out[i] = L_i^T R_i (m x m row-major)
 //   int rotate(Blk X, const double *C);                X <- X C (m x m row-major)
@@ -55,6 +59,8 @@ namespace de
     int verbose = 0;
     bool has_B = false;      // generalized problem
     bool largest = false;    // largest instead of smallest eigenvalues
+    int cheb_degree = 0;     // > 0: Chebyshev polynomial preconditioner W <- p(A) W with this many applications of A
+    double cheb_ratio = 0.0; // p approximates A^-1 on [lambda_bound / cheb_ratio, lambda_bound]; 0: chosen from the degree
     const char *name = "StandardLOBPCG";
   };
 
@@ -117,6 +123,31 @@ namespace de
       DE_LOBPCG_TRY(ops.alloc(&BP));
     }
 
+    // Chebyshev polynomial preconditioner (cheb_degree applications of A per iteration, no factorisation): the
+    // classical Chebyshev iteration for A z = r on [lo, hi] started from z = 0, hi a Gershgorin bound of the spectrum.
+    // Its residual polynomial 1 - lambda p(lambda) = T_k((theta - lambda)/delta) / T_k(theta/delta) lies in (0, 1) for
+    // lambda in (0, lo) and in [-eps_k, eps_k] on [lo, hi], so p(A) is symmetric positive definite on the whole
+    // spectrum -- a valid LOBPCG preconditioner -- and the part of the spectrum above lo is compressed to 1 +- eps_k.
+    const bool cheb = prm.cheb_degree > 0 && !prm.largest;
+    Blk CD = X, CZ = X, CAD = X;
+    double cheb_theta = 0.0, cheb_delta = 0.0;
+    if (cheb)
+    {
+      DE_LOBPCG_TRY(ops.alloc(&CD));
+      DE_LOBPCG_TRY(ops.alloc(&CZ));
+      DE_LOBPCG_TRY(ops.alloc(&CAD));
+      double hi = 0.0;
+      DE_LOBPCG_TRY(ops.spectral_bound(&hi));
+      if (!(hi > 0.0))
+        return kLobpcgRitzFailed;
+      // the interval a degree-k polynomial damps to ~0.1: T_k(sigma) >= 10 needs about k >= 1.5 sqrt(hi/lo)
+      const double ratio = prm.cheb_ratio > 1.0 ? prm.cheb_ratio
+                                                : std::max(4.0, (prm.cheb_degree + 1) * (prm.cheb_degree + 1) / 2.25);
+      const double lo = hi / ratio;
+      cheb_theta = 0.5 * (hi + lo);
+      cheb_delta = 0.5 * (hi - lo);
+    }
+
     res.theta.assign(m, 0.0);
     res.resnorm.assign(m, 0.0);
     res.iterations = 0;
@@ -166,6 +197,24 @@ namespace de
         break;
 
       DE_LOBPCG_TRY(ops.precondition(W));
+      if (cheb)
+      {
+        // three-term form: z_1 = r / theta, z_{i+1} = z_i + rho_{i+1} rho_i (z_i - z_{i-1}) + (2 rho_{i+1} / delta) (r - A z_i)
+        const double sigma1 = cheb_theta / cheb_delta;
+        double rho = 1.0 / sigma1;
+        DE_LOBPCG_TRY(ops.cheb_start(CZ, CD, W, 1.0 / cheb_theta));
+        for (int i = 0; i < prm.cheb_degree; ++i)
+        {
+          DE_LOBPCG_TRY(ops.apply_A(CAD, CZ));
+          const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+          DE_LOBPCG_TRY(ops.cheb_step(CD, CZ, W, CAD, rho_new * rho, 2.0 * rho_new / cheb_delta));
+          std::swap(CD, CZ); // CZ = newest iterate
+          rho = rho_new;
+        }
+        std::swap(W, CZ); // W = p(A) r ; the residual block becomes scratch
+        if (!prm.has_B)
+          BW = W;
+      }
       DE_LOBPCG_TRY(ops.project(W, X, BX));
       DE_LOBPCG_TRY(ops.orthonormalize(W, BW));
       DE_LOBPCG_TRY(ops.apply_A(AW, W));

@@ -550,15 +550,16 @@ def GeneralizedLOBPCG(ctx, A, B, tol, maxiter, nev, verbose=0, seed=123, start=N
     return Result(ev, V, it.value)
 
 
-def lobpcg_mv(ctx, dA, Q, tol, maxiter, nev=None, dB=None, dT=None, largest=False, verbose=0):
+def lobpcg_mv(ctx, dA, Q, tol, maxiter, nev=None, dB=None, dT=None, largest=False, verbose=0, cheb_degree=0):
     """Device-resident LOBPCG with all options (de_lobpcg_mv): Q holds the start block on entry and the m Ritz vectors
-    on return; dB: mass matrix or None; dT: a Factor used as preconditioner or None.
+    on return; dB: mass matrix or None; dT: a Factor used as preconditioner or None; cheb_degree > 0: Chebyshev
+    polynomial preconditioner with that many applications of A per iteration (the drivers' default is 8).
     Returns (eval[m], resnorm[m], iterations, restarts, converged)."""
     nev = Q.m if nev is None else nev
     ev, rn = np.zeros(Q.m), np.zeros(Q.m)
     it, rs, cv = C.c_int(0), C.c_int(0), C.c_int(0)
     check(capi.lib().de_lobpcg_mv(ctx._h, dA._h, dB._h if dB is not None else None, dT._h if dT is not None else None,
-                                  1 if largest else 0, tol, maxiter, nev, Q._h, dptr(ev), dptr(rn), verbose,
+                                  1 if largest else 0, int(cheb_degree), tol, maxiter, nev, Q._h, dptr(ev), dptr(rn), verbose,
                                   C.byref(it), C.byref(rs), C.byref(cv)), ctx._h)
     return ev, rn, it.value, rs.value, bool(cv.value)
 

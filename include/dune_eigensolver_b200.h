@@ -251,12 +251,18 @@ int de_standard_lobpcg(de_context *ctx, const de_matrix *A, double tol, int maxi
                        const double *start_panel8, double *eval, double *evec, int verbose, int *iterations);
 int de_generalized_lobpcg(de_context *ctx, const de_matrix *A, const de_matrix *B, double tol, int maxiter, int nev,
                           const double *start_panel8, double *eval, double *evec, int verbose, int *iterations);
+/* Preconditioner of the two drivers above: a Chebyshev polynomial in A of this degree (that many extra SpMMs per
+ * iteration, no factorisation, works row-partitioned): p(A) ~ A^-1 on the upper part of the spectrum, bounded by the
+ * Gershgorin row sums. Measured on the 100^3 27-point matrix: see DESIGN.md §10. */
+#define DE_LOBPCG_DEFAULT_CHEB_DEGREE 8
 /* device-resident variant with all options: B may be NULL (standard problem); T, if not NULL, is a factorisation used
- * as preconditioner W <- T^-1 W (e.g. of A + shift*B; single GPU only); largest != 0 selects the largest eigenvalues.
+ * as preconditioner W <- T^-1 W (e.g. of A + shift*B; single GPU only) and takes precedence over cheb_degree;
+ * cheb_degree: 0 = unpreconditioned, k > 0 = Chebyshev polynomial preconditioner with k applications of A (smallest
+ * eigenvalues only); largest != 0 selects the largest eigenvalues.
  * Q: start block on entry, all m Ritz vectors on return; eval_m / resnorm_m (may be NULL): m Ritz values and residual
  * norms; restarts / converged may be NULL. Works on a row-partitioned matrix (n = owned rows; reductions all-reduced). */
-int de_lobpcg_mv(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *T, int largest, double tol,
-                 int maxiter, int nev, de_mv *Q, double *eval_m, double *resnorm_m, int verbose, int *iterations,
+int de_lobpcg_mv(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *T, int largest,
+                 int cheb_degree, double tol, int maxiter, int nev, de_mv *Q, double *eval_m, double *resnorm_m, int verbose, int *iterations,
                  int *restarts, int *converged);
 /* Host-only (no GPU): the dense symmetric eigensolvers of the Rayleigh-Ritz step. A = V diag(w) V^T (w ascending,
  * eigenvector j in column j of the row-major V); GA c = w GB c with C^T GB C = I, *min_pivot (may be NULL) = smallest

@@ -2,7 +2,7 @@
 // solver (host_eig.hpp): the same template the library instantiates with its device kernels is instantiated here with
 // plain host loops. TEST INFRASTRUCTURE ONLY -- nothing in the library links or calls this.
 //
-// usage: lobpcg_host_test N nev tol generalized(0|1) largest(0|1) [verbose] [mgs(0|1)]
+// usage: lobpcg_host_test N nev tol generalized(0|1) largest(0|1) [verbose] [mgs(0|1)] [cheb_degree] [cheb_ratio]
 // prints "iterations k", "restarts r", "eval ...", "maxres ...", "orth ..." ; exit code 0 if converged.
 #include <cmath>
 #include <cstdio>
@@ -170,6 +170,7 @@ struct HostOps
   }
   int apply_A(Blk Y, Blk X)
   {
+    ++spmm_count;
     A->apply(X, Y, m);
     return 0;
   }
@@ -192,6 +193,35 @@ struct HostOps
     return 0;
   }
   int precondition(Blk) { return 0; }
+  int spectral_bound(double *b)
+  {
+    double g = 0.0;
+    for (int i = 0; i < n; ++i)
+    {
+      double r = 0.0;
+      for (int k = A->ptr[i]; k < A->ptr[i + 1]; ++k)
+        r += std::abs(A->val[k]);
+      g = std::max(g, r);
+    }
+    *b = g;
+    return 0;
+  }
+  int cheb_start(Blk Z, Blk Zold, Blk R, double s)
+  {
+    for (size_t e = 0; e < (size_t)n * m; ++e)
+    {
+      Z[e] = s * R[e];
+      Zold[e] = 0.0;
+    }
+    return 0;
+  }
+  int cheb_step(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta)
+  {
+    for (size_t e = 0; e < (size_t)n * m; ++e)
+      Zold[e] = Z[e] + alpha * (Z[e] - Zold[e]) + beta * (R[e] - AZ[e]);
+    return 0;
+  }
+  long spmm_count = 0;
   int project(Blk W, Blk X, Blk BX)
   {
     std::vector<double> G((size_t)m * m);
@@ -272,6 +302,8 @@ int main(int argc, char **argv)
   prm.verbose = argc > 6 ? std::atoi(argv[6]) : 0;
   prm.has_B = generalized != 0;
   prm.largest = largest != 0;
+  prm.cheb_degree = argc > 8 ? std::atoi(argv[8]) : 0;
+  prm.cheb_ratio = argc > 9 ? std::atof(argv[9]) : 0.0;
 
   double *X;
   ops.alloc(&X);
@@ -283,7 +315,8 @@ int main(int argc, char **argv)
   de::LobpcgResult res;
   const int rc = de::lobpcg_run(ops, prm, X, res);
   std::printf("rc %d\n", rc);
-  std::printf("iterations %d\nrestarts %d\nconverged %d\n", res.iterations, res.restarts, (int)res.converged);
+  std::printf("iterations %d\nrestarts %d\nconverged %d\nspmm %ld\n", res.iterations, res.restarts, (int)res.converged,
+              ops.spmm_count);
   std::printf("eval");
   for (int j = 0; j < nev; ++j)
     std::printf(" %.15e", res.theta[j]);

@@ -1,5 +1,6 @@
 """Worker for tests/test_multigpu_gpu.py: one process per GPU (torchrun). Row-partitioned SpMM with halo exchange,
-all-reduced Gram / dots, CholQR2 and a complete StandardLargest solve, each compared with the single-process oracle."""
+all-reduced Gram / dots, CholQR2 and a complete StandardLargest solve, each compared with the single-process oracle;
+LOBPCG (new driver) against a dense solve of the global matrix."""
 import os
 import sys
 
@@ -78,6 +79,15 @@ def main():
         evr, Vr, k = orc.standard_largest(Aglob, 0.0, 1e-9, 3000, nev)
         if abs(it - k) > 1 or np.abs(ev - evr).max() > 1e-8 * np.abs(evr).max():
             fails.append(("largest", shape, it, k, float(np.abs(ev - evr).max())))
+        # LOBPCG across ranks (plain and with the Chebyshev polynomial preconditioner): the Rayleigh-Ritz problem is
+        # solved redundantly on every rank from bit-identical all-reduced Gram matrices, so all ranks take the same
+        # decisions; smallest eigenvalues against a dense solve of the global matrix
+        dense = np.linalg.eigvalsh(M.to_scipy(Aglob).toarray())[:m]
+        for deg in (0, 6):
+            Q.upload_rowmajor(np.ascontiguousarray(start[r0:r1]))
+            lam, rn, it2, rs, conv = E.lobpcg_mv(ctx, dA, Q, 1e-9, 2000, nev=m, cheb_degree=deg)
+            if not conv or np.abs(lam - dense).max() > 1e-10 * np.abs(dense).max():
+                fails.append(("lobpcg", deg, shape, it2, bool(conv), float(np.abs(lam - dense).max())))
     t = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(t)
     if rank == 0:

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--tol", type=float, default=2e-3)
     ap.add_argument("--maxiter", type=int, default=4000)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--cheb", default="8", help="degree of the Chebyshev preconditioner (0: none); 8 is the default of "
+                                                "the StandardLOBPCG driver. A comma-separated list prints one line each.")
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--verbose", type=int, default=0)
     args = ap.parse_args()
@@ -45,11 +47,18 @@ def main():
     start = E.start_block(n, m, 123)
     Q = E.MultiVector(ctx, n, m)
 
+    degrees = [int(x) for x in str(args.cheb).split(",")]
+    for deg in degrees:
+        args.cheb = deg
+        probe_one(args, E, ctx, dA, Q, start, A, analytic, n, m)
+
+
+def probe_one(args, E, ctx, dA, Q, start, A, analytic, n, m):
     def solve():
         Q.upload_panels(start)
         ctx.synchronize()
         t0 = time.perf_counter()
-        out = E.lobpcg_mv(ctx, dA, Q, args.tol, args.maxiter, nev=args.nev, verbose=args.verbose)
+        out = E.lobpcg_mv(ctx, dA, Q, args.tol, args.maxiter, nev=args.nev, verbose=args.verbose, cheb_degree=args.cheb)
         ctx.synchronize()
         return time.perf_counter() - t0, out
 
@@ -71,7 +80,7 @@ def main():
         "workload": "3D %s Laplace %d^3 (n=%d), %d smallest eigenpairs, m=%d, relative residual tol=%g, seed=123" %
                     ("Q1 27-point FE stiffness" if args.stencil == "q1" else "7-point FD", args.grid, n, args.nev, m,
                      args.tol),
-        "seconds": float(np.median(times)), "seconds_all": [round(t, 5) for t in times],
+        "chebyshev_degree": args.cheb, "seconds": float(np.median(times)), "seconds_all": [round(t, 5) for t in times],
         "iterations": it, "restarts": restarts, "converged": conv, "ms_per_iteration": 1e3 * float(np.median(times)) / max(it, 1),
         "max_rel_residual": float((rn[:args.nev] / np.abs(lam[:args.nev])).max()),
         "max_rel_eigenvalue_error_vs_analytic": float((np.abs(lam[:args.nev] - analytic[:args.nev]) / analytic[:args.nev]).max()),
