@@ -61,7 +61,10 @@ def parse():
     ap.add_argument("--cpu-sample-iters", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-lobpcg", action="store_true", help="skip the StandardLOBPCG leg (the \"lobpcg\" object)")
+    ap.add_argument("--no-lobpcg", action="store_true", help="skip the LOBPCG legs (the \"lobpcg\" objects)")
+    ap.add_argument("--lobpcg-pencil-grid", type=int, default=128,
+                    help="grid of the GeneralizedLOBPCG leg (stiffness + mass pencil, 64 eigenpairs: BASELINE.json "
+                         "configs[2]); 0 skips it")
     return ap.parse_args()
 
 
@@ -446,23 +449,28 @@ def run_b200(args):
         "eigenvalues_head": [float(x) for x in ev[:4]], "step_ms": [round(x, 3) for x in step_ms],
     }
     if world == 1 and not args.no_lobpcg:
-        line["lobpcg"] = lobpcg_leg(args)
+        line["lobpcg"] = lobpcg_leg(["--grid", str(args.grid), "--stencil", args.stencil, "--nev", str(args.nev), "--tol",
+                                     str(args.tol), "--maxiter", str(args.maxiter)], 150)
+        if args.lobpcg_pencil_grid > 0:
+            # configs[2]: A x = lambda B x, Q1 stiffness + mass, 128^3, 64 eigenpairs -- by GeneralizedLOBPCG, i.e.
+            # without the 3D factorisation the reference's GeneralizedInverse would need (UMFPACK, absent here)
+            line["lobpcg_pencil"] = lobpcg_leg(["--grid", str(args.lobpcg_pencil_grid), "--mass", "--nev", "64", "--tol",
+                                                str(args.tol), "--maxiter", "400", "--steps", "1"], 200)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def lobpcg_leg(args):
+def lobpcg_leg(probe_args, timeout_s):
     """BASELINE.json configs[1] names StandardLOBPCG; the reference has none, so the headline above
     stays on the driver the reference arm can run and this object reports the new driver next to it: the nev SMALLEST
     eigenpairs of the same matrix. Runs tools/lobpcg_probe.py as a child process (after everything else was measured)
     so that no failure in the new driver can cost the main line."""
     import subprocess
 
-    cmd = [sys.executable, os.path.join(ROOT, "tools", "lobpcg_probe.py"), "--grid", str(args.grid), "--stencil",
-           args.stencil, "--nev", str(args.nev), "--tol", str(args.tol), "--maxiter", str(args.maxiter)]
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "lobpcg_probe.py")] + list(probe_args)
     try:
-        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
         for ln in reversed(out.stdout.splitlines()):
             if ln.startswith("{"):
                 return json.loads(ln)  # one degree requested -> one line

@@ -1,7 +1,7 @@
 """StandardLOBPCG on one B200: time-to-nev-smallest-eigenpairs of a 3D Laplacian (BASELINE.json configs[1]:
 "3D Q1 Laplace 100^3, 32 eigenpairs via StandardLOBPCG on 1 B200"), printed as ONE JSON line.
 
-    python tools/lobpcg_probe.py [--grid 100] [--stencil q1|fd] [--nev 32] [--tol 2e-3] [--steps 3] [--verify]
+    python tools/lobpcg_probe.py [--grid 100] [--stencil q1|fd] [--mass] [--nev 32] [--tol 2e-3] [--steps 3] [--verify]
 
 The reference has no LOBPCG and its shift-invert drivers cannot reach the smallest eigenpairs of this matrix without a
 3D factorisation, so there is no reference arm for this number; what pins the result is the analytic spectrum of the
@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--cheb", default="8", help="degree of the Chebyshev preconditioner (0: none); 8 is the default of "
                                                 "the StandardLOBPCG driver. A comma-separated list prints one line each.")
+    ap.add_argument("--mass", action="store_true", help="generalized problem A x = lambda B x with the consistent Q1 mass "
+                                                        "matrix (GeneralizedLOBPCG; BASELINE.json configs[2])")
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--verbose", type=int, default=0)
     args = ap.parse_args()
@@ -40,25 +42,33 @@ def main():
     shape = (args.grid,) * 3
     n = args.grid ** 3
     m = E.padded_cols(args.nev)
+    if args.mass:
+        args.stencil = "q1"
     A = M.q1_stiffness(shape) if args.stencil == "q1" else M.laplacian_fd(shape)
-    analytic = (M.eigenvalues_q1_stiffness(shape) if args.stencil == "q1" else M.eigenvalues_laplacian_fd(shape))[:m]
+    B = M.q1_mass(shape) if args.mass else None
+    if args.mass:
+        analytic = M.eigenvalues_q1_pencil(shape)[:m]
+    else:
+        analytic = (M.eigenvalues_q1_stiffness(shape) if args.stencil == "q1" else M.eigenvalues_laplacian_fd(shape))[:m]
     ctx = E.Context(0)
     dA = E.Matrix(ctx, A)
+    dB = E.Matrix(ctx, B) if B is not None else None
     start = E.start_block(n, m, 123)
     Q = E.MultiVector(ctx, n, m)
 
     degrees = [int(x) for x in str(args.cheb).split(",")]
     for deg in degrees:
         args.cheb = deg
-        probe_one(args, E, ctx, dA, Q, start, A, analytic, n, m)
+        probe_one(args, E, ctx, dA, dB, Q, start, A, B, analytic, n, m)
 
 
-def probe_one(args, E, ctx, dA, Q, start, A, analytic, n, m):
+def probe_one(args, E, ctx, dA, dB, Q, start, A, B, analytic, n, m):
     def solve():
         Q.upload_panels(start)
         ctx.synchronize()
         t0 = time.perf_counter()
-        out = E.lobpcg_mv(ctx, dA, Q, args.tol, args.maxiter, nev=args.nev, verbose=args.verbose, cheb_degree=args.cheb)
+        out = E.lobpcg_mv(ctx, dA, Q, args.tol, args.maxiter, nev=args.nev, dB=dB, verbose=args.verbose,
+                          cheb_degree=args.cheb)
         ctx.synchronize()
         return time.perf_counter() - t0, out
 
@@ -76,10 +86,11 @@ def probe_one(args, E, ctx, dA, Q, start, A, analytic, n, m):
     ctx.set_profiling(False)
     kernel_ms = sum(v[0] for v in prof.values())
     line = {
-        "driver": "StandardLOBPCG (de_lobpcg_mv, blocks resident in HBM)",
-        "workload": "3D %s Laplace %d^3 (n=%d), %d smallest eigenpairs, m=%d, relative residual tol=%g, seed=123" %
-                    ("Q1 27-point FE stiffness" if args.stencil == "q1" else "7-point FD", args.grid, n, args.nev, m,
-                     args.tol),
+        "driver": "%s (de_lobpcg_mv, blocks resident in HBM)" % ("GeneralizedLOBPCG" if args.mass else "StandardLOBPCG"),
+        "workload": "3D %s %d^3 (n=%d), %d smallest eigenpairs, m=%d, relative residual tol=%g, seed=123" %
+                    ("Q1 stiffness + consistent mass pencil (27-point)" if args.mass else
+                     "Q1 27-point FE stiffness Laplace" if args.stencil == "q1" else "7-point FD Laplace", args.grid, n,
+                     args.nev, m, args.tol),
         "chebyshev_degree": args.cheb, "seconds": float(np.median(times)), "seconds_all": [round(t, 5) for t in times],
         "iterations": it, "restarts": restarts, "converged": conv, "ms_per_iteration": 1e3 * float(np.median(times)) / max(it, 1),
         "max_rel_residual": float((rn[:args.nev] / np.abs(lam[:args.nev])).max()),
@@ -96,9 +107,10 @@ def probe_one(args, E, ctx, dA, Q, start, A, analytic, n, m):
 
         As = sp.csr_matrix((A[2], A[1], A[0]), shape=(n, n))
         X = Q.download_rowmajor()[:, :args.nev]
-        R = As @ X - X * lam[:args.nev]
+        BX = X if B is None else sp.csr_matrix((B[2], B[1], B[0]), shape=(n, n)) @ X
+        R = As @ X - BX * lam[:args.nev]
         line["verified_max_rel_residual"] = float((np.linalg.norm(R, axis=0) / np.abs(lam[:args.nev])).max())
-        line["verified_orthonormality_defect"] = float(np.abs(X.T @ X - np.eye(args.nev)).max())
+        line["verified_orthonormality_defect"] = float(np.abs(X.T @ BX - np.eye(args.nev)).max())
     print(json.dumps(line))
 
 
