@@ -34,11 +34,12 @@ static Matrix laplacian(int N, const char *kind, int overlap)
         val.push_back(v);
       };
       const double diag = !std::strcmp(kind, "neumann") ? (double)nb : 4.0;
-      if (y > 0) put(x, y - 1, -1.0);
-      if (x > 0) put(x - 1, y, -1.0);
+      const double off = !std::strcmp(kind, "mass") ? 0.5 : -1.0; // "mass": an SPD matrix on the same pattern
+      if (y > 0) put(x, y - 1, off);
+      if (x > 0) put(x - 1, y, off);
       put(x, y, diag);
-      if (x < N - 1) put(x + 1, y, -1.0);
-      if (y < N - 1) put(x, y + 1, -1.0);
+      if (x < N - 1) put(x + 1, y, off);
+      if (y < N - 1) put(x, y + 1, off);
       ptr.push_back((long)col.size());
     }
   return Matrix((std::size_t)N * N, (std::size_t)N * N, ptr.data(), col.data(), val.data());
@@ -88,6 +89,15 @@ int main(int argc, char **argv)
     {
       Matrix A = laplacian(N, "dirichlet", 0);
       StandardLOBPCG(A, tol, 4000, nev, eval, evec, 0, 123);
+    }
+    else if (mode == "globpcg")
+    {
+      Matrix A = laplacian(N, "dirichlet", 0), B = laplacian(N, "mass", 0);
+      std::vector<double> ev;
+      std::vector<std::vector<double>> V;
+      GeneralizedLOBPCG(A, B, tol, 4000, nev, ev, V, 0, 123); // resizes its outputs like GeneralizedInverse
+      eval = ev;
+      evec = V;
     }
     else if (mode == "kernels")
     {
