@@ -444,7 +444,11 @@ def run_b200(args):
                    "multi_gpu_data_path": ("NVLink peer memory: halo rows stored into the neighbours' windows, one-shot "
                                            "peer all-reduce of the Gram matrices / Rayleigh quotients" if ctx.peer_ready()
                                            else "NCCL send/recv + all-reduce") if world > 1 else None,
-                   "spmm_format": dA.spmm_info()["format"]},
+                   "spmm_format": dA.spmm_info()["format"],
+                   "driver_choice": "headline = StandardLargest, the driver of this path that the reference implements "
+                                    "(its CPU run is the reference arm); BASELINE.json configs[1] names StandardLOBPCG, "
+                                    "which the reference lacks (SURVEY.md §0): that driver's time on the same matrix is "
+                                    "the 'lobpcg' object of this line, configs[2]'s pencil the 'lobpcg_pencil' object"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "eigenvalues_head": [float(x) for x in ev[:4]], "step_ms": [round(x, 3) for x in step_ms],
     }
