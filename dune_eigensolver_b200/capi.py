@@ -79,6 +79,7 @@ SIGNATURES = {
     "de_standard_lobpcg": [_vp, _vp, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip],
     "de_generalized_lobpcg": [_vp, _vp, _vp, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip],
     "de_lobpcg_mv": [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _vp, _dp, _dp, C.c_int, _ip, _ip, _ip],
+    "de_block_lincomb": [_vp, _vp, C.c_int, _vpp, _dp],
     "de_host_sym_eig": [C.c_int, _dp, _dp, _dp],
     "de_host_sym_gen_eig": [C.c_int, _dp, _dp, _dp, _dp, _dp],
     "de_start_block": [C.c_int64, C.c_int, C.c_uint, _dp],

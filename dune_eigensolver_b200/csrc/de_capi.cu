@@ -3724,6 +3724,31 @@ extern "C"
     return DE_OK;
   }
 
+  int de_block_lincomb(de_mv *out, de_mv *out2, int ns, const de_mv *const *S, const double *C_host)
+  {
+    if (!out || !S || !C_host || ns < 1 || ns > 3)
+      return set_error(nullptr, DE_ERR_INVALID, "de_block_lincomb: bad arguments");
+    de_context *ctx = out->ctx;
+    for (int s = 0; s < ns; ++s)
+      if (!S[s] || S[s]->n != out->n || S[s]->m != out->m)
+        return set_error(ctx, DE_ERR_INVALID, "de_block_lincomb: blocks must have the same shape");
+    if (out2 && (out2->n != out->n || out2->m != out->m || out2->d == S[0]->d || out2->d == out->d))
+      return set_error(ctx, DE_ERR_INVALID, "de_block_lincomb: out2 must have the same shape and alias neither out nor S[0]");
+    for (int s = 1; s < ns; ++s)
+      if (out->d == S[s]->d)
+        return set_error(ctx, DE_ERR_INVALID, "de_block_lincomb: out may alias S[0] only");
+    DE_TRY(bind_device(ctx));
+    const int m = out->m;
+    ScopedBlocks tmp;
+    double *dC = nullptr;
+    DE_TRY(tmp.alloc(ctx, &dC, (size_t)3 * m * m));
+    DE_CUDA(ctx, cudaMemcpyAsync(dC, C_host, sizeof(double) * (size_t)ns * m * m, cudaMemcpyHostToDevice, ctx->stream));
+    const double *src[3] = {S[0]->d, ns > 1 ? S[1]->d : nullptr, ns > 2 ? S[2]->d : nullptr};
+    DE_TRY(lincomb_device(ctx, m, out->n, ns, src, dC, out->d, (out2 && ns > 1) ? out2->d : nullptr));
+    DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // dC returns to the allocator, C_host to the caller
+    return DE_OK;
+  }
+
   int de_host_sym_eig(int n, const double *A, double *w, double *V)
   {
     if (n < 0 || (n > 0 && (!A || !w || !V)))

@@ -564,6 +564,15 @@ def lobpcg_mv(ctx, dA, Q, tol, maxiter, nev=None, dB=None, dT=None, largest=Fals
     return ev, rn, it.value, rs.value, bool(cv.value)
 
 
+def block_lincomb(out, sources, coeffs, out2=None):
+    """out = sum_s sources[s] @ coeffs[s]; out2 (optional) = the same sum without sources[0] -- one fused pass
+    (de_block_lincomb). out may be sources[0]; out2 may be sources[1] or sources[2]."""
+    ns = len(sources)
+    Cm = f64(np.stack([f64(c) for c in coeffs]))
+    arr = (C.c_void_p * ns)(*[s._h for s in sources])
+    check(capi.lib().de_block_lincomb(out._h, out2._h if out2 is not None else None, ns, arr, dptr(Cm)), out.ctx._h)
+
+
 def host_sym_eig(A):
     """(w ascending, V with eigenvector j in column j) of a dense symmetric matrix -- the host Rayleigh-Ritz solver."""
     A = f64(A)

@@ -264,6 +264,12 @@ int de_generalized_lobpcg(de_context *ctx, const de_matrix *A, const de_matrix *
 int de_lobpcg_mv(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *T, int largest,
                  int cheb_degree, double tol, int maxiter, int nev, de_mv *Q, double *eval_m, double *resnorm_m, int verbose, int *iterations,
                  int *restarts, int *converged);
+/* The fused block combination of an LOBPCG iteration as a kernel of its own (csrc/kernels_lobpcg.cuh):
+ * out = sum_{s < ns} S[s] C_s and, if out2 is not NULL and ns > 1, out2 = sum_{1 <= s < ns} S[s] C_s, with ns <= 3
+ * blocks of one shape and C_host = ns row-major m x m matrices one after the other. Every source is read once.
+ * out may alias S[0]; out2 may alias S[1] or S[2]. Generalises the reference's V <- V U and Q_j -= Q_k S
+ * (kernels_cpp.hh:293-305, :335-348) to several sources and two results. */
+int de_block_lincomb(de_mv *out, de_mv *out2, int ns, const de_mv *const *S, const double *C_host);
 /* Host-only (no GPU): the dense symmetric eigensolvers of the Rayleigh-Ritz step. A = V diag(w) V^T (w ascending,
  * eigenvector j in column j of the row-major V); GA c = w GB c with C^T GB C = I, *min_pivot (may be NULL) = smallest
  * Cholesky pivot of the unit-diagonal-scaled GB. DE_ERR_SINGULAR if GB is not positive definite. */

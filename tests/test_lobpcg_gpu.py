@@ -138,6 +138,35 @@ def test_lobpcg_mv_chebyshev_preconditioner(ctx):
         h.close()
 
 
+@pytest.mark.parametrize("m", [8, 16, 24, 32, 40, 48, 56, 64])
+def test_block_lincomb_kernel(ctx, m):
+    """the fused combination kernel of the iteration (X <- X Cx + W Cw + P Cp, P <- W Cw + P Cp) on its own, every
+    width, a row count that is not a multiple of the tile, 3 / 2 / 1 sources, and the driver's aliasing"""
+    n = 1000 + 37
+    rng = np.random.default_rng(m)
+    S = [rng.standard_normal((n, m)) for _ in range(3)]
+    Cs = [rng.standard_normal((m, m)) for _ in range(3)]
+    d = [E.MultiVector.from_array(ctx, x) for x in S]
+    out, out2 = E.MultiVector(ctx, n, m), E.MultiVector(ctx, n, m)
+    ref2 = S[1] @ Cs[1] + S[2] @ Cs[2]
+    ref = S[0] @ Cs[0] + ref2
+    E.block_lincomb(out, d, Cs, out2)
+    assert np.abs(out.download() - ref).max() <= 1e-11 and np.abs(out2.download() - ref2).max() <= 1e-11
+    E.block_lincomb(out, d[:2], Cs[:2], out2)
+    assert np.abs(out.download() - (S[0] @ Cs[0] + S[1] @ Cs[1])).max() <= 1e-11
+    assert np.abs(out2.download() - S[1] @ Cs[1]).max() <= 1e-11
+    E.block_lincomb(out, d[:1], Cs[:1])
+    assert np.abs(out.download() - S[0] @ Cs[0]).max() <= 1e-11
+    E.block_lincomb(d[0], d, Cs, d[2])  # in place, as the driver calls it
+    assert np.abs(d[0].download() - ref).max() <= 1e-11 and np.abs(d[2].download() - ref2).max() <= 1e-11
+    assert np.abs(d[1].download() - S[1]).max() == 0.0
+    with pytest.raises(E.DeError) as e:
+        E.block_lincomb(d[1], d, Cs)  # out may alias the first source only
+    assert e.value.status == E.capi.DE_ERR_INVALID
+    for h in d + [out, out2]:
+        h.close()
+
+
 def test_lobpcg_argument_errors(ctx):
     A = M.laplacian_dirichlet_2d(12)
     with pytest.raises(E.DeError) as e:
