@@ -54,7 +54,11 @@ def main():
             "gram_xy": 16.0 * n * m,
             "update": 16.0 * n * m,
             "ortho": 24.0 * n * m,  # single-pass CholQR minimum; extra passes count against it
+            "lincomb3": 40.0 * n * m,  # LOBPCG: 3 sources read once, 2 results written (kernels_lobpcg.cuh)
         }
+        Z = E.MultiVector(ctx, n, m)
+        Z.copy_from(X)
+        C3 = [rng.standard_normal((m, m)) / m for _ in range(3)]
         calls = {
             "spmm": (lambda: E.matmul_sparse_tallskinny_blocked(Y, dA, X), "spmm"),
             "spmm+dot": (lambda: E.matmul_sparse_tallskinny_with_dots(Y, dA, X), "spmm"),
@@ -63,6 +67,7 @@ def main():
             "gram_xy": (lambda: E.dot_products_all_blocked(X, Y), "gram"),
             "update": (lambda: E.block_update(Y, R), "update"),
             "ortho": (lambda: E.orthonormalize_blocked(Y), None),
+            "lincomb3": (lambda: E.block_lincomb(Z, [Z, X, Y], C3, Y), "update"),
         }
         E.matmul_sparse_tallskinny_blocked(Y, dA, X)
         for name, (fn, cat) in calls.items():
@@ -83,6 +88,7 @@ def main():
             print("%4d %-10s %10.4f %10.1f %8.3f" % rows[-1])
         X.close()
         Y.close()
+        Z.close()
     if args.csv:
         with open(args.csv, "w") as f:
             f.write("grid,stencil,n,nnz,m,kernel,avg_ms,GBps,frac_of_measured_hbm_peak\n")
