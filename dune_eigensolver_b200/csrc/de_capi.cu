@@ -2146,38 +2146,49 @@ namespace
     {
       return (int)std::max<long long>(1, std::min<long long>((pairs + 255) / 256, (long long)ctx->sm_count * 8));
     }
-    /** Gershgorin bound over all ranks' rows. The all-reduce of this library sums, so every rank deposits its local
-     *  maximum in its own slot of a zeroed vector and the maximum is taken on the host. */
+    /** Jacobi scale dinv = 1 / diag(A) and the Gershgorin bound of D^-1 A over all ranks' rows. The all-reduce of this
+     *  library sums, so every rank deposits its local maximum in its own slot of a zeroed vector and the maximum is
+     *  taken on the host. */
+    double *ddinv = nullptr;
     int spectral_bound(double *b)
     {
       const int nr = std::max(1, ctx->nranks);
       double *slots = ctx->dDP(); // nr <= 64 doubles of scratch
+      DE_TRY(blocks.alloc(ctx, &ddinv, (size_t)std::max<long long>(n, 1)));
       DE_CUDA(ctx, cudaMemsetAsync(slots, 0, sizeof(double) * nr, ctx->stream));
       {
         ProfScope prof(ctx, DE_PROF_MISC);
         de::gershgorin_kernel<<<elementwise_grid(A->n), 256, 0, ctx->stream>>>(
-            A->n, A->rowptr, A->val, reinterpret_cast<unsigned long long *>(slots + ctx->rank));
+            A->n, A->rowptr, A->col, A->val, ddinv, reinterpret_cast<unsigned long long *>(slots + ctx->rank));
       }
       DE_LAUNCH_CHECK(ctx);
       DE_TRY(allreduce_sum(ctx, slots, nr));
       std::vector<double> h(nr, 0.0);
       DE_TRY(fetch_small(ctx, slots, h.data(), nr));
       *b = *std::max_element(h.begin(), h.end());
+      if (!std::isfinite(*b) || !(*b > 0.0))
+        return set_error(ctx, DE_ERR_INVALID,
+                         "LOBPCG: the Chebyshev preconditioner needs a matrix with a positive diagonal (use cheb_degree = 0)");
       return DE_OK;
+    }
+    /** (m/2, 256/(m/2)) thread blocks of the row-wise streaming kernels */
+    dim3 row_block() const { return dim3((unsigned)(m / 2), (unsigned)(256 / (m / 2))); }
+    int row_grid() const
+    {
+      const long long rpb = 256 / (m / 2);
+      return (int)std::max<long long>(1, std::min<long long>((n + rpb - 1) / rpb, (long long)ctx->sm_count * 8));
     }
     int cheb_start(Blk Z, Blk Zold, Blk R, double s)
     {
-      const long long pairs = n * m / 2;
       ProfScope prof(ctx, DE_PROF_MISC);
-      de::cheb_start_kernel<<<elementwise_grid(pairs), 256, 0, ctx->stream>>>(pairs, s, R, Z, Zold);
+      de::cheb_start_kernel<<<row_grid(), row_block(), 0, ctx->stream>>>(n, m / 2, s, ddinv, R, Z, Zold);
       DE_LAUNCH_CHECK(ctx);
       return DE_OK;
     }
     int cheb_step(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta)
     {
-      const long long pairs = n * m / 2;
       ProfScope prof(ctx, DE_PROF_MISC);
-      de::cheb_step_kernel<<<elementwise_grid(pairs), 256, 0, ctx->stream>>>(pairs, alpha, beta, Z, R, AZ, Zold);
+      de::cheb_step_kernel<<<row_grid(), row_block(), 0, ctx->stream>>>(n, m / 2, alpha, beta, ddinv, Z, R, AZ, Zold);
       DE_LAUNCH_CHECK(ctx);
       return DE_OK;
     }

@@ -1,8 +1,9 @@
 // Kernels of the LOBPCG drivers (lobpcg_core.hpp) that the subspace-iteration path did not need:
 //   lincomb_kernel   X <- X Cx + W Cw + P Cp  and  P <- W Cw + P Cp  in ONE pass over the three blocks
 //   residual_kernel  W = A X - B X diag(theta)
-//   cheb_start_kernel / cheb_step_kernel / gershgorin_kernel   the Chebyshev polynomial preconditioner (three-term
-//                    recurrence between two SpMMs: 40*n*m bytes per step, pure streaming) and its spectral bound
+//   cheb_start_kernel / cheb_step_kernel / gershgorin_kernel   the Jacobi-scaled Chebyshev polynomial preconditioner
+//                    (three-term recurrence between two SpMMs: 40*n*m bytes per step, pure streaming), its diagonal
+//                    scale and its spectral bound
 // Everything else of an LOBPCG iteration (SpMM, Gram, CholQR2, projection) reuses the kernels of the reference path.
 // No reference counterpart: normallytangent/dune-eigensolver has no LOBPCG; the closest relatives are
 // its block update V <- V U (kernels_cpp.hh:293-305) and projection Q_j -= Q_k S (:335-348).
@@ -141,48 +142,67 @@ namespace de
     }
   }
 
-  /** Z = s R ; Zold = 0  (first Chebyshev iterate z_1 = r / theta, z_0 = 0) */
+  // The three kernels below use a (m/2, 256/(m/2)) thread block: threadIdx.x walks the double2 pairs of a row,
+  // threadIdx.y the rows, so consecutive threads touch consecutive 16-byte words of the row-major block and the
+  // per-row Jacobi scale dinv[i] = 1 / a_ii is one load per row -- no index division.
+
+  /** Z = s D^-1 R ; Zold = 0  (first iterate of the Jacobi-scaled Chebyshev iteration, z_1 = D^-1 r / theta, z_0 = 0) */
   __global__ void __launch_bounds__(256)
-      cheb_start_kernel(long long pairs, double s, const double *__restrict__ R, double *__restrict__ Z,
-                        double *__restrict__ Zold)
+      cheb_start_kernel(long long n, int hp, double s, const double *__restrict__ dinv, const double *__restrict__ R,
+                        double *__restrict__ Z, double *__restrict__ Zold)
   {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < pairs; e += stride)
+    const long long rstride = (long long)gridDim.x * blockDim.y;
+    for (long long i = (long long)blockIdx.x * blockDim.y + threadIdx.y; i < n; i += rstride)
     {
-      const double2 r = ld2(R + 2 * e);
-      st2(Z + 2 * e, make_double2(s * r.x, s * r.y));
-      st2(Zold + 2 * e, make_double2(0.0, 0.0));
+      const double sc = s * __ldg(dinv + i);
+      const size_t e = ((size_t)i * hp + threadIdx.x) * 2;
+      const double2 r = ld2(R + e);
+      st2(Z + e, make_double2(sc * r.x, sc * r.y));
+      st2(Zold + e, make_double2(0.0, 0.0));
     }
   }
 
-  /** Zold <- Z + alpha (Z - Zold) + beta (R - AZ): the next Chebyshev iterate overwrites the one before the current */
+  /** Zold <- Z + alpha (Z - Zold) + beta D^-1 (R - AZ): the next Chebyshev iterate overwrites the one before the current */
   __global__ void __launch_bounds__(256)
-      cheb_step_kernel(long long pairs, double alpha, double beta, const double *__restrict__ Z,
-                       const double *__restrict__ R, const double *__restrict__ AZ, double *__restrict__ Zold)
+      cheb_step_kernel(long long n, int hp, double alpha, double beta, const double *__restrict__ dinv,
+                       const double *__restrict__ Z, const double *__restrict__ R, const double *__restrict__ AZ,
+                       double *__restrict__ Zold)
   {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < pairs; e += stride)
+    const long long rstride = (long long)gridDim.x * blockDim.y;
+    for (long long i = (long long)blockIdx.x * blockDim.y + threadIdx.y; i < n; i += rstride)
     {
-      const double2 z = ld2(Z + 2 * e), zo = ld2(Zold + 2 * e), r = ld2(R + 2 * e), a = ld2(AZ + 2 * e);
-      st2(Zold + 2 * e, make_double2(z.x + alpha * (z.x - zo.x) + beta * (r.x - a.x),
-                                     z.y + alpha * (z.y - zo.y) + beta * (r.y - a.y)));
+      const double bd = beta * __ldg(dinv + i);
+      const size_t e = ((size_t)i * hp + threadIdx.x) * 2;
+      const double2 z = ld2(Z + e), zo = ld2(Zold + e), r = ld2(R + e), a = ld2(AZ + e);
+      st2(Zold + e, make_double2(z.x + alpha * (z.x - zo.x) + bd * (r.x - a.x),
+                                 z.y + alpha * (z.y - zo.y) + bd * (r.y - a.y)));
     }
   }
 
-  /** out[0] = max(out[0], max_i sum_k |a_ik|) over this rank's rows: Gershgorin bound of the spectrum of a symmetric
-   *  matrix. Non-negative doubles compare like their bit patterns, so the maximum is an integer atomicMax. */
+  /** dinv[i] = 1 / a_ii and out[0] = max(out[0], max_i sum_k |a_ik| / a_ii) over this rank's rows: the Jacobi scale and
+   *  the Gershgorin bound of the spectrum of D^-1 A (equal to that of D^-1/2 A D^-1/2). Row i's diagonal entry is the
+   *  one with column index i (distributed matrices number their owned columns first). A row without a positive
+   *  diagonal entry makes the bound +inf, which the caller reports. Non-negative doubles compare like their bit
+   *  patterns, so the maximum is an integer atomicMax. */
   __global__ void __launch_bounds__(256)
-      gershgorin_kernel(long long n, const int *__restrict__ rowptr, const double *__restrict__ val,
-                        unsigned long long *out)
+      gershgorin_kernel(long long n, const int *__restrict__ rowptr, const int *__restrict__ col,
+                        const double *__restrict__ val, double *__restrict__ dinv, unsigned long long *out)
   {
     double best = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
-      double sum = 0.0;
+      double sum = 0.0, d = 0.0;
       for (int k = rowptr[i]; k < rowptr[i + 1]; ++k)
-        sum += fabs(val[k]);
-      best = fmax(best, sum);
+      {
+        const double v = val[k];
+        sum += fabs(v);
+        if (col[k] == i)
+          d = v;
+      }
+      const bool ok = d > 0.0;
+      dinv[i] = ok ? 1.0 / d : 1.0;
+      best = fmax(best, ok ? sum / d : __longlong_as_double(0x7ff0000000000000LL));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)

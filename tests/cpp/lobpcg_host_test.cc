@@ -193,32 +193,47 @@ struct HostOps
     return 0;
   }
   int precondition(Blk) { return 0; }
+  /** Jacobi-scaled Chebyshev: the bound is the Gershgorin bound of D^-1 A and every correction is scaled by D^-1 */
+  std::vector<double> dinv;
   int spectral_bound(double *b)
   {
     double g = 0.0;
+    dinv.assign(n, 1.0);
     for (int i = 0; i < n; ++i)
     {
-      double r = 0.0;
+      double r = 0.0, d = 0.0;
       for (int k = A->ptr[i]; k < A->ptr[i + 1]; ++k)
+      {
         r += std::abs(A->val[k]);
-      g = std::max(g, r);
+        if (A->col[k] == i)
+          d = A->val[k];
+      }
+      if (!(d > 0.0))
+        return 5;
+      dinv[i] = 1.0 / d;
+      g = std::max(g, r / d);
     }
     *b = g;
     return 0;
   }
   int cheb_start(Blk Z, Blk Zold, Blk R, double s)
   {
-    for (size_t e = 0; e < (size_t)n * m; ++e)
-    {
-      Z[e] = s * R[e];
-      Zold[e] = 0.0;
-    }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < m; ++j)
+      {
+        Z[(size_t)i * m + j] = s * dinv[i] * R[(size_t)i * m + j];
+        Zold[(size_t)i * m + j] = 0.0;
+      }
     return 0;
   }
   int cheb_step(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta)
   {
-    for (size_t e = 0; e < (size_t)n * m; ++e)
-      Zold[e] = Z[e] + alpha * (Z[e] - Zold[e]) + beta * (R[e] - AZ[e]);
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < m; ++j)
+      {
+        const size_t e = (size_t)i * m + j;
+        Zold[e] = Z[e] + alpha * (Z[e] - Zold[e]) + beta * dinv[i] * (R[e] - AZ[e]);
+      }
     return 0;
   }
   long spmm_count = 0;
@@ -277,6 +292,25 @@ struct HostOps
   }
 };
 
+// CSR matrix from a binary file: int64 n, int64 nnz, int64 rowptr[n+1], int64 col[nnz], double val[nnz]
+static bool load_csr(const char *path, Csr &A)
+{
+  FILE *f = std::fopen(path, "rb");
+  if (!f)
+    return false;
+  long long n = 0, nnz = 0;
+  bool ok = std::fread(&n, 8, 1, f) == 1 && std::fread(&nnz, 8, 1, f) == 1;
+  std::vector<long long> rp(ok ? n + 1 : 0), ci(ok ? nnz : 0);
+  A.val.resize(ok ? nnz : 0);
+  ok = ok && std::fread(rp.data(), 8, n + 1, f) == (size_t)(n + 1) && std::fread(ci.data(), 8, nnz, f) == (size_t)nnz &&
+       std::fread(A.val.data(), 8, nnz, f) == (size_t)nnz;
+  std::fclose(f);
+  A.n = (int)n;
+  A.ptr.assign(rp.begin(), rp.end());
+  A.col.assign(ci.begin(), ci.end());
+  return ok;
+}
+
 int main(int argc, char **argv)
 {
   const int N = argc > 1 ? std::atoi(argv[1]) : 20;
@@ -287,6 +321,12 @@ int main(int argc, char **argv)
 
   Csr A = stencil2d(N, 4.0, -1.0);
   Csr B = stencil2d(N, 4.0, 0.5); // SPD "mass-like" matrix on the same pattern
+  if (const char *fa = std::getenv("LOBPCG_TEST_A")) // any CSR matrix instead (tests with variable coefficients)
+    if (!load_csr(fa, A))
+      return 3;
+  if (const char *fb = std::getenv("LOBPCG_TEST_B"))
+    if (!load_csr(fb, B))
+      return 3;
   HostOps ops;
   ops.A = &A;
   ops.B = generalized ? &B : nullptr;

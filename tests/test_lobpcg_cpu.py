@@ -146,3 +146,35 @@ def test_lobpcg_orchestration_chebyshev_preconditioner(generalized):
         assert float(vals["maxres"]) <= 1e-9
     assert np.abs(runs[0][2] - runs[8][2]).max() <= 1e-12
     assert runs[8][0] * 3 <= runs[0][0] and runs[8][1] < runs[0][1]
+
+
+def _dump_csr(A, path):
+    rp, ci, v = A
+    with open(path, "wb") as f:
+        np.array([len(rp) - 1, len(ci)], dtype=np.int64).tofile(f)
+        np.asarray(rp, dtype=np.int64).tofile(f)
+        np.asarray(ci, dtype=np.int64).tofile(f)
+        np.asarray(v, dtype=np.float64).tofile(f)
+
+
+@pytest.mark.parametrize("contrast", [1e3, 1e6])
+def test_lobpcg_orchestration_high_contrast(tmp_path, contrast):
+    """configs[3]-type matrix (Q1 diffusion, kappa = 1 / contrast in a channel pattern): the Jacobi-scaled Chebyshev
+    preconditioner converges in a few dozen iterations where the plain iteration does not converge at all; the
+    eigenvalues agree with a shift-invert Lanczos solve (scipy ARPACK)"""
+    import scipy.sparse.linalg as spl
+
+    shape = (16, 16, 16)
+    A = M.q1_stiffness(shape, kappa=M.high_contrast_kappa(contrast, 8))
+    path = str(tmp_path / "A.bin")
+    _dump_csr(A, path)
+    env = dict(os.environ, LOBPCG_TEST_A=path)
+    out = subprocess.run([build_exe(), "16", "8", "1e-7", "0", "0", "0", "0", "8"], env=env, capture_output=True,
+                         text=True, timeout=600)
+    vals = dict(l.split(" ", 1) for l in out.stdout.splitlines() if " " in l)
+    assert out.returncode == 0, out.stdout
+    assert int(vals["iterations"]) <= 120
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    ref = np.sort(spl.eigsh(M.to_scipy(A).tocsc(), k=8, sigma=0.0, which="LM", tol=1e-13)[0])
+    assert np.abs(ev - ref).max() <= 1e-9 * np.abs(ref).max()
+    assert float(vals["maxres"]) <= 1e-7

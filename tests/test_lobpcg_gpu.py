@@ -167,6 +167,28 @@ def test_block_lincomb_kernel(ctx, m):
         h.close()
 
 
+@pytest.mark.parametrize("contrast", [1e3, 1e6])
+def test_standard_lobpcg_high_contrast(ctx, contrast):
+    """configs[3]-type matrix (Q1 diffusion with kappa = 1 / contrast channels): the drivers' Jacobi-scaled Chebyshev
+    preconditioner makes the 8 smallest eigenpairs reachable without a factorisation; checked against a shift-invert
+    Lanczos solve (scipy ARPACK, standing in for the reference's ARPACK++ comparator)"""
+    import scipy.sparse.linalg as spl
+
+    A = M.q1_stiffness((16, 16, 16), kappa=M.high_contrast_kappa(contrast, 8))
+    r = E.StandardLOBPCG(ctx, A, 1e-7, 2000, 8)
+    ref = np.sort(spl.eigsh(M.to_scipy(A).tocsc(), k=8, sigma=0.0, which="LM", tol=1e-13)[0])
+    assert r.iterations <= 300
+    assert np.abs(r.eval - ref).max() <= 1e-9 * np.abs(ref).max()
+    check_pairs(A, None, r.eval, r.evec, 1e-7)
+
+
+def test_lobpcg_chebyshev_needs_positive_diagonal(ctx):
+    rp, ci, v = M.laplacian_dirichlet_2d(12)
+    with pytest.raises(E.DeError) as e:
+        E.StandardLOBPCG(ctx, (rp, ci, -v), 1e-6, 50, 8)  # negative definite: diagonal -4
+    assert e.value.status == E.capi.DE_ERR_INVALID and "positive diagonal" in str(e.value)
+
+
 def test_lobpcg_argument_errors(ctx):
     A = M.laplacian_dirichlet_2d(12)
     with pytest.raises(E.DeError) as e:
