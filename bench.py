@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lobpcg", action="store_true", help="skip the LOBPCG legs (the \"lobpcg\" objects)")
+    ap.add_argument("--lobpcg-contrast", type=float, default=1e6,
+                    help="coefficient contrast of the high-contrast StandardLOBPCG leg (BASELINE.json configs[3]'s "
+                         "matrix type on one GPU); 0 skips it")
     ap.add_argument("--lobpcg-pencil-grid", type=int, default=128,
                     help="grid of the GeneralizedLOBPCG leg (stiffness + mass pencil, 64 eigenpairs: BASELINE.json "
                          "configs[2]); 0 skips it")
@@ -448,7 +451,8 @@ def run_b200(args):
                    "driver_choice": "headline = StandardLargest, the driver of this path that the reference implements "
                                     "(its CPU run is the reference arm); BASELINE.json configs[1] names StandardLOBPCG, "
                                     "which the reference lacks (SURVEY.md §0): that driver's time on the same matrix is "
-                                    "the 'lobpcg' object of this line, configs[2]'s pencil the 'lobpcg_pencil' object"},
+                                    "the 'lobpcg' object of this line, configs[2]'s pencil the 'lobpcg_pencil' object, "
+                                    "configs[3]'s coefficient on one GPU the 'lobpcg_high_contrast' object"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "eigenvalues_head": [float(x) for x in ev[:4]], "step_ms": [round(x, 3) for x in step_ms],
     }
@@ -460,6 +464,11 @@ def run_b200(args):
             # without the 3D factorisation the reference's GeneralizedInverse would need (UMFPACK, absent here)
             line["lobpcg_pencil"] = lobpcg_leg(["--grid", str(args.lobpcg_pencil_grid), "--mass", "--nev", "64", "--tol",
                                                 str(args.tol), "--maxiter", "400", "--steps", "1"], 200)
+        if args.lobpcg_contrast > 0.0:
+            # configs[3]'s matrix type on one GPU: high-contrast diffusion, same grid and block as the headline
+            line["lobpcg_high_contrast"] = lobpcg_leg(["--grid", str(args.grid), "--contrast", str(args.lobpcg_contrast),
+                                                       "--nev", str(args.nev), "--tol", str(args.tol), "--maxiter", "600",
+                                                       "--steps", "1", "--verify"], 150)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

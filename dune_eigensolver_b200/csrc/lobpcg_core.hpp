@@ -131,7 +131,7 @@ namespace de
     // T_k((theta - lambda)/delta) / T_k(theta/delta) lies in (0, 1) for lambda in (0, lo) and in [-eps_k, eps_k] on
     // [lo, hi]: the preconditioner D^-1/2 p(.) D^-1/2 is symmetric positive definite -- valid for LOBPCG -- and the
     // part of the scaled spectrum above lo is compressed to 1 +- eps_k. The Jacobi scaling is what makes it work for
-    // high-contrast coefficients (kappa = 1 / 10^6 channels, 24^3: 45 iterations; unscaled: no convergence in 2000).
+    // high-contrast coefficients (kappa in {1, 10^6} blocks, 24^3: 45 iterations; unscaled: no convergence in 2000).
     const bool cheb = prm.cheb_degree > 0 && !prm.largest;
     Blk CD = X, CZ = X, CAD = X;
     double cheb_theta = 0.0, cheb_delta = 0.0;

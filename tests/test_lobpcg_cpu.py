@@ -159,7 +159,7 @@ def _dump_csr(A, path):
 
 @pytest.mark.parametrize("contrast", [1e3, 1e6])
 def test_lobpcg_orchestration_high_contrast(tmp_path, contrast):
-    """configs[3]-type matrix (Q1 diffusion, kappa = 1 / contrast in a channel pattern): the Jacobi-scaled Chebyshev
+    """configs[3]-type matrix (Q1 diffusion, kappa in {1, contrast} in a block pattern): the Jacobi-scaled Chebyshev
     preconditioner converges in a few dozen iterations where the plain iteration does not converge at all; the
     eigenvalues agree with a shift-invert Lanczos solve (scipy ARPACK)"""
     import scipy.sparse.linalg as spl

@@ -169,7 +169,7 @@ def test_block_lincomb_kernel(ctx, m):
 
 @pytest.mark.parametrize("contrast", [1e3, 1e6])
 def test_standard_lobpcg_high_contrast(ctx, contrast):
-    """configs[3]-type matrix (Q1 diffusion with kappa = 1 / contrast channels): the drivers' Jacobi-scaled Chebyshev
+    """configs[3]-type matrix (Q1 diffusion with kappa in {1, contrast} in a block pattern): the drivers' Jacobi-scaled Chebyshev
     preconditioner makes the 8 smallest eigenpairs reachable without a factorisation; checked against a shift-invert
     Lanczos solve (scipy ARPACK, standing in for the reference's ARPACK++ comparator)"""
     import scipy.sparse.linalg as spl

@@ -33,6 +33,9 @@ def main():
                                                 "the StandardLOBPCG driver. A comma-separated list prints one line each.")
     ap.add_argument("--mass", action="store_true", help="generalized problem A x = lambda B x with the consistent Q1 mass "
                                                         "matrix (GeneralizedLOBPCG; BASELINE.json configs[2])")
+    ap.add_argument("--contrast", type=float, default=0.0,
+                    help="> 0: Q1 diffusion with coefficient `contrast` (1 elsewhere) in the block pattern of "
+                         "matrices.high_contrast_kappa (BASELINE.json configs[3] on one GPU); no analytic spectrum")
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--verbose", type=int, default=0)
     args = ap.parse_args()
@@ -44,9 +47,15 @@ def main():
     m = E.padded_cols(args.nev)
     if args.mass:
         args.stencil = "q1"
-    A = M.q1_stiffness(shape) if args.stencil == "q1" else M.laplacian_fd(shape)
+    if args.contrast > 0.0:
+        args.stencil = "q1"
+        A = M.q1_stiffness(shape, kappa=M.high_contrast_kappa(args.contrast, 8))
+    else:
+        A = M.q1_stiffness(shape) if args.stencil == "q1" else M.laplacian_fd(shape)
     B = M.q1_mass(shape) if args.mass else None
-    if args.mass:
+    if args.contrast > 0.0:
+        analytic = None
+    elif args.mass:
         analytic = M.eigenvalues_q1_pencil(shape)[:m]
     else:
         analytic = (M.eigenvalues_q1_stiffness(shape) if args.stencil == "q1" else M.eigenvalues_laplacian_fd(shape))[:m]
@@ -88,13 +97,18 @@ def probe_one(args, E, ctx, dA, dB, Q, start, A, B, analytic, n, m):
     line = {
         "driver": "%s (de_lobpcg_mv, blocks resident in HBM)" % ("GeneralizedLOBPCG" if args.mass else "StandardLOBPCG"),
         "workload": "3D %s %d^3 (n=%d), %d smallest eigenpairs, m=%d, relative residual tol=%g, seed=123" %
-                    ("Q1 stiffness + consistent mass pencil (27-point)" if args.mass else
-                     "Q1 27-point FE stiffness Laplace" if args.stencil == "q1" else "7-point FD Laplace", args.grid, n,
+                    (("Q1 diffusion, coefficient %g in a pattern of 8-cell blocks and 1 elsewhere (27-point)" % args.contrast
+                      if args.contrast > 0.0 else "") +
+                     (" + consistent mass pencil" if args.mass and args.contrast > 0.0 else
+                      "Q1 stiffness + consistent mass pencil (27-point)" if args.mass else
+                      "" if args.contrast > 0.0 else
+                      "Q1 27-point FE stiffness Laplace" if args.stencil == "q1" else "7-point FD Laplace"), args.grid, n,
                      args.nev, m, args.tol),
         "chebyshev_degree": args.cheb, "seconds": float(np.median(times)), "seconds_all": [round(t, 5) for t in times],
         "iterations": it, "restarts": restarts, "converged": conv, "ms_per_iteration": 1e3 * float(np.median(times)) / max(it, 1),
         "max_rel_residual": float((rn[:args.nev] / np.abs(lam[:args.nev])).max()),
-        "max_rel_eigenvalue_error_vs_analytic": float((np.abs(lam[:args.nev] - analytic[:args.nev]) / analytic[:args.nev]).max()),
+        "max_rel_eigenvalue_error_vs_analytic":
+            float((np.abs(lam[:args.nev] - analytic[:args.nev]) / analytic[:args.nev]).max()) if analytic is not None else None,
         "eigenvalues_head": [float(x) for x in lam[:4]],
         "kernel_ms_per_solve": {k: round(v[0], 3) for k, v in prof.items() if v[1] > 0},
         "kernel_launches_per_solve": {k: int(v[1]) for k, v in prof.items() if v[1] > 0},
