@@ -178,3 +178,19 @@ def test_lobpcg_orchestration_high_contrast(tmp_path, contrast):
     ref = np.sort(spl.eigsh(M.to_scipy(A).tocsc(), k=8, sigma=0.0, which="LM", tol=1e-13)[0])
     assert np.abs(ev - ref).max() <= 1e-9 * np.abs(ref).max()
     assert float(vals["maxres"]) <= 1e-7
+
+
+def test_host_sym_eig_clustered_and_graded():
+    """multiple eigenvalues (2D Laplacian: lambda_ij = lambda_ji) and a strongly graded matrix: the QL iteration must
+    keep the eigenvectors of a cluster orthonormal and the small eigenvalues of a graded matrix accurate"""
+    A = M.to_scipy(M.laplacian_dirichlet_2d(9)).toarray()
+    w, V = E.host_sym_eig(A)
+    assert np.abs(w - M.eigenvalues_laplace_dirichlet_2d(9)).max() <= 1e-13
+    assert np.abs(V.T @ V - np.eye(81)).max() <= 1e-13 and np.abs(A @ V - V * w).max() <= 1e-13
+    rng = np.random.default_rng(5)
+    Q, _ = np.linalg.qr(rng.standard_normal((40, 40)))
+    lam = 10.0 ** np.linspace(-8, 4, 40)
+    G = (Q * lam) @ Q.T
+    w, V = E.host_sym_eig(G)
+    assert np.abs(w - lam).max() <= 1e-12 * lam.max()
+    assert np.abs(V.T @ V - np.eye(40)).max() <= 1e-13
