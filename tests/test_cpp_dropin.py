@@ -84,28 +84,3 @@ def test_dropin_kernels(oracle):
     assert np.abs(dp - ref).max() <= 1e-12 * np.abs(ref).max()
     assert float(vals["ortho_defect"]) < 1e-13
     assert "number of cols must be a multiple of block size" in vals["caught"]
-
-
-@pytest.mark.gpu
-def test_dropin_standard_lobpcg_analytic():
-    """StandardLOBPCG through the C++ header template (new driver, reference parameter shape) against the analytic
-    spectrum of the reference's Laplacian (src/dune-eigensolver.cc:437-446)"""
-    rc, vals, text = run("lobpcg", 20, 8, 1e-9)
-    assert rc == 0, text
-    ev = np.array([float(x) for x in vals["eval"].split()])
-    an = M.eigenvalues_laplace_dirichlet_2d(20)[:8]
-    assert np.abs(ev - an).max() <= 1e-10 * an.max()
-
-
-@pytest.mark.gpu
-def test_dropin_generalized_lobpcg_analytic():
-    """GeneralizedLOBPCG through the C++ header template: 5-point Laplacian against an SPD matrix on the same pattern
-    (4 on the diagonal, 0.5 beside it); both are polynomials in the 1D second-difference matrices, so the pencil's
-    spectrum is (4 - 2 (c_i + c_j)) / (4 + (c_i + c_j)), c_i = cos(pi i / (N + 1))"""
-    N, nev = 16, 12
-    rc, vals, text = run("globpcg", N, nev, 1e-9)
-    assert rc == 0, text
-    ev = np.array([float(x) for x in vals["eval"].split()])
-    c = np.cos(np.pi * np.arange(1, N + 1) / (N + 1.0))
-    an = np.sort(((4.0 - 2.0 * (c[:, None] + c[None, :])) / (4.0 + (c[:, None] + c[None, :]))).reshape(-1))[:nev]
-    assert len(ev) == nev and np.abs(ev - an).max() <= 1e-10 * an.max()
