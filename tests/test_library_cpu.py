@@ -152,3 +152,24 @@ def test_bench_reference_arm_contract():
     assert d["higher_is_better"] is False and d["value"] > 0
     assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_lobpcg_legs_cannot_break_the_main_line():
+    """the LOBPCG legs of bench.py run in child processes: whatever happens there (here: no GPU at all) comes back as an
+    {"error": ...} object instead of an exception"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    res = mod.lobpcg_leg(["--grid", "6", "--nev", "4", "--steps", "1"], 120)
+    assert isinstance(res, dict)
+    if not has_gpu:
+        assert "no CPU fallback" in res["error"]
+    assert "error" in mod.lobpcg_leg(["--no-such-option"], 60)
