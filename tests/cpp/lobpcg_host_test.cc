@@ -2,7 +2,7 @@
 // solver (host_eig.hpp): the same template the library instantiates with its device kernels is instantiated here with
 // plain host loops. TEST INFRASTRUCTURE ONLY -- nothing in the library links or calls this.
 //
-// usage: lobpcg_host_test N nev tol generalized(0|1) largest(0|1) [verbose] [mgs(0|1)] [cheb_degree] [cheb_ratio]
+// usage: lobpcg_host_test N nev tol generalized(0|1) largest(0|1) [verbose] [mgs(0|1)] [cheb_degree] [cheb_ratio] [maxiter]
 // prints "iterations k", "restarts r", "eval ...", "maxres ...", "orth ..." ; exit code 0 if converged.
 #include <cmath>
 #include <cstdio>
@@ -338,7 +338,7 @@ int main(int argc, char **argv)
   prm.m = ops.m;
   prm.nev = nev;
   prm.tol = tol;
-  prm.maxiter = 2000;
+  prm.maxiter = argc > 10 ? std::atoi(argv[10]) : 2000;
   prm.verbose = argc > 6 ? std::atoi(argv[6]) : 0;
   prm.has_B = generalized != 0;
   prm.largest = largest != 0;

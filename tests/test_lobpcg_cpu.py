@@ -194,3 +194,17 @@ def test_host_sym_eig_clustered_and_graded():
     w, V = E.host_sym_eig(G)
     assert np.abs(w - lam).max() <= 1e-12 * lam.max()
     assert np.abs(V.T @ V - np.eye(40)).max() <= 1e-13
+
+
+def test_lobpcg_orchestration_maxiter_and_padding():
+    """the loop falls through silently at maxiter like the reference's drivers (eigensolver.hh:191, :327): exactly
+    maxiter basis updates, no error; maxiter = 0 returns the Rayleigh-Ritz vectors of the start block; nev = 3 runs a
+    block of 8 and tests convergence on the first 3 only"""
+    rc, vals, text = run(20, 8, 1e-12, 0, 0, 0, 0, 0, 0, 3)
+    assert int(vals["rc"]) == 0 and int(vals["iterations"]) == 3 and int(vals["converged"]) == 0, text
+    rc, vals, text = run(20, 8, 1e-12, 0, 0, 0, 0, 8, 0, 0)
+    assert int(vals["rc"]) == 0 and int(vals["iterations"]) == 0 and float(vals["orth"]) <= 1e-13, text
+    rc, vals, text = run(17, 3, 1e-8, 0, 0)
+    assert rc == 0 and len(vals["eval"].split()) == 3, text
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(17)[:3]).max() <= 1e-10
