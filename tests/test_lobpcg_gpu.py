@@ -25,8 +25,9 @@ def check_pairs(A, B, lam, V, tol):
 
 
 # Order matters under `pytest -x`: first the tests of the unpreconditioned / factored-preconditioner paths, then the
-# Chebyshev-preconditioned drivers, last the tests that were written after the round's GPU budget was spent (first
-# executed by the round-end run) -- so that a surprise in a later group cannot hide an earlier one.
+# Chebyshev-preconditioned drivers, then the kernel / high-contrast tests, last the C++ drop-in programs -- so that a
+# surprise in a later group cannot hide an earlier one. All groups have been run on a B200 except the generalized
+# drop-in program (written after the round's GPU budget was spent).
 
 
 def test_lobpcg_mv_largest_matches_reference_standard_largest(ctx, oracle):
