@@ -208,3 +208,34 @@ def test_lobpcg_orchestration_maxiter_and_padding():
     assert rc == 0 and len(vals["eval"].split()) == 3, text
     ev = np.array([float(x) for x in vals["eval"].split()])
     assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(17)[:3]).max() <= 1e-10
+
+
+def _stencil(N, c, o):
+    import scipy.sparse as sp
+
+    T = sp.diags([np.ones(N - 1), np.ones(N - 1)], [-1, 1])
+    I = sp.identity(N)
+    return (c * sp.identity(N * N) + o * (sp.kron(I, T) + sp.kron(T, I))).tocsr()
+
+
+@pytest.mark.parametrize("N,nev,tol,generalized,degree", [(20, 8, 1e-8, 0, 0), (16, 12, 1e-9, 1, 0), (40, 12, 1e-9, 0, 8),
+                                                          (30, 13, 1e-9, 1, 8), (40, 22, 1e-7, 0, 4)])
+def test_lobpcg_orchestration_matches_independent_oracle(N, nev, tol, generalized, degree):
+    """oracle/lobpcg_oracle.py (numpy / LAPACK, no code shared with the product) and the product's orchestration take
+    the same number of iterations (+-3: the two round differently) from the same start block and find the same
+    eigenvalues. A wrong search direction or coefficient block would still converge -- but not in the same number of
+    iterations. (Block boundaries that cut a multiple eigenvalue are avoided: there the count depends on rounding.)"""
+    from oracle import lobpcg_oracle as LO
+
+    m = E.padded_cols(nev)
+    n = N * N
+    # the test program fills its start block row-major from std::mt19937{123}: the same stream as one 8-wide panel
+    X0 = E.from_panels(E.start_block(n * m // 8, 8, 123), n * m // 8, 8).reshape(n, m)
+    A = _stencil(N, 4.0, -1.0)
+    B = _stencil(N, 4.0, 0.5) if generalized else None
+    theta, X, it, restarts, conv = LO.lobpcg(A, B, X0, nev, tol, 2000, degree)
+    rc, vals, text = run(N, nev, tol, generalized, 0, 0, 0, degree)
+    assert rc == 0 and conv, text
+    assert abs(int(vals["iterations"]) - it) <= 3, (vals["iterations"], it)
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    assert np.abs(ev - theta[:nev]).max() <= 1e-12
