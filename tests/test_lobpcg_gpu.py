@@ -237,3 +237,29 @@ def test_standard_lobpcg_iteration_parity_with_oracle(ctx, N, nev, tol):
     r = E.StandardLOBPCG(ctx, A, tol, 2000, nev)
     assert conv and abs(r.iterations - it) <= 5, (r.iterations, it)
     assert np.abs(r.eval - theta[:nev]).max() <= 1e-11
+
+
+def test_standard_lobpcg_full_size(ctx):
+    """BASELINE.json configs[1] at full size -- 3D Q1 Laplace 100^3, 32 eigenpairs via StandardLOBPCG, ini tolerance --
+    through size-independent properties (no reference run exists for this driver): analytic spectrum, residuals
+    recomputed on the host, orthonormality. This is tools/lobpcg_probe.py --verify as a test (that run: 36 iterations,
+    eigenvalues within 6e-7 relative, profiles/r01_lobpcg_q1100_chebyshev_sweep.jsonl)."""
+    shape, nev, tol = (100, 100, 100), 32, 2e-3
+    n = 100 ** 3
+    A = M.q1_stiffness(shape)
+    dA = E.Matrix(ctx, A)
+    Q = E.MultiVector(ctx, n, nev)
+    Q.upload_panels(E.start_block(n, nev, 123))
+    lam, rn, it, restarts, conv = E.lobpcg_mv(ctx, dA, Q, tol, 4000, nev=nev, cheb_degree=8)
+    assert conv and it <= 60, (conv, it)
+    an = M.eigenvalues_q1_stiffness(shape)[:nev]
+    assert (np.abs(lam - an) / an).max() <= 1e-4  # Ritz values: error ~ residual^2 / gap
+    assert np.all(np.diff(lam) >= -1e-12 * an.max())
+    X = Q.download_rowmajor()
+    S = M.to_scipy(A)
+    R = S @ X - X * lam
+    assert (np.linalg.norm(R, axis=0) / lam).max() <= 1.05 * tol
+    assert np.abs(rn - np.linalg.norm(R, axis=0)).max() <= 1e-6 * np.linalg.norm(R, axis=0).max()  # the driver's own norms
+    assert np.abs(X.T @ X - np.eye(nev)).max() <= 1e-12
+    Q.close()
+    dA.close()
