@@ -2165,11 +2165,8 @@ namespace
       DE_TRY(allreduce_sum(ctx, slots, nr));
       std::vector<double> h(nr, 0.0);
       DE_TRY(fetch_small(ctx, slots, h.data(), nr));
-      *b = *std::max_element(h.begin(), h.end());
-      if (!std::isfinite(*b) || !(*b > 0.0))
-        return set_error(ctx, DE_ERR_INVALID,
-                         "LOBPCG: the Chebyshev preconditioner needs a matrix with a positive diagonal (use cheb_degree = 0)");
-      return DE_OK;
+      *b = *std::max_element(h.begin(), h.end()); // +inf if some row has no positive diagonal entry: the caller then
+      return DE_OK;                               // runs without the preconditioner (lobpcg_core.hpp)
     }
     /** (m/2, 256/(m/2)) thread blocks of the row-wise streaming kernels */
     dim3 row_block() const { return dim3((unsigned)(m / 2), (unsigned)(256 / (m / 2))); }

@@ -28,7 +28,7 @@
 //   int residual(Blk W, Blk AX, Blk BX, const double *theta, double *norm2);   W = AX - BX diag(theta), column norms^2
 //   int precondition(Blk W);                           W <- T^-1 W (no-op without a preconditioner)
 //   int spectral_bound(double *b);                     Chebyshev only: prepares D = diag(A) and returns an upper bound
-//                                                      of the spectrum of D^-1 A (Gershgorin)
+//                                                      of the spectrum of D^-1 A (Gershgorin); +inf if some a_ii <= 0
 //   int cheb_start(Blk Z, Blk Zold, Blk R, double s);  Z = s D^-1 R ; Zold = 0
 //   int cheb_step(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta);
 //                                                      Zold <- Z + alpha (Z - Zold) + beta D^-1 (R - AZ)   (next iterate)
@@ -132,18 +132,27 @@ namespace de
     // [lo, hi]: the preconditioner D^-1/2 p(.) D^-1/2 is symmetric positive definite -- valid for LOBPCG -- and the
     // part of the scaled spectrum above lo is compressed to 1 +- eps_k. The Jacobi scaling is what makes it work for
     // high-contrast coefficients (kappa in {1, 10^6} blocks, 24^3: 45 iterations; unscaled: no convergence in 2000).
-    const bool cheb = prm.cheb_degree > 0 && !prm.largest;
+    bool cheb = prm.cheb_degree > 0 && !prm.largest;
     Blk CD = X, CZ = X, CAD = X;
     double cheb_theta = 0.0, cheb_delta = 0.0;
+    double hi = 0.0;
+    if (cheb)
+    {
+      // a matrix without a positive diagonal (spectral_bound then reports a bound that is not finite) has no Jacobi
+      // scale and need not be definite: the iteration itself is still valid, so it runs unpreconditioned
+      DE_LOBPCG_TRY(ops.spectral_bound(&hi));
+      if (!(hi > 0.0) || !(hi <= DBL_MAX))
+      {
+        cheb = false;
+        if (prm.verbose > 0)
+          std::printf("%s: no positive diagonal, running without the Chebyshev preconditioner\n", prm.name);
+      }
+    }
     if (cheb)
     {
       DE_LOBPCG_TRY(ops.alloc(&CD));
       DE_LOBPCG_TRY(ops.alloc(&CZ));
       DE_LOBPCG_TRY(ops.alloc(&CAD));
-      double hi = 0.0;
-      DE_LOBPCG_TRY(ops.spectral_bound(&hi));
-      if (!(hi > 0.0))
-        return kLobpcgRitzFailed;
       // the interval a degree-k polynomial damps to ~0.1: T_k(sigma) >= 10 needs about k >= 1.5 sqrt(hi/lo)
       const double ratio = prm.cheb_ratio > 1.0 ? prm.cheb_ratio
                                                 : std::max(4.0, (prm.cheb_degree + 1) * (prm.cheb_degree + 1) / 2.25);

@@ -253,7 +253,7 @@ int de_generalized_lobpcg(de_context *ctx, const de_matrix *A, const de_matrix *
                           const double *start_panel8, double *eval, double *evec, int verbose, int *iterations);
 /* Preconditioner of the two drivers above: a Jacobi-scaled Chebyshev polynomial in A of this degree (that many extra
  * SpMMs per iteration, no factorisation, works row-partitioned): ~ A^-1 on the upper part of the spectrum of
- * diag(A)^-1 A, bounded by its Gershgorin row sums; needs a positive diagonal. Measured: DESIGN.md §10. */
+ * diag(A)^-1 A, bounded by its Gershgorin row sums. A matrix without a positive diagonal is iterated without it. Measured: DESIGN.md §10. */
 #define DE_LOBPCG_DEFAULT_CHEB_DEGREE 8
 /* device-resident variant with all options: B may be NULL (standard problem); T, if not NULL, is a factorisation used
  * as preconditioner W <- T^-1 W (e.g. of A + shift*B; single GPU only) and takes precedence over cheb_degree;

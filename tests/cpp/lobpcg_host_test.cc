@@ -209,7 +209,10 @@ struct HostOps
           d = A->val[k];
       }
       if (!(d > 0.0))
-        return 5;
+      {
+        *b = HUGE_VAL; // like gershgorin_kernel: no Jacobi scale, the caller runs unpreconditioned
+        return 0;
+      }
       dinv[i] = 1.0 / d;
       g = std::max(g, r / d);
     }
@@ -321,6 +324,9 @@ int main(int argc, char **argv)
 
   Csr A = stencil2d(N, 4.0, -1.0);
   Csr B = stencil2d(N, 4.0, 0.5); // SPD "mass-like" matrix on the same pattern
+  if (std::getenv("LOBPCG_TEST_NEGATE_A")) // a negative definite matrix: no positive diagonal
+    for (double &v : A.val)
+      v = -v;
   if (const char *fa = std::getenv("LOBPCG_TEST_A")) // any CSR matrix instead (tests with variable coefficients)
     if (!load_csr(fa, A))
       return 3;

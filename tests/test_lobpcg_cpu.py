@@ -239,3 +239,16 @@ def test_lobpcg_orchestration_matches_independent_oracle(N, nev, tol, generalize
     assert abs(int(vals["iterations"]) - it) <= 3, (vals["iterations"], it)
     ev = np.array([float(x) for x in vals["eval"].split()])
     assert np.abs(ev - theta[:nev]).max() <= 1e-12
+
+
+def test_lobpcg_orchestration_without_positive_diagonal():
+    """a negative definite matrix has no Jacobi scale: the Chebyshev preconditioner is dropped and the plain iteration
+    runs (the drivers' default degree is 8, so this is what a caller of StandardLOBPCG gets)"""
+    out = subprocess.run([build_exe(), "12", "8", "1e-8", "0", "0", "1", "0", "8"], capture_output=True, text=True,
+                         timeout=300, env=dict(os.environ, LOBPCG_TEST_NEGATE_A="1"))
+    vals = dict(l.split(" ", 1) for l in out.stdout.splitlines() if " " in l)
+    assert out.returncode == 0 and "running without the Chebyshev preconditioner" in out.stdout, out.stdout
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    an = -M.eigenvalues_laplace_dirichlet_2d(12)[::-1][:8]
+    assert np.abs(ev - an).max() <= 1e-10 * np.abs(an).max()
+    assert int(vals["spmm"]) == 3 * int(vals["iterations"]) + 1  # A W, A X, A P per iteration: no Chebyshev products

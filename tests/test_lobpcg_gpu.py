@@ -188,11 +188,13 @@ def test_standard_lobpcg_high_contrast(ctx, contrast):
     assert np.abs(r.eval - ref).max() <= 1e-9 * np.abs(ref).max()
     check_pairs(A, None, r.eval, r.evec, 1e-7)
 
-def test_lobpcg_chebyshev_needs_positive_diagonal(ctx):
+def test_lobpcg_without_positive_diagonal_runs_unpreconditioned(ctx):
+    """a negative definite matrix has no Jacobi scale: the drivers fall back to the plain iteration instead of failing
+    (its smallest eigenvalues are minus the largest of the Laplacian)"""
     rp, ci, v = M.laplacian_dirichlet_2d(12)
-    with pytest.raises(E.DeError) as e:
-        E.StandardLOBPCG(ctx, (rp, ci, -v), 1e-6, 50, 8)  # negative definite: diagonal -4
-    assert e.value.status == E.capi.DE_ERR_INVALID and "positive diagonal" in str(e.value)
+    r = E.StandardLOBPCG(ctx, (rp, ci, -v), 1e-8, 2000, 8)
+    an = -M.eigenvalues_laplace_dirichlet_2d(12)[::-1][:8]
+    assert np.abs(r.eval - an).max() <= 1e-10 * np.abs(an).max()
 
 
 def test_dropin_standard_lobpcg_analytic():
