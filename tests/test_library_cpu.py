@@ -173,3 +173,31 @@ def test_bench_lobpcg_legs_cannot_break_the_main_line():
     if not has_gpu:
         assert "no CPU fallback" in res["error"]
     assert "error" in mod.lobpcg_leg(["--no-such-option"], 60)
+
+
+def test_c_abi_from_plain_c99(oracle):
+    """include/dune_eigensolver_b200.h is a C header: compiled with gcc -std=c99 -pedantic -Werror into a program
+    without any C++, linked against the library; host-only entry points work, a context needs a device"""
+    import subprocess
+
+    from dune_eigensolver_b200 import build as B
+
+    lib = B.build_library()
+    exe = os.path.join(ROOT, "tests", "c", "cabi_smoke")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "cabi_smoke.c"), "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib)],
+                   check=True, capture_output=True, text=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    f = out.stdout.split()
+    assert abs(float(f[3]) - 1.0) <= 1e-14 and abs(float(f[4]) - 3.0) <= 1e-14
+    assert float(f[6]) == float(np.asarray(oracle.start_block(2, 8, 123)).reshape(-1)[0])  # the reference's stream
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        assert f[8] == "3" and "no CPU fallback" in out.stdout
