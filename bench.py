@@ -458,7 +458,7 @@ def run_b200(args):
     }
     if world == 1 and not args.no_lobpcg:
         line["lobpcg"] = lobpcg_leg(["--grid", str(args.grid), "--stencil", args.stencil, "--nev", str(args.nev), "--tol",
-                                     str(args.tol), "--maxiter", str(args.maxiter)], 150)
+                                     str(args.tol), "--maxiter", str(args.maxiter), "--e2e"], 150)
         if args.lobpcg_pencil_grid > 0:
             # configs[2]: A x = lambda B x, Q1 stiffness + mass, 128^3, 64 eigenpairs -- by GeneralizedLOBPCG, i.e.
             # without the 3D factorisation the reference's GeneralizedInverse would need (UMFPACK, absent here)

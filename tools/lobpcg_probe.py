@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--contrast", type=float, default=0.0,
                     help="> 0: Q1 diffusion with coefficient `contrast` (1 elsewhere) in the block pattern of "
                          "matrices.high_contrast_kappa (BASELINE.json configs[3] on one GPU); no analytic spectrum")
+    ap.add_argument("--e2e", action="store_true", help="also time the host-buffer driver call (host CSR in, host "
+                                                       "eigenvectors out); standard problem, driver default degree")
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--verbose", type=int, default=0)
     args = ap.parse_args()
@@ -116,6 +118,15 @@ def probe_one(args, E, ctx, dA, dB, Q, start, A, B, analytic, n, m):
         "reference_arm": None,
         "note": "no reference arm: the reference has no LOBPCG and no factorisation-free route to these eigenpairs",
     }
+    if args.e2e and B is None and args.cheb == 8:
+        t_e2e = []
+        for _ in range(2):  # the second call is the measurement (allocator cache, pinned buffers warm)
+            t0 = time.perf_counter()
+            r = E.StandardLOBPCG(ctx, A, args.tol, args.maxiter, args.nev)
+            t_e2e.append(time.perf_counter() - t0)
+        line["e2e_seconds"] = t_e2e[-1]
+        line["e2e_iterations"] = r.iterations
+        line["e2e_api"] = "de_matrix_create_csr + de_standard_lobpcg (host CSR in, host eigenvectors out)"
     if args.verify:
         import scipy.sparse as sp
 
