@@ -1,0 +1,72 @@
+// Plain argument structs shared by the host runtime (de_internal.hpp) and the kernels that consume them
+// (kernels_peer.cuh, kernels_tail.cuh): the NVLink peer window layout and the fused reduction tail.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+namespace de
+{
+
+  constexpr int kPeerMaxRanks = 8;
+  constexpr int kPeerSlotDoubles = 4224; // >= 64 + 64 * 64
+  constexpr size_t kPeerFlagBytes = 4096;
+  constexpr size_t kPeerArOff = kPeerFlagBytes;
+  constexpr size_t kPeerHaloOff = kPeerArOff + (size_t)2 * kPeerMaxRanks * kPeerSlotDoubles * sizeof(double);
+
+  struct PeerArgs
+  {
+    int rank, nranks;
+    unsigned char *base[kPeerMaxRanks]; // window of every rank (own: local pointer)
+    unsigned long long epoch;           // of this operation; parity = epoch & 1
+    const int *done;                    // converged driver loop: no-op (the same on every rank)
+    int *err;                           // device error flag: a peer did not arrive
+  };
+
+  struct HaloPushArgs
+  {
+    int npeers;
+    int peer_rank[kPeerMaxRanks];
+    long long send_off[kPeerMaxRanks + 1]; // rows sent to peer p: send_rows[send_off[p] .. send_off[p+1])
+    long long deposit[kPeerMaxRanks];      // first row of this rank's rows in peer p's halo block
+    const int *send_rows;
+    const double *X;
+    int m;
+    size_t halo_cap_bytes;
+    int *ticket;
+  };
+
+  struct PeerList
+  {
+    int n;
+    int rank[kPeerMaxRanks];
+  };
+
+  enum
+  {
+    kTailNone = 0,
+    kTailChol = 1, // out = Gram matrix (m x m): Rinv = inverse Cholesky factor
+    kTailConv = 2  // out = [dp (m) | ...]: convergence test of the driver loop
+  };
+
+  struct TailArgs
+  {
+    int kind;
+    int do_allreduce;
+    PeerArgs pa;
+    int *ticket;
+    int m;
+    // Cholesky
+    double *Rinv;
+    int *status;
+    double *info;
+    int *identity_flag;
+    int *done;
+    // convergence
+    int k;
+    double shift, tol;
+    double *s_prev, *hist;
+    int *flags;
+  };
+
+} // namespace de

@@ -454,7 +454,7 @@ namespace de
   }
 
   template <int MP>
-  __global__ void __launch_bounds__(1024) chol_inverse2_kernel(int m, const double *__restrict__ G, double *__restrict__ Rinv,
+  static __global__ void __launch_bounds__(1024) chol_inverse2_kernel(int m, const double *__restrict__ G, double *__restrict__ Rinv,
                                                                int *__restrict__ status, double *__restrict__ info,
                                                                int *__restrict__ identity_flag, int *__restrict__ done)
   {

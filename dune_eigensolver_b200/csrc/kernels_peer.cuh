@@ -24,23 +24,11 @@
 
 #include <cuda_runtime.h>
 
+#include "de_types.hpp"
+
 namespace de
 {
 
-  constexpr int kPeerMaxRanks = 8;
-  constexpr int kPeerSlotDoubles = 4224; // >= 64 + 64 * 64
-  constexpr size_t kPeerFlagBytes = 4096;
-  constexpr size_t kPeerArOff = kPeerFlagBytes;
-  constexpr size_t kPeerHaloOff = kPeerArOff + (size_t)2 * kPeerMaxRanks * kPeerSlotDoubles * sizeof(double);
-
-  struct PeerArgs
-  {
-    int rank, nranks;
-    unsigned char *base[kPeerMaxRanks]; // window of every rank (own: local pointer)
-    unsigned long long epoch;           // of this operation; parity = epoch & 1
-    const int *done;                    // converged driver loop: no-op (the same on every rank)
-    int *err;                           // device error flag: a peer did not arrive
-  };
 
   __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
   {
@@ -112,27 +100,15 @@ namespace de
     __syncthreads();
   }
 
-  __global__ void __launch_bounds__(1024) peer_allreduce_kernel(const PeerArgs pa, double *__restrict__ buf, int len)
+  static __global__ void __launch_bounds__(1024) peer_allreduce_kernel(const PeerArgs pa, double *__restrict__ buf, int len)
   {
     if (pa.done != nullptr && *pa.done != 0)
       return;
     peer_allreduce_body(pa, threadIdx.x, buf, len);
   }
 
-  struct HaloPushArgs
-  {
-    int npeers;
-    int peer_rank[kPeerMaxRanks];
-    long long send_off[kPeerMaxRanks + 1]; // rows sent to peer p: send_rows[send_off[p] .. send_off[p+1])
-    long long deposit[kPeerMaxRanks];      // first row of this rank's rows in peer p's halo block
-    const int *send_rows;
-    const double *X;
-    int m;
-    size_t halo_cap_bytes;
-    int *ticket;
-  };
 
-  __global__ void __launch_bounds__(256) halo_push_kernel(const PeerArgs pa, const HaloPushArgs h)
+  static __global__ void __launch_bounds__(256) halo_push_kernel(const PeerArgs pa, const HaloPushArgs h)
   {
     if (pa.done != nullptr && *pa.done != 0)
       return;
@@ -166,14 +142,9 @@ namespace de
     }
   }
 
-  struct PeerList
-  {
-    int n;
-    int rank[kPeerMaxRanks];
-  };
 
   /** returns when the halo rows of this epoch from every listed peer have landed in this rank's window */
-  __global__ void __launch_bounds__(32) halo_wait_kernel(const PeerArgs pa, const PeerList peers)
+  static __global__ void __launch_bounds__(32) halo_wait_kernel(const PeerArgs pa, const PeerList peers)
   {
     if (pa.done != nullptr && *pa.done != 0)
       return;

@@ -421,7 +421,7 @@ namespace de
   /** dp[j] = sum_i X(i,j) Y(i,j) (reference dot_products_diagonal_blocked, kernels_cpp.hh:24-55).
    *  blockDim = (m/2, 256/(m/2)): x indexes a column pair, y a row lane; rows are strided over the grid.
    *  Leaves one partial vector per CTA. */
-  __global__ void __launch_bounds__(256) diag_dot_kernel(long long n, const double *__restrict__ X, int ldx,
+  static __global__ void __launch_bounds__(256) diag_dot_kernel(long long n, const double *__restrict__ X, int ldx,
                                                          const double *__restrict__ Y, int ldy, int m,
                                                          double *__restrict__ partials)
   {
@@ -468,7 +468,7 @@ namespace de
 
   /** out[e] = sum_p partials[p*len + e], p ascending: the fixed-order (deterministic) second stage of every
    *  reduction. blockDim = (32,32); each CTA owns 32 consecutive outputs. */
-  __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__restrict__ partials, int nparts,
+  static __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__restrict__ partials, int nparts,
                                                                  int len, double *__restrict__ out,
                                                                  const int *__restrict__ done = nullptr)
   {
@@ -526,7 +526,7 @@ namespace de
     (void)nthreads;
   }
 
-  __global__ void __launch_bounds__(64) convergence_kernel(int k, int m, double shift, double tol, const double *__restrict__ dp,
+  static __global__ void __launch_bounds__(64) convergence_kernel(int k, int m, double shift, double tol, const double *__restrict__ dp,
                                                            double *__restrict__ s_prev, double *__restrict__ hist,
                                                            int *__restrict__ flags)
   {
@@ -537,7 +537,7 @@ namespace de
 
   // ---- layout conversion at the boundary (reference MultiVector layout <-> row-major) ------------------
   /** to_rowmajor: dst[i*m + j] = src[((j/8)*n + i)*8 + j%8]; else the inverse. One thread per (row, 8-col panel). */
-  __global__ void __launch_bounds__(256) panel8_convert_kernel(long long n, int m, const double *__restrict__ src,
+  static __global__ void __launch_bounds__(256) panel8_convert_kernel(long long n, int m, const double *__restrict__ src,
                                                                double *__restrict__ dst, int to_rowmajor)
   {
     const int np = m / 8;
@@ -557,7 +557,7 @@ namespace de
   }
 
   /** evec[j*n + i] = X(i,j), j < nev (copy-out of eigensolver.hh:109-111): tiled transpose through smem. */
-  __global__ void __launch_bounds__(256) extract_columns_kernel(long long n, int m, int nev,
+  static __global__ void __launch_bounds__(256) extract_columns_kernel(long long n, int m, int nev,
                                                                 const double *__restrict__ X,
                                                                 double *__restrict__ out)
   {
@@ -579,7 +579,7 @@ namespace de
   }
 
   /** halo pack: buf[s*m + c] = X[rows[s]*m + c] */
-  __global__ void __launch_bounds__(256) pack_rows_kernel(long long count, const int *__restrict__ rows, int m,
+  static __global__ void __launch_bounds__(256) pack_rows_kernel(long long count, const int *__restrict__ rows, int m,
                                                           const double *__restrict__ X, double *__restrict__ buf)
   {
     const int hp = m / 2;

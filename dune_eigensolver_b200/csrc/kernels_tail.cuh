@@ -7,6 +7,7 @@
 // of it launch and dependency latency.
 #pragma once
 
+#include "de_types.hpp"
 #include "kernels_dense.cuh"
 #include "kernels_peer.cuh"
 #include "kernels_sparse.cuh"
@@ -14,35 +15,9 @@
 namespace de
 {
 
-  enum
-  {
-    kTailNone = 0,
-    kTailChol = 1, // out = Gram matrix (m x m): Rinv = inverse Cholesky factor
-    kTailConv = 2  // out = [dp (m) | ...]: convergence test of the driver loop
-  };
-
-  struct TailArgs
-  {
-    int kind;
-    int do_allreduce;
-    PeerArgs pa;
-    int *ticket;
-    int m;
-    // Cholesky
-    double *Rinv;
-    int *status;
-    double *info;
-    int *identity_flag;
-    int *done;
-    // convergence
-    int k;
-    double shift, tol;
-    double *s_prev, *hist;
-    int *flags;
-  };
 
   /** blockDim = (32, 32); gridDim.x = ceil(len / 32) */
-  __global__ void __launch_bounds__(1024) reduce_tail_kernel(const double *__restrict__ partials, int nparts, int len,
+  static __global__ void __launch_bounds__(1024) reduce_tail_kernel(const double *__restrict__ partials, int nparts, int len,
                                                              double *__restrict__ out, const int *__restrict__ done_in,
                                                              const TailArgs t)
   {
