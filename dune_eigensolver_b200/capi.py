@@ -41,6 +41,20 @@ SIGNATURES = {
     "de_matrix_create_csr": [_vp, C.c_int64, C.c_int64, _i64p, _i64p, _dp, _vpp],
     "de_matrix_create_distributed": [_vp, C.c_int64, C.c_int64, C.c_int64, _i64p, _i64p, _dp, C.c_int, _ip, _i64p,
                                      _i64p, _i64p, _vpp],
+    "de_halo_plan_peers": [C.c_int, C.c_int, _i64p, _i64p, _i64p, C.c_int64, _ip, _ip, _i64p, _i64p, _i64p, _i64p, _i64p, _ip],
+    "de_matrix_create_rowblock": [_vp, C.c_int64, C.c_int64, _i64p, _i64p, _dp, _i64p, _vp, _vp, _vpp],
+    "de_multi_create": [_ip, C.c_int, C.c_int64, _vpp],
+    "de_multi_destroy": [_vp],
+    "de_multi_size": [_vp, _ip],
+    "de_multi_context": [_vp, C.c_int, _vpp],
+    "de_multi_last_error": [_vp],
+    "de_multi_launch_count": [_vp, _i64p],
+    "de_multi_standard_largest": [_vp, C.c_int64, C.c_int64, _i64p, _i64p, _dp, C.c_int64, C.c_double, C.c_double,
+                                  C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip],
+    "de_multi_standard_lobpcg": [_vp, C.c_int64, C.c_int64, _i64p, _i64p, _dp, C.c_int64, C.c_double, C.c_int, C.c_int,
+                                 _dp, _dp, _dp, C.c_int, _ip],
+    "de_multi_generalized_lobpcg": [_vp, C.c_int64, C.c_int64, _i64p, _i64p, _dp, C.c_int64, _i64p, _i64p, _dp,
+                                    C.c_int64, C.c_double, C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, _ip],
     "de_matrix_destroy": [_vp],
     "de_matrix_rows": [_vp, _i64p, _i64p],
     "de_matrix_set_spmm_format": [_vp, C.c_int],
@@ -89,7 +103,8 @@ SIGNATURES = {
                               C.POINTER(_dp), _lp],
     "de_host_factor_destroy": [_vp],
 }
-_RESTYPES = {"de_last_error_string": C.c_char_p}
+_RESTYPES = {"de_last_error_string": C.c_char_p, "de_multi_last_error": C.c_char_p}
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
 
 _lib = None
 

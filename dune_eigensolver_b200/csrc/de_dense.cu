@@ -14,11 +14,75 @@ using namespace dei;
 namespace dei
 {
   // ---- reductions -----------------------------------------------------------------------------------
+  int flush_pending_dot(de_context *ctx)
+  {
+    if (!ctx->pending_dot.valid)
+      return DE_OK;
+    const de_context::PendingDot p = ctx->pending_dot;
+    ctx->pending_dot.valid = false;
+    ctx->tail = p.conv;
+    ctx->tail_armed = true;
+    ctx->tail_did_allreduce = ctx->tail_did_op = false;
+    DE_TRY(reduce_partials(ctx, ctx->partials, p.nparts, p.m, ctx->dDG()));
+    DE_TRY(allreduce_sum(ctx, ctx->dDG(), (size_t)p.m));
+    if (ctx->tail_did_op)
+      ctx->tail_did_op = false;
+    else
+    {
+      de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(p.conv.k, p.conv.m, p.conv.shift, p.conv.tol, ctx->dDP(), p.conv.s_prev,
+                                                        p.conv.hist, p.conv.flags);
+      DE_LAUNCH_CHECK(ctx);
+    }
+    ctx->tail_armed = false;
+    return DE_OK;
+  }
+
   int reduce_partials(de_context *ctx, const double *partials, int nparts, int len, double *out)
   {
     dim3 block(32, 32);
-    ProfScope prof(ctx, DE_PROF_SMALL);
     const bool multi = ctx->nranks > 1;
+    if (ctx->pending_dot.valid)
+    {
+      const de_context::PendingDot p = ctx->pending_dot;
+      const bool fusable = ctx->tail_armed && ctx->tail.kind == de::kTailChol && ctx->dtail_ticket &&
+                           partials == ctx->partials + kDotPartialsReserve &&
+                           (!multi || (ctx->peer_ready && len + p.m <= de::kPeerSlotDoubles));
+      if (!fusable)
+      {
+        // cannot share a launch: the partials of this reduction sit behind the reserve, the deferred ones are flushed first
+        DE_TRY(flush_pending_dot(ctx));
+      }
+      else
+      {
+        // [dp | G] <- reduce both partial sets -> ONE all-reduce -> convergence test -> Cholesky (kernels_tail.cuh).
+        // The result lives in dDG() (dp at its head, G behind it), not in `out`: nothing reads G after the Cholesky.
+        ProfScope prof(ctx, DE_PROF_SMALL);
+        ctx->pending_dot.valid = false;
+        de::TailArgs t = ctx->tail;
+        t.kind = de::kTailChol | de::kTailConv;
+        t.k = p.conv.k;
+        t.shift = p.conv.shift;
+        t.tol = p.conv.tol;
+        t.s_prev = p.conv.s_prev;
+        t.hist = p.conv.hist;
+        t.flags = p.conv.flags;
+        t.partials2 = ctx->partials;
+        t.nparts2 = p.nparts;
+        t.len2 = p.m;
+        t.do_allreduce = multi ? 1 : 0;
+        if (multi)
+          t.pa = peer_args(ctx, ++ctx->ar_epoch);
+        t.ticket = ctx->dtail_ticket;
+        ctx->tail_armed = false;
+        ctx->tail_did_allreduce = true;
+        ctx->tail_did_op = true;
+        DE_CUDA(ctx, launch_pdl(de::reduce_tail_kernel, dim3((len + p.m + 31) / 32), block, 0, ctx->stream, partials, nparts,
+                                len, ctx->dDG(), ctx->done_ptr, t));
+        DE_LAUNCH_CHECK(ctx);
+        return DE_OK;
+      }
+    }
+    ProfScope prof(ctx, DE_PROF_SMALL);
     if (ctx->tail_armed && ctx->dtail_ticket && (!multi || (ctx->peer_ready && len <= de::kPeerSlotDoubles)))
     {
       // reduce -> (all-reduce) -> Cholesky / convergence test in ONE launch
@@ -70,6 +134,8 @@ namespace dei
       DE_LAUNCH_CHECK(ctx);
       return DE_OK;
     }
+    if (!ctx->comm)
+      return set_error(ctx, DE_ERR_UNSUPPORTED, "all-reduce: vector exceeds the peer window slot and the context has no NCCL communicator");
     DE_NCCL(ctx, nccl_api().AllReduce(buf, buf, count, ncclDouble, ncclSum, ctx->comm, ctx->stream));
     return DE_OK;
   }
@@ -81,12 +147,13 @@ namespace dei
     dim3 block(hp, 256 / hp);
     const long long need = (n + block.y - 1) / block.y;
     const int grid = (int)std::max<long long>(1, std::min<long long>(need, kMaxPartials));
+    double *part = reduction_partials(ctx);
     {
       ProfScope prof(ctx, DE_PROF_DOT);
-      de::diag_dot_kernel<<<grid, block, 0, ctx->stream>>>(n, X, m, Y, m, m, ctx->partials);
+      de::diag_dot_kernel<<<grid, block, 0, ctx->stream>>>(n, X, m, Y, m, m, part);
     }
     DE_LAUNCH_CHECK(ctx);
-    DE_TRY(reduce_partials(ctx, ctx->partials, grid, m, out));
+    DE_TRY(reduce_partials(ctx, part, grid, m, out));
     return allreduce_sum(ctx, out, m);
   }
 
@@ -114,7 +181,7 @@ namespace dei
       DE_TRY(ensure_func_smem(ctx, (const void *)de::ts2_update_kernel<M, DO_GRAM>, C2::SMEM));
       const long long nt2 = (a.n + C2::TR - 1) / C2::TR;
       const int grid2 = (int)std::max<long long>(1, std::min<long long>(nt2, (long long)ctx->sm_count));
-      a.partials = ctx->partials;
+      a.partials = reduction_partials(ctx);
       a.done = ctx->done_ptr;
       {
         ProfScope prof(ctx, DE_PROF_UPDATE);
@@ -122,7 +189,7 @@ namespace dei
       }
       DE_LAUNCH_CHECK(ctx);
       if (DO_GRAM)
-        DE_TRY(reduce_partials(ctx, ctx->partials, grid2, M * M, gram_out));
+        DE_TRY(reduce_partials(ctx, a.partials, grid2, M * M, gram_out));
       return DE_OK;
     }
     if constexpr (!DO_UPDATE && DO_GRAM && UPPER && SAME)
@@ -132,14 +199,14 @@ namespace dei
       DE_TRY(ensure_func_smem(ctx, (const void *)de::ts2_gram_kernel<M>, C3::SMEM));
       const long long nt3 = (a.n + C3::TR - 1) / C3::TR;
       const int grid3 = (int)std::max<long long>(1, std::min<long long>(nt3, (long long)ctx->sm_count));
-      a.partials = ctx->partials;
+      a.partials = reduction_partials(ctx);
       a.done = ctx->done_ptr;
       {
         ProfScope prof(ctx, DE_PROF_GRAM);
         DE_CUDA(ctx, launch_pdl(de::ts2_gram_kernel<M>, dim3(grid3), dim3(de::kTg2Threads), C3::SMEM, ctx->stream, a));
       }
       DE_LAUNCH_CHECK(ctx);
-      return reduce_partials(ctx, ctx->partials, grid3, M * M, gram_out);
+      return reduce_partials(ctx, a.partials, grid3, M * M, gram_out);
     }
     constexpr int NOPS = (DO_GRAM && !SAME) ? 2 : 1;
     using C = de::TsCfg<M, UPPER, NOPS>;
@@ -151,7 +218,7 @@ namespace dei
     ctas_per_sm = std::min(ctas_per_sm, 2);
     const long long ntiles = (a.n + C::TR - 1) / C::TR;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * ctas_per_sm));
-    a.partials = ctx->partials;
+    a.partials = reduction_partials(ctx);
     a.done = ctx->done_ptr;
     {
       ProfScope prof(ctx, DO_UPDATE ? DE_PROF_UPDATE : DE_PROF_GRAM);
@@ -159,7 +226,7 @@ namespace dei
     }
     DE_LAUNCH_CHECK(ctx);
     if (DO_GRAM)
-      DE_TRY(reduce_partials(ctx, ctx->partials, grid, M * M, gram_out));
+      DE_TRY(reduce_partials(ctx, a.partials, grid, M * M, gram_out));
     return DE_OK;
   }
 
@@ -187,12 +254,13 @@ namespace dei
     using C = de::GramCfg<M, UPPER, SAME>;
     const long long ntiles = (n + C::TR - 1) / C::TR;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, kMaxPartials));
+    double *part = reduction_partials(ctx);
     {
       ProfScope prof(ctx, DE_PROF_GRAM);
-      de::gram_kernel<M, UPPER, SAME><<<grid, C::THREADS, 0, ctx->stream>>>(n, X, ldx, Y, ldy, ctx->partials);
+      de::gram_kernel<M, UPPER, SAME><<<grid, C::THREADS, 0, ctx->stream>>>(n, X, ldx, Y, ldy, part);
     }
     DE_LAUNCH_CHECK(ctx);
-    return reduce_partials(ctx, ctx->partials, grid, M * M, out);
+    return reduce_partials(ctx, part, grid, M * M, out);
   }
 
   template <bool UPPER, bool SAME>

@@ -285,7 +285,12 @@ extern "C"
     struct Guard
     {
       de_context *c;
-      ~Guard() { c->done_ptr = nullptr; }
+      ~Guard()
+      {
+        c->done_ptr = nullptr;
+        c->defer_dot = false;
+        c->pending_dot.valid = false;
+      }
     } guard{ctx};
     const size_t need = 64 + (size_t)std::max(maxiter, 2) + 1;
     if (ctx->dconv_cap < need)
@@ -301,6 +306,8 @@ extern "C"
     DE_CUDA(ctx, cudaMemsetAsync(ctx->dflags, 0, 4 * sizeof(int), ctx->stream));
     DE_CUDA(ctx, cudaMemsetAsync(ctx->dconv, 0, need * sizeof(double), ctx->stream));
     ctx->done_ptr = ctx->dflags + 1;
+    // one all-reduce wait less per iteration: the Rayleigh quotients travel with the next Gram matrix
+    ctx->defer_dot = ts_supported(m) && (ctx->nranks <= 1 || ctx->peer_ready) && ctx->dtail_ticket != nullptr;
     DE_TRY(orthonormalize_device(ctx, n, m, Qa)); // (:69)
     s2.assign(m, 0.0);
     int enqueued = 0;
@@ -329,7 +336,9 @@ extern "C"
       ctx->tail_armed = true;
       ctx->tail_did_allreduce = ctx->tail_did_op = false;
       DE_TRY(spmm_device(ctx, A, Qb, Qa, m, true, kFuseGramIntoSpmm ? &have_gram : nullptr));
-      if (ctx->tail_did_op)
+      if (ctx->pending_dot.valid)
+        ; // deferred: reduced, all-reduced and tested in the tail of the next iteration's first Gram reduction
+      else if (ctx->tail_did_op)
         ctx->tail_did_op = false;
       else
       {
@@ -359,6 +368,8 @@ extern "C"
         slot ^= 1;
       }
     }
+    DE_TRY(flush_pending_dot(ctx)); // the last iteration's Rayleigh quotients have no following Gram reduction
+    ctx->defer_dot = false;
     ctx->done_ptr = nullptr;
     const double t_enq = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_enq0).count();
     // final state

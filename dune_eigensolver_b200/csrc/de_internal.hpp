@@ -81,6 +81,7 @@ struct de_context
   void *xfer = nullptr;       // XferEngine: pinned staging buffers and copy streams (created on first use)
   // NVLink peer window (kernels_peer.cuh); peer_ready once every rank's window is mapped
   bool peer_ready = false;
+  bool peer_ipc = true; // peer windows were opened from CUDA IPC handles (else: same-process allocations, de_multi.cu)
   unsigned char *window = nullptr;
   size_t window_bytes = 0, halo_cap = 0;
   unsigned char *peer_base[de::kPeerMaxRanks] = {};
@@ -90,6 +91,16 @@ struct de_context
   de::TailArgs tail{};
   mutable bool tail_armed = false; // cleared by any error return (set_error), so a failed call cannot leave it behind
   mutable bool tail_did_allreduce = false, tail_did_op = false; // one-shot: the following allreduce_sum / chol / convergence is skipped
+  // Rayleigh-quotient partials of the last SpMM whose reduction + convergence test were deferred into the tail of the
+  // NEXT Gram reduction (asynchronous driver loop: one all-reduce per iteration less); see reduce_partials
+  bool defer_dot = false;
+  struct PendingDot
+  {
+    bool valid = false;
+    int nparts = 0, m = 0;
+    de::TailArgs conv{};
+  };
+  mutable PendingDot pending_dot;
   int *dtail_ticket = nullptr;
   size_t dconv_cap = 0;
   double *hsmall = nullptr;   // pinned mirror of dsmall
@@ -396,7 +407,16 @@ namespace dei
   // ---- de_dense.cu --------------------------------------------------------------------------------------------
   inline bool ts_supported(int w) { return w == 8 || w == 16 || w == 32 || w == 64; }
   de::PeerArgs peer_args(de_context *ctx, unsigned long long epoch);
+  /** doubles at the head of ctx->partials reserved for deferred Rayleigh-quotient partials */
+  constexpr size_t kDotPartialsReserve = (size_t)kMaxPartials * DE_KERNEL_MAX_M;
+  /** where a reduction kernel launched NOW must leave its per-CTA partials */
+  inline double *reduction_partials(de_context *ctx)
+  {
+    return ctx->partials + (ctx->pending_dot.valid ? kDotPartialsReserve : 0);
+  }
   int reduce_partials(de_context *ctx, const double *partials, int nparts, int len, double *out);
+  /** reduce + all-reduce + convergence test of deferred Rayleigh-quotient partials in a launch of their own */
+  int flush_pending_dot(de_context *ctx);
   int allreduce_sum(de_context *ctx, double *buf, size_t count);
   int diag_dot_device(de_context *ctx, long long n, int m, const double *X, const double *Y, double *out);
   int gram_device(de_context *ctx, int w, long long n, const double *X, int ldx, const double *Y, int ldy, bool symmetric,

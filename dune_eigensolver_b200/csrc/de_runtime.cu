@@ -48,6 +48,7 @@ namespace dei
     {
       ctx->err = msg;
       ctx->tail_armed = ctx->tail_did_allreduce = ctx->tail_did_op = false;
+      ctx->pending_dot.valid = false;
     }
     return code;
   }
@@ -579,7 +580,7 @@ extern "C"
         cudaEventDestroy(e);
     dev_free(ctx->dconv);
     for (int q = 0; q < de::kPeerMaxRanks; ++q)
-      if (ctx->peer_base[q] && q != ctx->rank)
+      if (ctx->peer_base[q] && q != ctx->rank && ctx->peer_ipc)
         cudaIpcCloseMemHandle(ctx->peer_base[q]);
     if (ctx->window)
       cudaFree(ctx->window);

@@ -529,6 +529,10 @@ namespace dei
       }
       else
       {
+        if (!ctx->comm)
+          return set_error(ctx, DE_ERR_UNSUPPORTED,
+                           "SpMM: the halo block does not fit the peer window (or the matrix has no peer deposits) and the "
+                           "context has no NCCL communicator; create the window with a larger halo_bytes");
         DE_TRY(ensure_halo_buffers(ctx, A, m));
         A->halo_view = A->halo_buf;
         if (A->n_send > 0)
@@ -598,6 +602,17 @@ namespace dei
     }
     if (DOT)
     {
+      if (ctx->defer_dot && !gram && g1 + g2 > 0 && ctx->tail_armed && ctx->tail.kind == de::kTailConv)
+      {
+        // asynchronous driver loop: the partials stay where they are; the tail of the next Gram reduction reduces and
+        // all-reduces them together with the Gram matrix and runs the convergence test (reduce_partials, de_dense.cu)
+        ctx->pending_dot.valid = true;
+        ctx->pending_dot.nparts = g1 + g2;
+        ctx->pending_dot.m = m;
+        ctx->pending_dot.conv = ctx->tail;
+        ctx->tail_armed = false;
+        return DE_OK;
+      }
       // dp (and G = Y^T Y when the Gram epilogue ran) are reduced, and all-reduced, as ONE vector dDG = [dp | G]
       const int len = gram ? m + m * m : m;
       if (g1 + g2 > 0)

@@ -47,7 +47,7 @@ namespace de
     kTailNone = 0,
     kTailChol = 1, // out = Gram matrix (m x m): Rinv = inverse Cholesky factor
     kTailConv = 2  // out = [dp (m) | ...]: convergence test of the driver loop
-  };
+  };                // kTailChol | kTailConv: out = [dp (m) | Gram matrix], see reduce_tail_kernel
 
   struct TailArgs
   {
@@ -67,6 +67,9 @@ namespace de
     double shift, tol;
     double *s_prev, *hist;
     int *flags;
+    // second segment of the reduction (the SpMM's Rayleigh-quotient partials), placed in front of the first
+    const double *partials2;
+    int nparts2, len2;
   };
 
 } // namespace de

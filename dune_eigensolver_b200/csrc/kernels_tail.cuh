@@ -16,7 +16,11 @@ namespace de
 {
 
 
-  /** blockDim = (32, 32); gridDim.x = ceil(len / 32) */
+  /** blockDim = (32, 32); gridDim.x = ceil((len + t.len2) / 32).
+   *  out = [ second segment (t.len2 values reduced from t.partials2) | first segment (len values from partials) ]:
+   *  the second segment carries the Rayleigh-quotient partials the preceding SpMM left behind, so that their
+   *  reduction, the Gram reduction, ONE all-reduce over both, the convergence test and the Cholesky share a launch
+   *  (one all-reduce wait per iteration less on several GPUs). */
   static __global__ void __launch_bounds__(1024) reduce_tail_kernel(const double *__restrict__ partials, int nparts, int len,
                                                              double *__restrict__ out, const int *__restrict__ done_in,
                                                              const TailArgs t)
@@ -28,13 +32,19 @@ namespace de
     __shared__ int last;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int e = blockIdx.x * 32 + threadIdx.x;
+    const int total = len + t.len2;
     double s = 0.0;
-    if (e < len)
+    if (e < t.len2)
+    {
+      for (int p = threadIdx.y; p < t.nparts2; p += 32)
+        s += t.partials2[(size_t)p * t.len2 + e];
+    }
+    else if (e < total)
       for (int p = threadIdx.y; p < nparts; p += 32)
-        s += partials[(size_t)p * len + e];
+        s += partials[(size_t)p * len + (e - t.len2)];
     red[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
-    if (threadIdx.y == 0 && e < len)
+    if (threadIdx.y == 0 && e < total)
     {
       double tot = 0.0;
 #pragma unroll
@@ -53,16 +63,21 @@ namespace de
       *t.ticket = 0;
     __threadfence();
     if (t.do_allreduce)
-      peer_allreduce_body(t.pa, tid, out, len);
-    if (t.kind == kTailChol)
+      peer_allreduce_body(t.pa, tid, out, total);
+    if (t.kind & kTailConv)
+    {
+      convergence_body(tid, 1024, t.k, t.m, t.shift, t.tol, out, t.s_prev, t.hist, t.flags);
+      __syncthreads();
+      if ((t.kind & kTailChol) && *reinterpret_cast<volatile int *>(t.flags + 1) != 0)
+        return; // converged: the blocks stay as they are
+    }
+    if (t.kind & kTailChol)
     {
       if (t.m <= 32)
-        chol_inverse2_body<32>(tid, t.m, out, t.Rinv, t.status, t.info, t.identity_flag, t.done);
+        chol_inverse2_body<32>(tid, t.m, out + t.len2, t.Rinv, t.status, t.info, t.identity_flag, t.done);
       else
-        chol_inverse2_body<64>(tid, t.m, out, t.Rinv, t.status, t.info, t.identity_flag, t.done);
+        chol_inverse2_body<64>(tid, t.m, out + t.len2, t.Rinv, t.status, t.info, t.identity_flag, t.done);
     }
-    else if (t.kind == kTailConv)
-      convergence_body(tid, 1024, t.k, t.m, t.shift, t.tol, out, t.s_prev, t.hist, t.flags);
   }
 
 } // namespace de

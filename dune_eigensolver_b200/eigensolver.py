@@ -152,6 +152,32 @@ class Matrix:
                                                       i64ptr(sr), C.byref(h)), ctx._h)
         return cls(ctx, _handle=h)
 
+    @classmethod
+    def rowblock(cls, ctx, rowptr, col_global, val, part, allgather=None):
+        """This rank's part of a row-partitioned matrix from its rows with GLOBAL column indices (C ABI
+        de_matrix_create_rowblock: halo planning and the exchange of the halo lists happen inside the library).
+        allgather(send: bytes-like of length b) -> bytes of length nranks*b, in rank order."""
+        rp, ci, v, part = i64(rowptr), i64(col_global), f64(val), i64(part)
+        h = C.c_void_p()
+        err = []
+
+        def _ag(user, send, recv, nbytes):
+            try:
+                out = allgather(C.string_at(send, nbytes))
+                C.memmove(recv, bytes(out), len(out))
+                return 0
+            except Exception as e:  # noqa: BLE001  (must not propagate through the C frame)
+                err.append(e)
+                return 1
+
+        cb = capi.ALLGATHER_FN(_ag) if allgather is not None else C.cast(None, capi.ALLGATHER_FN)
+        st = capi.lib().de_matrix_create_rowblock(ctx._h, len(rp) - 1, len(ci), i64ptr(rp), i64ptr(ci), dptr(v),
+                                                  i64ptr(part), cb, None, C.byref(h))
+        if err:
+            raise err[0]
+        check(st, ctx._h)
+        return cls(ctx, _handle=h)
+
     def set_peer_deposit(self, deposit_rows, max_halo_rows_all_ranks):
         d = i64(deposit_rows)
         check(capi.lib().de_matrix_set_peer_deposit(self._h, i64ptr(d), int(max_halo_rows_all_ranks)), self.ctx._h)
@@ -189,6 +215,74 @@ class Matrix:
             self.close()
         except Exception:
             pass
+
+
+class Multi:
+    """Single-process multi-GPU front end (C ABI de_multi_*): one host thread and one context per GPU inside the
+    library, NVLink peer windows of the same process. devices may repeat an ordinal (several ranks on one GPU)."""
+
+    def __init__(self, devices, halo_bytes=0):
+        self._h = C.c_void_p()
+        d = capi.i32(list(devices))
+        check(capi.lib().de_multi_create(capi.i32ptr(d), len(d), int(halo_bytes), C.byref(self._h)))
+        self.ndev = len(d)
+
+    def close(self):
+        if self._h:
+            capi.lib().de_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != capi.DE_OK:
+            msg = capi.lib().de_multi_last_error(self._h)
+            raise DeError(st, (msg or b"").decode() or "de_status %d" % st)
+
+    def launch_count(self):
+        c = C.c_int64(0)
+        self._check(capi.lib().de_multi_launch_count(self._h, C.byref(c)))
+        return c.value
+
+    def _start(self, n, m, seed, start):
+        return start_block(n, m, seed) if start is None else f64(start)
+
+    def StandardLargest(self, A, shift, tol, maxiter, nev, verbose=0, seed=123, start=None, row_align=1):
+        """reference StandardLargest (eigensolver.hh:28-112), rows split over the GPUs; A is shifted in place"""
+        rp, ci, v = _csr(A)
+        n, m = len(rp) - 1, padded_cols(nev)
+        if shift != 0.0:
+            _add_to_diagonal(rp, ci, v, shift)
+        st = self._start(n, m, seed, start)
+        ev, V, it = np.zeros(nev), np.zeros((nev, n)), C.c_int(0)
+        self._check(capi.lib().de_multi_standard_largest(self._h, n, len(ci), i64ptr(rp), i64ptr(ci), dptr(v), int(row_align),
+                                                         shift, tol, maxiter, nev, dptr(st), dptr(ev), dptr(V), verbose,
+                                                         C.byref(it)))
+        return Result(ev, V, it.value)
+
+    def StandardLOBPCG(self, A, tol, maxiter, nev, verbose=0, seed=123, start=None, row_align=1):
+        rp, ci, v = _csr(A)
+        n, m = len(rp) - 1, padded_cols(nev)
+        st = self._start(n, m, seed, start)
+        ev, V, it = np.zeros(nev), np.zeros((nev, n)), C.c_int(0)
+        self._check(capi.lib().de_multi_standard_lobpcg(self._h, n, len(ci), i64ptr(rp), i64ptr(ci), dptr(v), int(row_align),
+                                                        tol, maxiter, nev, dptr(st), dptr(ev), dptr(V), verbose, C.byref(it)))
+        return Result(ev, V, it.value)
+
+    def GeneralizedLOBPCG(self, A, B, tol, maxiter, nev, verbose=0, seed=123, start=None, row_align=1):
+        rp, ci, v = _csr(A)
+        brp, bci, bv = _csr(B)
+        n, m = len(rp) - 1, padded_cols(nev)
+        st = self._start(n, m, seed, start)
+        ev, V, it = np.zeros(nev), np.zeros((nev, n)), C.c_int(0)
+        self._check(capi.lib().de_multi_generalized_lobpcg(self._h, n, len(ci), i64ptr(rp), i64ptr(ci), dptr(v), len(bci),
+                                                           i64ptr(brp), i64ptr(bci), dptr(bv), int(row_align), tol, maxiter,
+                                                           nev, dptr(st), dptr(ev), dptr(V), verbose, C.byref(it)))
+        return Result(ev, V, it.value)
 
 
 class MultiVector:

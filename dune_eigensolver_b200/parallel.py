@@ -78,30 +78,33 @@ def exchange_send_lists(halo_global, recv_counts, part, rank, dist=None):
     return {p: in_lists[p].cpu().numpy().astype(np.int64) for p in range(nranks) if p != rank and counts_in_l[p] > 0}
 
 
+def allgather_bytes(dist=None):
+    """all-gather of equal-length byte strings over torch.distributed, in the form Matrix.rowblock wants"""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+
+    def ag(send):
+        t = torch.frombuffer(bytearray(send), dtype=torch.uint8)
+        dev = None
+        if dist.get_backend() == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device())
+            t = t.to(dev)
+        out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, t)
+        return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+
+    return ag
+
+
 def build_distributed_matrix(ctx, rowptr, col_global, val, part, rank, dist=None):
-    """Create this rank's device matrix from its global-index CSR row block."""
+    """Create this rank's device matrix from its global-index CSR row block. Halo planning, the exchange of the halo
+    lists (two all-gathers) and the peer-deposit offsets are computed inside the library (de_matrix_create_rowblock);
+    torch.distributed only carries the all-gather."""
     from .eigensolver import Matrix
 
-    col_local, halo_global, recv_counts = halo_plan_local(rowptr, col_global, part, rank)
-    send_lists = exchange_send_lists(halo_global, recv_counts, part, rank, dist)
-    nranks = len(part) - 1
-    peers = sorted(set(send_lists.keys()) | {p for p in range(nranks) if recv_counts[p] > 0})
-    recv = [int(recv_counts[p]) for p in peers]
-    send_offsets, send_rows = [0], []
-    for p in peers:
-        lst = send_lists.get(p, np.zeros(0, dtype=np.int64))
-        send_rows.append(lst)
-        send_offsets.append(send_offsets[-1] + len(lst))
-    send_rows = np.concatenate(send_rows) if send_rows else np.zeros(0, dtype=np.int64)
-    n_owned = len(rowptr) - 1
-    dA = Matrix.distributed(ctx, n_owned, len(halo_global), rowptr, col_local, val, peers, recv, send_offsets,
-                            send_rows)
-    if ctx.peer_ready():
-        # where do my rows start in each neighbour's halo block? its halo rows are ordered by owner rank, so the
-        # offset is the number of rows it receives from ranks below mine
-        deposits, max_halo = peer_deposit_offsets(recv_counts, peers, rank, dist)
-        dA.set_peer_deposit(deposits, max_halo)
-    return dA
+    assert ctx.rank()[0] == rank or ctx.rank()[1] == 1
+    return Matrix.rowblock(ctx, rowptr, col_global, val, part, allgather_bytes(dist))
 
 
 def peer_deposit_offsets(recv_counts, peers, rank, dist=None):

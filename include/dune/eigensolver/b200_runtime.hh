@@ -54,6 +54,75 @@ namespace de_b200
     }
   };
 
+  /** Process-wide multi-GPU configuration of the drop-in drivers (new key `parallel.numgpus` of the ini, read by the
+   *  driver program; the reference has `parallel.numthreads` for its replica harness only, src/dune-eigensolver.cc:757).
+   *  With more than one device StandardLargest / StandardLOBPCG / GeneralizedLOBPCG run row-partitioned through the
+   *  single-process front end of the C ABI (de_multi_*): one library thread per GPU, halo rows and the small reductions
+   *  over NVLink peer memory. The factored drivers stay on one GPU (triangular solves do not row-shard). */
+  class Parallel
+  {
+    std::vector<int> devices_{0};
+    std::int64_t row_align_ = 1;
+    std::int64_t halo_bytes_ = 0;
+    de_multi *multi_ = nullptr;
+
+    Parallel() = default;
+
+  public:
+    ~Parallel() { de_multi_destroy(multi_); }
+    Parallel(const Parallel &) = delete;
+    Parallel &operator=(const Parallel &) = delete;
+    static Parallel &instance()
+    {
+      static Parallel p;
+      return p;
+    }
+    //! CUDA ordinals to use, e.g. {0,1,2,3}; one entry = the single-GPU path (Context::default_device follows it)
+    void set_devices(const std::vector<int> &devices)
+    {
+      if (devices.empty())
+        throw std::invalid_argument("Parallel::set_devices: empty device list");
+      de_multi_destroy(multi_);
+      multi_ = nullptr;
+      devices_ = devices;
+    }
+    //! use the first n devices of the machine
+    void set_num_gpus(int n)
+    {
+      std::vector<int> d;
+      for (int i = 0; i < n; ++i)
+        d.push_back(i);
+      set_devices(d);
+    }
+    //! cut the rows only at multiples of this many rows (one grid plane of a lexicographic 3D grid keeps halos thin)
+    void set_row_align(std::int64_t rows) { row_align_ = rows < 1 ? 1 : rows; }
+    void set_halo_bytes(std::int64_t bytes)
+    {
+      halo_bytes_ = bytes;
+      de_multi_destroy(multi_);
+      multi_ = nullptr;
+    }
+    int num_gpus() const { return (int)devices_.size(); }
+    int first_device() const { return devices_[0]; }
+    std::int64_t row_align() const { return row_align_; }
+    de_multi *multi()
+    {
+      if (!multi_)
+        check(de_multi_create(devices_.data(), (int)devices_.size(), halo_bytes_, &multi_));
+      return multi_;
+    }
+    void check_multi(int status) const
+    {
+      if (status == DE_OK)
+        return;
+      const char *msg = de_multi_last_error(multi_);
+      const std::string text = (msg && *msg) ? msg : ("dune-eigensolver-b200: status " + std::to_string(status));
+      if (status == DE_ERR_INVALID || status == DE_ERR_SINGULAR)
+        throw std::invalid_argument(text);
+      throw std::runtime_error(text);
+    }
+  };
+
   //! CSR copy of an ISTL-style matrix with 1x1 blocks, taken through its row / column iterators
   struct HostCsr
   {

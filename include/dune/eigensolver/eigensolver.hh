@@ -93,13 +93,25 @@ void StandardLargest(ISTLM &A, double shift, double tol, int maxiter, int nev, s
   if (shift != 0.0)
     de_b200::add_to_diagonal(A, shift); // overwrites the caller's matrix, like the reference
 
-  auto &ctx = de_b200::Context::thread_default();
-  de_b200::DeviceMatrix dA(ctx, A);
   std::vector<double> values(nev), vectors((std::size_t)nev * n);
   int iterations = 0;
-  de_b200::check(de_standard_largest(ctx.get(), dA.get(), shift, tol, maxiter, nev, start.data(), values.data(),
-                                     vectors.data(), verbose, &iterations),
-                 ctx.get());
+  auto &par = de_b200::Parallel::instance();
+  if (par.num_gpus() > 1)
+  {
+    // row-partitioned over the configured GPUs (parallel.numgpus): same arguments, same results to rounding
+    const de_b200::HostCsr H(A);
+    par.check_multi(de_multi_standard_largest(par.multi(), H.n, (std::int64_t)H.col.size(), H.rowptr.data(), H.col.data(),
+                                              H.val.data(), par.row_align(), shift, tol, maxiter, nev, start.data(),
+                                              values.data(), vectors.data(), verbose, &iterations));
+  }
+  else
+  {
+    auto &ctx = de_b200::Context::thread_default();
+    de_b200::DeviceMatrix dA(ctx, A);
+    de_b200::check(de_standard_largest(ctx.get(), dA.get(), shift, tol, maxiter, nev, start.data(), values.data(),
+                                       vectors.data(), verbose, &iterations),
+                   ctx.get());
+  }
   de_b200::scatter_results(nev, n, values, vectors, eval, evec);
 }
 
@@ -191,13 +203,24 @@ void StandardLOBPCG(const ISTLM &A, double tol, int maxiter, int nev, std::vecto
   const std::size_t n = A.N();
   const std::size_t m = de_b200::padded_columns(nev, 8);
   MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
-  auto &ctx = de_b200::Context::thread_default();
-  de_b200::DeviceMatrix dA(ctx, A);
   std::vector<double> values(nev), vectors((std::size_t)nev * n);
   int iterations = 0;
-  de_b200::check(de_standard_lobpcg(ctx.get(), dA.get(), tol, maxiter, nev, start.data(), values.data(), vectors.data(),
-                                    verbose, &iterations),
-                 ctx.get());
+  auto &par = de_b200::Parallel::instance();
+  if (par.num_gpus() > 1)
+  {
+    const de_b200::HostCsr H(A);
+    par.check_multi(de_multi_standard_lobpcg(par.multi(), H.n, (std::int64_t)H.col.size(), H.rowptr.data(), H.col.data(),
+                                             H.val.data(), par.row_align(), tol, maxiter, nev, start.data(), values.data(),
+                                             vectors.data(), verbose, &iterations));
+  }
+  else
+  {
+    auto &ctx = de_b200::Context::thread_default();
+    de_b200::DeviceMatrix dA(ctx, A);
+    de_b200::check(de_standard_lobpcg(ctx.get(), dA.get(), tol, maxiter, nev, start.data(), values.data(), vectors.data(),
+                                      verbose, &iterations),
+                   ctx.get());
+  }
   de_b200::scatter_results(nev, n, values, vectors, eval, evec);
 }
 
@@ -212,13 +235,25 @@ void GeneralizedLOBPCG(const ISTLM &A, const ISTLM &B, double tol, int maxiter, 
   const std::size_t n = A.N();
   const std::size_t m = de_b200::padded_columns(nev, 8);
   MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
-  auto &ctx = de_b200::Context::thread_default();
-  de_b200::DeviceMatrix dA(ctx, A), dB(ctx, B);
   std::vector<double> values(nev), vectors((std::size_t)nev * n);
   int iterations = 0;
-  de_b200::check(de_generalized_lobpcg(ctx.get(), dA.get(), dB.get(), tol, maxiter, nev, start.data(), values.data(),
-                                       vectors.data(), verbose, &iterations),
-                 ctx.get());
+  auto &par = de_b200::Parallel::instance();
+  if (par.num_gpus() > 1)
+  {
+    const de_b200::HostCsr HA(A), HB(B);
+    par.check_multi(de_multi_generalized_lobpcg(par.multi(), HA.n, (std::int64_t)HA.col.size(), HA.rowptr.data(),
+                                                HA.col.data(), HA.val.data(), (std::int64_t)HB.col.size(), HB.rowptr.data(),
+                                                HB.col.data(), HB.val.data(), par.row_align(), tol, maxiter, nev,
+                                                start.data(), values.data(), vectors.data(), verbose, &iterations));
+  }
+  else
+  {
+    auto &ctx = de_b200::Context::thread_default();
+    de_b200::DeviceMatrix dA(ctx, A), dB(ctx, B);
+    de_b200::check(de_generalized_lobpcg(ctx.get(), dA.get(), dB.get(), tol, maxiter, nev, start.data(), values.data(),
+                                         vectors.data(), verbose, &iterations),
+                   ctx.get());
+  }
   if (eval.size() != (std::size_t)nev)
     eval.resize(nev);
   if (evec.size() != (std::size_t)nev)

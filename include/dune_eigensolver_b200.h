@@ -149,6 +149,29 @@ int de_halo_plan_local(int64_t n_owned, const int64_t *rowptr, const int64_t *co
                        const int64_t *part, int64_t *col_local, int64_t *halo_global, int64_t *n_halo,
                        int64_t *recv_counts);
 
+/* Host-only second half of the planning (no GPU needed; exercised by the gloo CPU tests): from the all-gathered
+ * results of de_halo_plan_local -- counts_all[q*nranks + p] = halo rows rank q receives from owner p, lists_all + q *
+ * list_stride = rank q's halo_global list -- derive this rank's neighbours. Outputs (caller-allocated, nranks entries;
+ * send_offsets nranks + 1; send_rows sum_q counts_all[q*nranks + rank]): peers in ascending rank order, rows received
+ * from / sent to each (send_rows are LOCAL row indices in the receiver's halo order), deposit_rows[p] = first row of
+ * this rank's rows inside peer p's halo block, the largest halo block over all ranks, and whether the send / receive
+ * relation is symmetric between every pair of ranks (the peer-store exchange requires it). */
+int de_halo_plan_peers(int nranks, int rank, const int64_t *part, const int64_t *counts_all, const int64_t *lists_all,
+                       int64_t list_stride, int *npeers, int *peer_ranks, int64_t *recv_counts, int64_t *send_offsets,
+                       int64_t *send_rows, int64_t *deposit_rows, int64_t *max_halo_rows, int *symmetric);
+
+/* One rank's part of a row-partitioned matrix, straight from its rows with GLOBAL column indices: halo planning
+ * (de_halo_plan_local), the exchange of the halo lists between the ranks and the peer-deposit offsets happen inside.
+ * part[0..nranks] are the partition offsets (this rank owns rows [part[rank], part[rank+1]) = n_owned rows; rank and
+ * nranks are the context's, see de_context_init_comm / de_multi_create). The only thing the caller supplies is an
+ * all-gather over the ranks of the job: every rank passes `bytes` bytes in `send`, `recv` receives nranks*bytes in
+ * rank order; return 0 on success (torch.distributed / MPI_Allgather in a multi-process job; de_multi_* brings its
+ * own). With one rank this is de_matrix_create_csr and allgather may be NULL. */
+typedef int (*de_allgather_fn)(void *user, const void *send, void *recv, int64_t bytes);
+int de_matrix_create_rowblock(de_context *ctx, int64_t n_owned, int64_t nnz, const int64_t *rowptr,
+                              const int64_t *col_global, const double *val, const int64_t *part,
+                              de_allgather_fn allgather, void *user, de_matrix **out);
+
 /* ---- multivector: replaces MultiVector<double,8> (multivector.hh:17-146) ---------------------------
  * Device-resident n x m block (row-major inside the library; the layout is opaque). m % 8 == 0 is enforced
  * like multivector.hh:48-49; storage is zero-initialised like multivector.hh:52. For a distributed run n is
@@ -235,6 +258,36 @@ int de_standard_inverse(de_context *ctx, const de_matrix *A, const de_factor *F,
 int de_generalized_inverse(de_context *ctx, const de_matrix *A, const de_matrix *B, const de_factor *F, double shift,
                            double tol, int maxiter, int nev, const double *start_panel8, double *eval, double *evec,
                            int verbose, int *iterations, double *relerror);
+
+/* ---- single-process multi-GPU front end -----------------------------------------------------------------------
+ * SURVEY.md §8b's `de_context_create(const int *device_ids, int ndev, ...)`: ONE process drives ndev GPUs (1..8), one
+ * host thread and one de_context per GPU inside the library; the windows of the NVLink data path (halo rows as peer
+ * stores, one-shot peer all-reduce of the m and m x m reductions) are peer-mapped allocations of this process, so no
+ * NCCL, MPI or Python is involved. halo_bytes: capacity of each of the two halo buffers per GPU (0: 128 MB; a block of
+ * halo rows of the widest vector block must fit). The same ordinal may be listed more than once (several ranks on one
+ * GPU: used by the tests on single-GPU machines). The drivers take the GLOBAL matrix (host CSR, as
+ * de_matrix_create_csr) and the GLOBAL start block and return global eigenvectors, exactly like their single-GPU
+ * counterparts de_standard_largest / de_standard_lobpcg / de_generalized_lobpcg; rows are split into ndev contiguous
+ * blocks, cut only at multiples of row_align (e.g. one grid plane; <= 1: anywhere). Results agree with the one-GPU
+ * run to rounding (different reduction order); every rank takes the same convergence decision. */
+typedef struct de_multi de_multi;
+int de_multi_create(const int *device_ids, int ndev, int64_t halo_bytes, de_multi **out);
+int de_multi_destroy(de_multi *M);
+int de_multi_size(const de_multi *M, int *ndev);
+/* rank r's context (borrowed; owned by M): for profiling / launch counts or rank-level calls from r's own thread */
+int de_multi_context(de_multi *M, int rank, de_context **ctx);
+const char *de_multi_last_error(const de_multi *M);
+int de_multi_launch_count(const de_multi *M, int64_t *count);
+int de_multi_standard_largest(de_multi *M, int64_t n, int64_t nnz, const int64_t *rowptr, const int64_t *col,
+                              const double *val, int64_t row_align, double shift, double tol, int maxiter, int nev,
+                              const double *start_panel8, double *eval, double *evec, int verbose, int *iterations);
+int de_multi_standard_lobpcg(de_multi *M, int64_t n, int64_t nnz, const int64_t *rowptr, const int64_t *col,
+                             const double *val, int64_t row_align, double tol, int maxiter, int nev,
+                             const double *start_panel8, double *eval, double *evec, int verbose, int *iterations);
+int de_multi_generalized_lobpcg(de_multi *M, int64_t n, int64_t nnz, const int64_t *rowptr, const int64_t *col,
+                                const double *val, int64_t b_nnz, const int64_t *b_rowptr, const int64_t *b_col,
+                                const double *b_val, int64_t row_align, double tol, int maxiter, int nev,
+                                const double *start_panel8, double *eval, double *evec, int verbose, int *iterations);
 
 /* ---- LOBPCG drivers -------------------------------------------------------------------------------------
  * NEW: the reference has no LOBPCG (its drivers are eigensolver.hh:28-112, :116-198, :204-351); BASELINE.json names

@@ -59,9 +59,27 @@ int main(int argc, char **argv)
   const int N = argc > 2 ? std::atoi(argv[2]) : 12;
   const int nev = argc > 3 ? std::atoi(argv[3]) : 8;
   const double tol = argc > 4 ? std::atof(argv[4]) : 1e-10;
+  // 5th argument: comma-separated CUDA ordinals, e.g. "0,1" (or "0,0": two ranks on one GPU) -> the drivers run
+  // row-partitioned through the single-process multi-GPU front end (ini key parallel.numgpus of the driver program)
+  const std::string devs = argc > 5 ? argv[5] : "";
   const std::size_t n = (std::size_t)N * N;
   try
   {
+    if (!devs.empty())
+    {
+      std::vector<int> d;
+      for (std::size_t i = 0; i < devs.size();)
+      {
+        const std::size_t j = devs.find(',', i);
+        d.push_back(std::atoi(devs.substr(i, j == std::string::npos ? j : j - i).c_str()));
+        if (j == std::string::npos)
+          break;
+        i = j + 1;
+      }
+      de_b200::Parallel::instance().set_devices(d);
+      de_b200::Parallel::instance().set_row_align(N); // one grid line of the 2D grid
+      std::printf("gpus %d\n", de_b200::Parallel::instance().num_gpus());
+    }
     std::vector<double> eval(nev);
     std::vector<std::vector<double>> evec(nev, std::vector<double>(n));
     if (mode == "largest")

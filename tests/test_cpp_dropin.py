@@ -84,3 +84,24 @@ def test_dropin_kernels(oracle):
     assert np.abs(dp - ref).max() <= 1e-12 * np.abs(ref).max()
     assert float(vals["ortho_defect"]) < 1e-13
     assert "number of cols must be a multiple of block size" in vals["caught"]
+
+
+@pytest.mark.gpu
+def test_dropin_multi_gpu_from_cpp(oracle):
+    """`StandardLargest(A, ...)` of the C++ drop-in header on several ranks without Python / MPI / NCCL (C ABI
+    de_multi_*). On a one-GPU box the ranks share ordinal 0."""
+    import torch
+
+    have = max(torch.cuda.device_count(), 1)
+    for ranks in (2, 4):
+        devs = ",".join(str(r % have) for r in range(ranks))
+        rc, vals, text = run("largest", 24, 8, 1e-10, devs)
+        assert rc == 0, text
+        assert vals["gpus"] == str(ranks)
+        ev = np.array([float(x) for x in vals["eval"].split()])
+        ref, V, k = oracle.standard_largest(M.laplacian_dirichlet_2d(24), 0.0, 1e-10, 4000, 8)
+        assert np.abs(ev - ref).max() <= 1e-10 * np.abs(ref).max()
+        rc, vals, text = run("lobpcg", 24, 8, 1e-9, devs)
+        assert rc == 0, text
+        ev = np.array([float(x) for x in vals["eval"].split()])
+        assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(24)[:8]).max() <= 1e-9 * 8.0

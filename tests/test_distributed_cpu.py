@@ -72,6 +72,35 @@ def _worker(rank, world, port, shape, kind, ret):
                 if dst == rank:
                     halo_peer[off:off + len(rows)] = rows
         peer_ok = bool(np.array_equal(halo_peer, halo)) and max_halo >= len(halo_global)
+        # --- the same plan from the C ABI's host-only planner (de_halo_plan_peers: what de_matrix_create_rowblock and
+        # the single-process de_multi_* front end use) fed with all-gathered counts and halo lists
+        import ctypes as C
+
+        from dune_eigensolver_b200 import capi
+
+        allc = [None] * world
+        dist.all_gather_object(allc, [int(c) for c in recv_counts])
+        alll = [None] * world
+        dist.all_gather_object(alll, [int(g) for g in halo_global])
+        stride = max(1, max(len(x) for x in alll))
+        counts_all = capi.i64(np.asarray(allc).reshape(-1))
+        lists_all = np.full((world, stride), -1, dtype=np.int64)
+        for q, lst in enumerate(alll):
+            lists_all[q, :len(lst)] = lst
+        npeers, sym, mx = C.c_int(0), C.c_int(0), C.c_int64(0)
+        pr = np.zeros(world, dtype=np.int32)
+        rc, so, dep = (np.zeros(world + 1, dtype=np.int64) for _ in range(3))
+        sr = np.zeros(max(1, int(sum(allc[q][rank] for q in range(world) if q != rank))), dtype=np.int64)
+        capi.check(capi.lib().de_halo_plan_peers(world, rank, capi.i64ptr(capi.i64(part)), capi.i64ptr(counts_all),
+                                                 capi.i64ptr(lists_all), stride, C.byref(npeers), capi.i32ptr(pr),
+                                                 capi.i64ptr(rc), capi.i64ptr(so), capi.i64ptr(sr), capi.i64ptr(dep),
+                                                 C.byref(mx), C.byref(sym)))
+        k = npeers.value
+        c_ok = (list(pr[:k]) == peers and list(dep[:k]) == [int(d) for d in deposits] and mx.value == max_halo
+                and sym.value == 1 and list(rc[:k]) == [int(recv_counts[p]) for p in peers]
+                and all(np.array_equal(sr[so[i]:so[i + 1]], send_lists.get(p, np.zeros(0, dtype=np.int64)))
+                        for i, p in enumerate(peers)))
+        peer_ok = peer_ok and bool(c_ok)
         import scipy.sparse as sp
 
         Aloc = sp.csr_matrix((v, col_local, rp), shape=(n_owned, n_owned + len(halo_global)))
