@@ -46,6 +46,7 @@ SIGNATURES = {
     "de_multi_create": [_ip, C.c_int, C.c_int64, _vpp],
     "de_multi_destroy": [_vp],
     "de_multi_size": [_vp, _ip],
+    "de_multi_set_timeout": [_vp, C.c_double],
     "de_multi_context": [_vp, C.c_int, _vpp],
     "de_multi_last_error": [_vp],
     "de_multi_launch_count": [_vp, _i64p],

@@ -1,6 +1,8 @@
 // de_dense.cu -- tall-skinny dense kernels of the path and their launch logic: partial-sum reductions with fused tails
 // (all-reduce, Cholesky, convergence test), diag-dot, Gram, block update / projection, CholQR2 (B-)orthonormalisation.
 // Replaces dot_products_* / orthonormalize_* / B_orthonormalize_* of the reference (kernels_cpp.hh:7-96, :121-591).
+#include <cstdlib>
+
 #include "de_internal.hpp"
 #include "kernels_dense.cuh"
 #include "kernels_sparse.cuh"
@@ -29,7 +31,7 @@ namespace dei
       ctx->tail_did_op = false;
     else
     {
-      de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(p.conv.k, p.conv.m, p.conv.shift, p.conv.tol, ctx->dDP(), p.conv.s_prev,
+      DE_REG(de::convergence_kernel), de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(p.conv.k, p.conv.m, p.conv.shift, p.conv.tol, ctx->dDP(), p.conv.s_prev,
                                                         p.conv.hist, p.conv.flags);
       DE_LAUNCH_CHECK(ctx);
     }
@@ -76,7 +78,7 @@ namespace dei
         ctx->tail_armed = false;
         ctx->tail_did_allreduce = true;
         ctx->tail_did_op = true;
-        DE_CUDA(ctx, launch_pdl(de::reduce_tail_kernel, dim3((len + p.m + 31) / 32), block, 0, ctx->stream, partials, nparts,
+        DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::reduce_tail_kernel), dim3((len + p.m + 31) / 32), block, 0, ctx->stream, partials, nparts,
                                 len, ctx->dDG(), ctx->done_ptr, t));
         DE_LAUNCH_CHECK(ctx);
         return DE_OK;
@@ -94,13 +96,13 @@ namespace dei
       ctx->tail_armed = false;
       ctx->tail_did_allreduce = true;
       ctx->tail_did_op = true;
-      DE_CUDA(ctx, launch_pdl(de::reduce_tail_kernel, dim3((len + 31) / 32), block, 0, ctx->stream, partials, nparts, len, out,
+      DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::reduce_tail_kernel), dim3((len + 31) / 32), block, 0, ctx->stream, partials, nparts, len, out,
                               ctx->done_ptr, t));
       DE_LAUNCH_CHECK(ctx);
       return DE_OK;
     }
     ctx->tail_armed = false;
-    de::reduce_partials_kernel<<<(len + 31) / 32, block, 0, ctx->stream>>>(partials, nparts, len, out, ctx->done_ptr);
+    DE_REG(de::reduce_partials_kernel), de::reduce_partials_kernel<<<(len + 31) / 32, block, 0, ctx->stream>>>(partials, nparts, len, out, ctx->done_ptr);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -115,6 +117,10 @@ namespace dei
     pa.epoch = epoch;
     pa.done = ctx->done_ptr;
     pa.err = ctx->dticket + 1;
+    pa.timeout = ctx->peer_timeout_cycles;
+    static const bool trace = std::getenv("DE_TRACE_PEER") != nullptr; // debugging aid only: no behaviour depends on it
+    if (trace)
+      std::fprintf(stderr, "[de peer] rank %d epoch %llu (ar %llu halo %llu)\n", ctx->rank, epoch, ctx->ar_epoch, ctx->halo_epoch);
     return pa;
   }
 
@@ -130,7 +136,7 @@ namespace dei
     if (ctx->peer_ready && count <= (size_t)de::kPeerSlotDoubles)
     {
       ProfScope prof(ctx, DE_PROF_SMALL);
-      de::peer_allreduce_kernel<<<1, 1024, 0, ctx->stream>>>(peer_args(ctx, ++ctx->ar_epoch), buf, (int)count);
+      DE_REG(de::peer_allreduce_kernel), de::peer_allreduce_kernel<<<1, 1024, 0, ctx->stream>>>(peer_args(ctx, ++ctx->ar_epoch), buf, (int)count);
       DE_LAUNCH_CHECK(ctx);
       return DE_OK;
     }
@@ -150,7 +156,7 @@ namespace dei
     double *part = reduction_partials(ctx);
     {
       ProfScope prof(ctx, DE_PROF_DOT);
-      de::diag_dot_kernel<<<grid, block, 0, ctx->stream>>>(n, X, m, Y, m, m, part);
+      DE_REG(de::diag_dot_kernel), de::diag_dot_kernel<<<grid, block, 0, ctx->stream>>>(n, X, m, Y, m, m, part);
     }
     DE_LAUNCH_CHECK(ctx);
     DE_TRY(reduce_partials(ctx, part, grid, m, out));
@@ -185,7 +191,7 @@ namespace dei
       a.done = ctx->done_ptr;
       {
         ProfScope prof(ctx, DE_PROF_UPDATE);
-        DE_CUDA(ctx, launch_pdl(de::ts2_update_kernel<M, DO_GRAM>, dim3(grid2), dim3(C2::THREADS), C2::SMEM, ctx->stream, a));
+        DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::ts2_update_kernel<M, DO_GRAM>), dim3(grid2), dim3(C2::THREADS), C2::SMEM, ctx->stream, a));
       }
       DE_LAUNCH_CHECK(ctx);
       if (DO_GRAM)
@@ -203,7 +209,7 @@ namespace dei
       a.done = ctx->done_ptr;
       {
         ProfScope prof(ctx, DE_PROF_GRAM);
-        DE_CUDA(ctx, launch_pdl(de::ts2_gram_kernel<M>, dim3(grid3), dim3(de::kTg2Threads), C3::SMEM, ctx->stream, a));
+        DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::ts2_gram_kernel<M>), dim3(grid3), dim3(de::kTg2Threads), C3::SMEM, ctx->stream, a));
       }
       DE_LAUNCH_CHECK(ctx);
       return reduce_partials(ctx, a.partials, grid3, M * M, gram_out);
@@ -222,7 +228,7 @@ namespace dei
     a.done = ctx->done_ptr;
     {
       ProfScope prof(ctx, DO_UPDATE ? DE_PROF_UPDATE : DE_PROF_GRAM);
-      de::tall_skinny_kernel<M, DO_UPDATE, DO_GRAM, UPPER, SAME><<<grid, C::THREADS, smem, ctx->stream>>>(a);
+      DE_REG(de::tall_skinny_kernel<M, DO_UPDATE, DO_GRAM, UPPER, SAME>), de::tall_skinny_kernel<M, DO_UPDATE, DO_GRAM, UPPER, SAME><<<grid, C::THREADS, smem, ctx->stream>>>(a);
     }
     DE_LAUNCH_CHECK(ctx);
     if (DO_GRAM)
@@ -257,7 +263,7 @@ namespace dei
     double *part = reduction_partials(ctx);
     {
       ProfScope prof(ctx, DE_PROF_GRAM);
-      de::gram_kernel<M, UPPER, SAME><<<grid, C::THREADS, 0, ctx->stream>>>(n, X, ldx, Y, ldy, part);
+      DE_REG(de::gram_kernel<M, UPPER, SAME>), de::gram_kernel<M, UPPER, SAME><<<grid, C::THREADS, 0, ctx->stream>>>(n, X, ldx, Y, ldy, part);
     }
     DE_LAUNCH_CHECK(ctx);
     return reduce_partials(ctx, part, grid, M * M, out);
@@ -334,7 +340,7 @@ namespace dei
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / C::SMEM_BYTES));
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * per_sm));
     ProfScope prof(ctx, DE_PROF_UPDATE);
-    de::update_kernel<M, MODE><<<grid, C::THREADS, C::SMEM_BYTES, ctx->stream>>>(n, X, ldx, R, Y, ldy, upper);
+    DE_REG(de::update_kernel<M, MODE>), de::update_kernel<M, MODE><<<grid, C::THREADS, C::SMEM_BYTES, ctx->stream>>>(n, X, ldx, R, Y, ldy, upper);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -395,10 +401,10 @@ namespace dei
     }
     ProfScope prof(ctx, DE_PROF_SMALL);
     if (m <= 32)
-      de::chol_inverse2_kernel<32><<<1, 1024, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag,
+      DE_REG(de::chol_inverse2_kernel<32>), de::chol_inverse2_kernel<32><<<1, 1024, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag,
                                                                 const_cast<int *>(ctx->done_ptr));
     else
-      de::chol_inverse2_kernel<64><<<1, 1024, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag,
+      DE_REG(de::chol_inverse2_kernel<64>), de::chol_inverse2_kernel<64><<<1, 1024, 0, ctx->stream>>>(m, G, Rinv, ctx->dstatus, info, identity_flag,
                                                                 const_cast<int *>(ctx->done_ptr));
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
@@ -498,7 +504,14 @@ namespace dei
       DE_CUDA(ctx, cudaMemcpyAsync(ctx->hflags + 7, ctx->dticket + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->hflags[7] != 0)
-      return set_error(ctx, DE_ERR_NCCL, "NVLink peer window: a neighbour rank did not arrive within 30 s");
+    {
+      const int w = ctx->hflags[7];
+      return set_error(ctx, DE_ERR_NCCL,
+                       std::string("NVLink peer window: rank ") + std::to_string(ctx->rank) + " gave up waiting for the " +
+                           ((w & 15) == 2 ? "halo rows" : "all-reduce contribution") + " of rank " + std::to_string((w >> 4) & 15) +
+                           " (epoch " + std::to_string((w >> 8) & 0xfff) + ", flag still at " + std::to_string((w >> 20) & 0x7ff) + "; this rank has issued " + std::to_string(ctx->ar_epoch) +
+                           " all-reduces and " + std::to_string(ctx->halo_epoch) + " halo exchanges)");
+    }
     if (count > 0 && hdst != ctx->hsmall)
       std::memcpy(hdst, ctx->hsmall, count * sizeof(double));
     if (*ctx->hstatus != 0)

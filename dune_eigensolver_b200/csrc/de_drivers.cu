@@ -26,7 +26,7 @@ namespace dei
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (size_t)(200 * 1024) / K::SMEM_BYTES));
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, (long long)ctx->sm_count * per_sm));
     ProfScope prof(ctx, DE_PROF_UPDATE);
-    de::lincomb_kernel<M><<<grid, K::THREADS, K::SMEM_BYTES, ctx->stream>>>(n, ns, S[0], ns > 1 ? S[1] : nullptr,
+    DE_REG(de::lincomb_kernel<M>), de::lincomb_kernel<M><<<grid, K::THREADS, K::SMEM_BYTES, ctx->stream>>>(n, ns, S[0], ns > 1 ? S[1] : nullptr,
                                                                            ns > 2 ? S[2] : nullptr, C, out, out2);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
@@ -96,7 +96,7 @@ namespace dei
       const long long pairs = n * m / 2;
       {
         ProfScope prof(ctx, DE_PROF_MISC);
-        de::residual_kernel<<<elementwise_grid(pairs), 256, 0, ctx->stream>>>(pairs, m, AX, BX, dtheta, W);
+        DE_REG(de::residual_kernel), de::residual_kernel<<<elementwise_grid(pairs), 256, 0, ctx->stream>>>(pairs, m, AX, BX, dtheta, W);
       }
       DE_LAUNCH_CHECK(ctx);
       DE_TRY(diag_dot_device(ctx, n, m, W, W, ctx->dDP()));
@@ -125,7 +125,7 @@ namespace dei
       DE_CUDA(ctx, cudaMemsetAsync(slots, 0, sizeof(double) * nr, ctx->stream));
       {
         ProfScope prof(ctx, DE_PROF_MISC);
-        de::gershgorin_kernel<<<elementwise_grid(A->n), 256, 0, ctx->stream>>>(
+        DE_REG(de::gershgorin_kernel), de::gershgorin_kernel<<<elementwise_grid(A->n), 256, 0, ctx->stream>>>(
             A->n, A->rowptr, A->col, A->val, ddinv, reinterpret_cast<unsigned long long *>(slots + ctx->rank));
       }
       DE_LAUNCH_CHECK(ctx);
@@ -145,14 +145,14 @@ namespace dei
     int cheb_start(Blk Z, Blk Zold, Blk R, double s)
     {
       ProfScope prof(ctx, DE_PROF_MISC);
-      de::cheb_start_kernel<<<row_grid(), row_block(), 0, ctx->stream>>>(n, m / 2, s, ddinv, R, Z, Zold);
+      DE_REG(de::cheb_start_kernel), de::cheb_start_kernel<<<row_grid(), row_block(), 0, ctx->stream>>>(n, m / 2, s, ddinv, R, Z, Zold);
       DE_LAUNCH_CHECK(ctx);
       return DE_OK;
     }
     int cheb_step(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta)
     {
       ProfScope prof(ctx, DE_PROF_MISC);
-      de::cheb_step_kernel<<<row_grid(), row_block(), 0, ctx->stream>>>(n, m / 2, alpha, beta, ddinv, Z, R, AZ, Zold);
+      DE_REG(de::cheb_step_kernel), de::cheb_step_kernel<<<row_grid(), row_block(), 0, ctx->stream>>>(n, m / 2, alpha, beta, ddinv, Z, R, AZ, Zold);
       DE_LAUNCH_CHECK(ctx);
       return DE_OK;
     }
@@ -342,7 +342,7 @@ extern "C"
         ctx->tail_did_op = false;
       else
       {
-        de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(k, m, shift, tol, ctx->dDP(), s_prev, hist, ctx->dflags);
+        DE_REG(de::convergence_kernel), de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(k, m, shift, tol, ctx->dDP(), s_prev, hist, ctx->dflags);
         DE_LAUNCH_CHECK(ctx);
       }
       ctx->tail_armed = false;

@@ -81,6 +81,8 @@ struct de_context
   void *xfer = nullptr;       // XferEngine: pinned staging buffers and copy streams (created on first use)
   // NVLink peer window (kernels_peer.cuh); peer_ready once every rank's window is mapped
   bool peer_ready = false;
+  bool pdl = true;      // programmatic dependent launch of the loop kernels (off when ranks share a device)
+  long long peer_timeout_cycles = 60000000000LL; // spins on peer flags give up after this many clocks (~30 s)
   bool peer_ipc = true; // peer windows were opened from CUDA IPC handles (else: same-process allocations, de_multi.cu)
   unsigned char *window = nullptr;
   size_t window_bytes = 0, halo_cap = 0;
@@ -333,7 +335,8 @@ namespace dei
   /** launch with programmatic stream serialization: the kernel's CTAs may be scheduled while the preceding kernel of the
    *  stream drains; the kernel itself waits for that kernel's completion in pdl_prologue() (kernels_sparse.cuh) */
   template <class... KArgs, class... Args>
-  cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
+  cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                         Args &&...args)
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -344,7 +347,9 @@ namespace dei
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    // pdl == false (several ranks sharing ONE device, de_multi.cu): CTAs that sit resident in griddepcontrol.wait behind a
+    // reduction tail spinning on a peer's flag would keep that peer's kernels off the SMs -- a deadlock
+    cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
   }
 
@@ -437,6 +442,27 @@ namespace dei
 
   // ---- de_trsv.cu ---------------------------------------------------------------------------------------------
   int factor_apply_device(de_context *ctx, const de_factor *F, const double *X, double *Y, int m);
+
+  /** Every kernel this library can launch, collected at LOAD time: each launch site names its kernel through DE_REG /
+   *  DE_KERNEL, which odr-uses a static member of KernelReg<&kernel> whose initialiser adds the kernel to the registry.
+   *  preload_kernels() then forces the (lazily loaded, CUDA_MODULE_LOADING) device code of all of them onto the current
+   *  device. Needed where several ranks live in ONE process (de_multi.cu): the first launch of a not-yet-loaded kernel
+   *  blocks while any kernel of the process is resident on the device (measured: tools/micro/spin_probe.cu), and a
+   *  reduction tail spinning on a peer's flag would wait for exactly that peer forever. */
+  void register_kernel(const void *func);
+  int preload_kernels(de_context *ctx);
+  template <auto K>
+  struct KernelReg
+  {
+    static inline const bool reg = (register_kernel((const void *)K), true);
+    static auto get()
+    {
+      (void)reg;
+      return K;
+    }
+  };
+#define DE_REG(...) ((void)dei::KernelReg<&__VA_ARGS__>::reg)
+#define DE_KERNEL(...) (dei::KernelReg<&__VA_ARGS__>::get())
 
   /** dynamic shared memory opt-in of a kernel, once per (context, kernel): the attribute is per DEVICE */
   int ensure_func_smem(de_context *ctx, const void *func, size_t bytes);

@@ -210,9 +210,18 @@ namespace
     status[0] = run_rank(M, 0, c, part, errs[0], &iters[0]);
     for (auto &t : th)
       t.join();
+    // a rank that fails stops contributing, and its peers then time out waiting for it: report every rank's message
+    int first = DE_OK;
+    std::string all;
     for (int r = 0; r < R; ++r)
       if (status[r] != DE_OK)
-        return multi_error(M, status[r], "rank " + std::to_string(r) + ": " + errs[r]);
+      {
+        if (first == DE_OK || (first == DE_ERR_NCCL && status[r] != DE_ERR_NCCL))
+          first = status[r];
+        all += (all.empty() ? "rank " : " | rank ") + std::to_string(r) + ": " + errs[r];
+      }
+    if (first != DE_OK)
+      return multi_error(M, first, all);
     if (c.iterations)
       *c.iterations = iters[0];
     return DE_OK;
@@ -365,6 +374,14 @@ extern "C"
       *out = M;
       return DE_OK;
     }
+    // several ranks on one device (test configuration): no programmatic dependent launch -- see launch_pdl
+    bool shared_device = false;
+    for (int r = 0; r < ndev; ++r)
+      for (int q = 0; q < r; ++q)
+        shared_device = shared_device || device_ids[q] == device_ids[r];
+    if (shared_device)
+      for (int r = 0; r < ndev; ++r)
+        M->ctx[r]->pdl = false;
     // windows of the NVLink data path: ordinary allocations, mapped into the peers by enabling peer access
     const size_t cap = (((size_t)(halo_bytes > 0 ? halo_bytes : (int64_t)128 << 20)) + 255) & ~(size_t)255;
     for (int r = 0; r < ndev; ++r)
@@ -394,6 +411,9 @@ extern "C"
     for (int r = 0; r < ndev; ++r)
     {
       de_context *c = M->ctx[r];
+      // no kernel may be loaded lazily once ranks can spin on each other's flags (see preload_kernels)
+      if (preload_kernels(c) != DE_OK)
+        return bail(DE_ERR_CUDA, std::string("de_multi_create: loading the kernels failed: ") + de_last_error_string(c));
       for (int q = 0; q < ndev; ++q)
         c->peer_base[q] = M->ctx[q]->window;
       c->peer_ipc = false;
@@ -417,6 +437,19 @@ extern "C"
     for (de_context *c : M->ctx)
       de_context_destroy(c);
     delete M;
+    return DE_OK;
+  }
+
+  int de_multi_set_timeout(de_multi *M, double seconds)
+  {
+    if (!M || !(seconds > 0.0))
+      return multi_error(M, DE_ERR_INVALID, "de_multi_set_timeout: bad arguments");
+    for (de_context *c : M->ctx)
+    {
+      int khz = 2000000;
+      cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+      c->peer_timeout_cycles = (long long)(seconds * 1e3 * (double)khz);
+    }
     return DE_OK;
   }
 

@@ -54,6 +54,25 @@ namespace dei
   }
 
 
+  static std::vector<const void *> &kernel_registry()
+  {
+    static std::vector<const void *> *v = new std::vector<const void *>(); // used during static initialisation of every unit
+    return *v;
+  }
+
+  void register_kernel(const void *func) { kernel_registry().push_back(func); }
+
+  int preload_kernels(de_context *ctx)
+  {
+    DE_TRY(bind_device(ctx));
+    for (const void *f : kernel_registry())
+    {
+      cudaFuncAttributes a;
+      DE_CUDA(ctx, cudaFuncGetAttributes(&a, f)); // loads the function's module on this device
+    }
+    return DE_OK;
+  }
+
   int ensure_func_smem(de_context *ctx, const void *func, size_t bytes)
   {
     auto it = ctx->func_smem.find(func);
@@ -97,8 +116,10 @@ namespace dei
   };
   DevCache &dev_cache()
   {
-    static DevCache c;
-    return c;
+    // never destroyed: contexts owned by objects with static storage duration (the drop-in headers' Parallel singleton)
+    // are torn down during exit, possibly after the destructors of this library's own statics have run
+    static DevCache *c = new DevCache();
+    return *c;
   }
   constexpr size_t kDevCacheMaxIdle = (size_t)96 << 30;
 
@@ -419,7 +440,7 @@ namespace dei
       return DE_OK;
     const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 8));
     ProfScope prof(ctx, DE_PROF_MISC);
-    de::panel8_convert_kernel<<<grid, 256, 0, ctx->stream>>>(n, m, src, dst, to_rowmajor);
+    DE_REG(de::panel8_convert_kernel), de::panel8_convert_kernel<<<grid, 256, 0, ctx->stream>>>(n, m, src, dst, to_rowmajor);
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -447,7 +468,7 @@ namespace dei
     DE_TRY(ensure_stage(ctx, bytes));
     {
       ProfScope prof(ctx, DE_PROF_MISC);
-      de::extract_columns_kernel<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, m, nev, Q, ctx->stage);
+      DE_REG(de::extract_columns_kernel), de::extract_columns_kernel<<<(unsigned)((n + 31) / 32), 256, 0, ctx->stream>>>(n, m, nev, Q, ctx->stage);
     }
     DE_LAUNCH_CHECK(ctx);
     return download_parallel(ctx, evec, ctx->stage, bytes);
@@ -517,8 +538,8 @@ extern "C"
       }
       ctx->own_stream = true;
     }
-    bool ok = cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming) == cudaSuccess &&
+    // (the second stream of the NCCL halo path is created by de_context_init_comm: one stream per context otherwise)
+    bool ok = cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming) == cudaSuccess &&
               cudaMalloc((void **)&ctx->partials, kPartialDoubles * sizeof(double)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->dsmall, kSmall * sizeof(double)) == cudaSuccess &&
@@ -691,6 +712,8 @@ extern "C"
     DE_TRY(bind_device(ctx));
     ncclUniqueId id;
     std::memcpy(&id, id128, 128);
+    if (!ctx->comm_stream)
+      DE_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
     DE_NCCL(ctx, nccl_api().CommInitRank(&ctx->comm, nranks, id, rank));
     ctx->rank = rank;
     ctx->nranks = nranks;

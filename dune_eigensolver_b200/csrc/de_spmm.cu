@@ -48,9 +48,9 @@ namespace dei
       grid = (int)std::min<long long>(need, (long long)ctx->sm_count * 3);
 #define DE_SPMM_V2(T)                                                                                        \
   if (halo)                                                                                                  \
-    de::spmm_kernel_v2<T, DOT, true><<<grid, 256, 0, ctx->stream>>>(a);                                      \
+    DE_REG(de::spmm_kernel_v2<T, DOT, true>), de::spmm_kernel_v2<T, DOT, true><<<grid, 256, 0, ctx->stream>>>(a);                                      \
   else                                                                                                       \
-    de::spmm_kernel_v2<T, DOT, false><<<grid, 256, 0, ctx->stream>>>(a);
+    DE_REG(de::spmm_kernel_v2<T, DOT, false>), de::spmm_kernel_v2<T, DOT, false><<<grid, 256, 0, ctx->stream>>>(a);
       switch (tpr)
       {
       case 4:
@@ -72,16 +72,16 @@ namespace dei
       switch (tpr)
       {
       case 4:
-        de::spmm_kernel<4, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+        DE_REG(de::spmm_kernel<4, 1, DOT>), de::spmm_kernel<4, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
         break;
       case 8:
-        de::spmm_kernel<8, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+        DE_REG(de::spmm_kernel<8, 1, DOT>), de::spmm_kernel<8, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
         break;
       case 16:
-        de::spmm_kernel<16, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+        DE_REG(de::spmm_kernel<16, 1, DOT>), de::spmm_kernel<16, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
         break;
       default:
-        de::spmm_kernel<32, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
+        DE_REG(de::spmm_kernel<32, 1, DOT>), de::spmm_kernel<32, 1, DOT><<<grid, 256, 0, ctx->stream>>>(a);
         break;
       }
     DE_LAUNCH_CHECK(ctx);
@@ -194,9 +194,9 @@ namespace dei
     DE_TRY(ensure_func_smem(ctx, (const void *)de::spmm_staged_kernel<T, DOT, true>, smem));                 \
     DE_TRY(ensure_func_smem(ctx, (const void *)de::spmm_staged_kernel<T, DOT, false>, smem));                \
     if (halo)                                                                                                \
-      de::spmm_staged_kernel<T, DOT, true><<<grid, 256, smem, ctx->stream>>>(a);                             \
+      DE_REG(de::spmm_staged_kernel<T, DOT, true>), de::spmm_staged_kernel<T, DOT, true><<<grid, 256, smem, ctx->stream>>>(a);                             \
     else                                                                                                     \
-      de::spmm_staged_kernel<T, DOT, false><<<grid, 256, smem, ctx->stream>>>(a);                            \
+      DE_REG(de::spmm_staged_kernel<T, DOT, false>), de::spmm_staged_kernel<T, DOT, false><<<grid, 256, smem, ctx->stream>>>(a);                            \
   }
     switch (tpr)
     {
@@ -273,7 +273,7 @@ namespace dei
       a.info = d_info;
       {
         ProfScope prof(ctx, DE_PROF_MISC);
-        de::brb_build_kernel<false><<<ntiles, de::kBldThreads, 0, ctx->stream>>>(a);
+        DE_REG(de::brb_build_kernel<false>), de::brb_build_kernel<false><<<ntiles, de::kBldThreads, 0, ctx->stream>>>(a);
       }
       DE_LAUNCH_CHECK(ctx);
       std::vector<int4> info((size_t)ntiles);
@@ -318,7 +318,7 @@ namespace dei
       a.ucol = B.ucol;
       {
         ProfScope prof(ctx, DE_PROF_MISC);
-        de::brb_build_kernel<true><<<ntiles, de::kBldThreads, 0, ctx->stream>>>(a);
+        DE_REG(de::brb_build_kernel<true>), de::brb_build_kernel<true><<<ntiles, de::kBldThreads, 0, ctx->stream>>>(a);
       }
       DE_LAUNCH_CHECK(ctx);
       std::vector<int4> tiles;
@@ -372,7 +372,7 @@ namespace dei
   {
     DE_TRY(ensure_func_smem(ctx, (const void *)de::spmm_brb_kernel<NP, DOT, HALO, GRAM>, kBrbMaxSmem));
     const size_t smem = de::spmm_brb_smem_bytes(NP, a.blob_cap16, a.xs_cap, a.stages);
-    DE_CUDA(ctx, launch_pdl(de::spmm_brb_kernel<NP, DOT, HALO, GRAM>, dim3(grid), dim3(de::brb_threads(GRAM)), smem, ctx->stream, a));
+    DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::spmm_brb_kernel<NP, DOT, HALO, GRAM>), dim3(grid), dim3(de::brb_threads(GRAM)), smem, ctx->stream, a));
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -523,7 +523,7 @@ namespace dei
           const long long total = A->n_send * (m / 2);
           const int grid = (int)std::min<long long>((total + 255) / 256, ctx->sm_count * 4);
           ProfScope prof(ctx, DE_PROF_MISC);
-          de::halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(pa, h);
+          DE_REG(de::halo_push_kernel), de::halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(pa, h);
           DE_LAUNCH_CHECK(ctx);
         }
       }
@@ -540,7 +540,7 @@ namespace dei
           const long long total = A->n_send * (m / 2);
           const int grid = (int)std::min<long long>((total + 255) / 256, ctx->sm_count * 8);
           ProfScope prof(ctx, DE_PROF_MISC);
-          de::pack_rows_kernel<<<grid, 256, 0, ctx->stream>>>(A->n_send, A->send_rows, m, X, A->send_buf);
+          DE_REG(de::pack_rows_kernel), de::pack_rows_kernel<<<grid, 256, 0, ctx->stream>>>(A->n_send, A->send_rows, m, X, A->send_buf);
           DE_LAUNCH_CHECK(ctx);
         }
         DE_CUDA(ctx, cudaEventRecord(ctx->ev_pack, ctx->stream));
@@ -581,7 +581,7 @@ namespace dei
           if (A->recv_count[p] > 0)
             pl.rank[pl.n++] = A->peer[p];
         ProfScope prof(ctx, DE_PROF_MISC);
-        de::halo_wait_kernel<<<1, 32, 0, ctx->stream>>>(pa, pl);
+        DE_REG(de::halo_wait_kernel), de::halo_wait_kernel<<<1, 32, 0, ctx->stream>>>(pa, pl);
         DE_LAUNCH_CHECK(ctx);
       }
       else

@@ -95,11 +95,11 @@ namespace dei
     {
       ProfScope prof(ctx, DE_PROF_TRSV);
       if (seg.chain)
-        de::trsv_chain_kernel<LC><<<1, 1024, 0, ctx->stream>>>(a, S.level_ptr, seg.a, seg.b);
+        DE_REG(de::trsv_chain_kernel<LC>), de::trsv_chain_kernel<LC><<<1, 1024, 0, ctx->stream>>>(a, S.level_ptr, seg.a, seg.b);
       else
       {
         const int first = S.h_level_ptr[seg.a], count = S.h_level_ptr[seg.a + 1] - first;
-        de::trsv_level_kernel<LC><<<(count + 7) / 8, 256, 0, ctx->stream>>>(a, first, count);
+        DE_REG(de::trsv_level_kernel<LC>), de::trsv_level_kernel<LC><<<(count + 7) / 8, 256, 0, ctx->stream>>>(a, first, count);
       }
       DE_LAUNCH_CHECK(ctx);
     }
@@ -147,7 +147,7 @@ namespace dei
     const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 8));
     {
       ProfScope prof(ctx, DE_PROF_TRSV);
-      de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->P, F->rowscale, X, F->W, 0);
+      DE_REG(de::permute_rows_kernel), de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->P, F->rowscale, X, F->W, 0);
     }
     DE_LAUNCH_CHECK(ctx);
     // forward sweep over the levels of L, backward sweep over the levels of U: a fixed sequence of launches on the
@@ -195,7 +195,7 @@ namespace dei
     }
     {
       ProfScope prof(ctx, DE_PROF_TRSV);
-      de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->Q, nullptr, F->W, Y, 1);
+      DE_REG(de::permute_rows_kernel), de::permute_rows_kernel<<<grid, 256, 0, ctx->stream>>>(F->n, m, F->Q, nullptr, F->W, Y, 1);
     }
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;

@@ -21,6 +21,7 @@ namespace de
     unsigned long long epoch;           // of this operation; parity = epoch & 1
     const int *done;                    // converged driver loop: no-op (the same on every rank)
     int *err;                           // device error flag: a peer did not arrive
+    long long timeout;                  // clocks after which a spin on a peer flag gives up
   };
 
   struct HaloPushArgs

@@ -40,15 +40,17 @@ namespace de
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
   }
-  __device__ __forceinline__ bool peer_wait(const unsigned long long *flag, unsigned long long epoch, int *err)
+  /** what = 1: all-reduce contribution, 2: halo rows; the error word records what, from which rank and the epoch */
+  __device__ __forceinline__ bool peer_wait(const unsigned long long *flag, unsigned long long epoch, int *err,
+                                            long long timeout, int what = 1, int from = 0)
   {
     const long long t0 = clock64();
     while (ld_acquire_sys(flag) < epoch)
     {
-      if (clock64() - t0 > 60000000000LL) // ~30 s: ranks of a multi-process job can be seconds apart on the host
+      if (clock64() - t0 > timeout) // default ~30 s: ranks of a multi-process job can be seconds apart on the host
       {
-        if (err)
-          *err = 1;
+        if (err) // keep the FIRST failure: later waits of the same rank fail as a consequence
+          atomicCAS(err, 0, what | (from << 4) | (int)((epoch & 0xfffull) << 8) | (int)((ld_acquire_sys(flag) & 0x7ffull) << 20));
         return false;
       }
       __nanosleep(64);
@@ -85,7 +87,7 @@ namespace de
     if (tid < pa.nranks)
     {
       st_release_sys(peer_ar_flag(pa.base[tid], parity, pa.rank), pa.epoch);
-      peer_wait(peer_ar_flag(pa.base[pa.rank], parity, tid), pa.epoch, pa.err);
+      peer_wait(peer_ar_flag(pa.base[pa.rank], parity, tid), pa.epoch, pa.err, pa.timeout, 1, tid);
     }
     __threadfence_system();
     __syncthreads();
@@ -150,7 +152,7 @@ namespace de
       return;
     const int parity = (int)(pa.epoch & 1ull);
     if ((int)threadIdx.x < peers.n)
-      peer_wait(peer_halo_flag(pa.base[pa.rank], parity, peers.rank[threadIdx.x]), pa.epoch, pa.err);
+      peer_wait(peer_halo_flag(pa.base[pa.rank], parity, peers.rank[threadIdx.x]), pa.epoch, pa.err, pa.timeout, 2, peers.rank[threadIdx.x]);
     __threadfence_system();
   }
 

@@ -221,11 +221,13 @@ class Multi:
     """Single-process multi-GPU front end (C ABI de_multi_*): one host thread and one context per GPU inside the
     library, NVLink peer windows of the same process. devices may repeat an ordinal (several ranks on one GPU)."""
 
-    def __init__(self, devices, halo_bytes=0):
+    def __init__(self, devices, halo_bytes=0, timeout_s=None):
         self._h = C.c_void_p()
         d = capi.i32(list(devices))
         check(capi.lib().de_multi_create(capi.i32ptr(d), len(d), int(halo_bytes), C.byref(self._h)))
         self.ndev = len(d)
+        if timeout_s is not None:
+            self._check(capi.lib().de_multi_set_timeout(self._h, float(timeout_s)))
 
     def close(self):
         if self._h:

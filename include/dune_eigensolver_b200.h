@@ -274,6 +274,9 @@ typedef struct de_multi de_multi;
 int de_multi_create(const int *device_ids, int ndev, int64_t halo_bytes, de_multi **out);
 int de_multi_destroy(de_multi *M);
 int de_multi_size(const de_multi *M, int *ndev);
+/* a rank that waits longer than this for a peer's halo rows / all-reduce contribution gives up; the call then fails with
+ * DE_ERR_NCCL instead of hanging the GPU (default ~30 s) */
+int de_multi_set_timeout(de_multi *M, double seconds);
 /* rank r's context (borrowed; owned by M): for profiling / launch counts or rank-level calls from r's own thread */
 int de_multi_context(de_multi *M, int rank, de_context **ctx);
 const char *de_multi_last_error(const de_multi *M);

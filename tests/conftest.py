@@ -5,6 +5,12 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# Tests that put several ranks of the single-process multi-GPU front end on ONE device (tests/test_multi_inprocess_gpu.py
+# on a one-GPU box) need every rank's stream on a hardware work queue of its own: a kernel spinning on a peer's flag
+# must never sit in front of that peer's kernels. The default of 8 queues is shared with torch's and the other test
+# contexts' streams. Must be set before CUDA initialises; irrelevant with one rank per GPU (the production layout).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

@@ -101,7 +101,8 @@ def test_dropin_multi_gpu_from_cpp(oracle):
         ev = np.array([float(x) for x in vals["eval"].split()])
         ref, V, k = oracle.standard_largest(M.laplacian_dirichlet_2d(24), 0.0, 1e-10, 4000, 8)
         assert np.abs(ev - ref).max() <= 1e-10 * np.abs(ref).max()
-        rc, vals, text = run("lobpcg", 24, 8, 1e-9, devs)
-        assert rc == 0, text
-        ev = np.array([float(x) for x in vals["eval"].split()])
-        assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(24)[:8]).max() <= 1e-9 * 8.0
+        if have >= ranks:  # LOBPCG needs one GPU per rank (tests/test_multi_inprocess_gpu.py::test_partitioned_lobpcg)
+            rc, vals, text = run("lobpcg", 24, 8, 1e-9, devs)
+            assert rc == 0, text
+            ev = np.array([float(x) for x in vals["eval"].split()])
+            assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(24)[:8]).max() <= 1e-9 * 8.0
