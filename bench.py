@@ -47,6 +47,21 @@ ITERATIONS_TO_CONVERGENCE = {(100, "q1", 32, 2e-3): 41}
 NCU_DRAM_TRAFFIC_PER_LAUNCH = {(100, "q1", 32): 748.1e6}
 
 
+def ncu_traffic(grid, stencil, m):
+    """(bytes per launch, source) of the dominant kernel from the newest committed ncu capture: profiles/ncu_traffic.json
+    is written by tools/ncu_summary.py from an `ncu --set full` report of this very command and names the commit it was
+    taken at; the constant above (round 1's capture) is the fallback."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    key = "%d_%s_%d" % (grid, stencil, m)
+    try:
+        d = json.load(open(path))
+        e = d[key]
+        return float(e["dram_bytes_per_launch"]), "profiles/ncu_traffic.json: %s (commit %s)" % (e.get("source", "?"), e.get("commit", "?"))
+    except Exception:  # noqa: BLE001
+        v = NCU_DRAM_TRAFFIC_PER_LAUNCH.get((grid, stencil, m))
+        return v, "profiles/r01_ncu_kernels_final.csv (round-1 capture; no newer profiles/ncu_traffic.json entry)"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -68,6 +83,13 @@ def parse():
     ap.add_argument("--lobpcg-pencil-grid", type=int, default=128,
                     help="grid of the GeneralizedLOBPCG leg (stiffness + mass pencil, 64 eigenpairs: BASELINE.json "
                          "configs[2]); 0 skips it")
+    ap.add_argument("--no-c4", action="store_true", help="skip the configs[3] leg (256^3 high-contrast, N > 1 only)")
+    ap.add_argument("--c4-grid", type=int, default=256)
+    ap.add_argument("--no-c5", action="store_true", help="skip the configs[4] leg (block-width sweep on 200^3)")
+    ap.add_argument("--c5-grid", type=int, default=200)
+    ap.add_argument("--no-tight", action="store_true", help="skip the tight-tolerance StandardLargest leg")
+    ap.add_argument("--full-reference", action="store_true",
+                    help="--impl reference: every replica runs the COMPLETE solve (default: bounded sample, extrapolated)")
     return ap.parse_args()
 
 
@@ -165,7 +187,7 @@ def _replica(conf, barrier, out, idx):
     from oracle import oracle as O
     from dune_eigensolver_b200 import matrices as M
 
-    grid, stencil, nev, sample_iters = conf
+    grid, stencil, nev, sample_iters = conf[:4]
     orc = O.load_best()
     A = (M.q1_stiffness if stencil == "q1" else M.laplacian_fd)((grid,) * 3)
     rp, ci, v = (np.ascontiguousarray(A[0], dtype=np.int64), np.ascontiguousarray(A[1], dtype=np.int64),
@@ -177,6 +199,14 @@ def _replica(conf, barrier, out, idx):
         assert k == max(iters, 1), (k, iters)
         return time.perf_counter() - t0
 
+    if sample_iters <= 0:
+        # the COMPLETE solve with the workload's own tolerance (no extrapolation)
+        tol, maxiter = conf[4], conf[5]
+        barrier.wait()
+        t0 = time.perf_counter()
+        ev, V, k = orc.standard_largest((rp, ci, v), 0.0, tol, maxiter, nev)
+        out[idx] = (time.perf_counter() - t0, int(k), orc.kind)
+        return
     barrier.wait()
     t_short = run(1)
     barrier.wait()
@@ -196,7 +226,7 @@ def cpu_reference_sample(args, sample_iters, iterations_full, replicas=None):
     mpc = mp.get_context("spawn")  # the parent may hold a CUDA context: never fork it
     barrier = mpc.Barrier(P)
     out = mpc.Manager().dict()
-    conf = (args.grid, args.stencil, args.nev, sample_iters)
+    conf = (args.grid, args.stencil, args.nev, sample_iters, args.tol, args.maxiter)
     procs = [mpc.Process(target=_replica, args=(conf, barrier, out, i)) for i in range(P)]
     for p in procs:
         p.start()
@@ -204,6 +234,11 @@ def cpu_reference_sample(args, sample_iters, iterations_full, replicas=None):
         p.join()
     if len(out) != P:
         raise RuntimeError("a reference replica failed (is oracle/ built? run __graft_entry__.build())")
+    if sample_iters <= 0:
+        one = float(np.mean([t for t, _, _ in out.values()]))
+        its = sorted({k for _, k, _ in out.values()})
+        assert its == [iterations_full] or iterations_full is None, (its, iterations_full)
+        return one / P, one, P, list(out.values())[0][2]
     per_iter = float(np.mean([(tl - ts) / sample_iters for ts, tl, _ in out.values()]))
     fixed = float(np.mean([max(ts - (tl - ts) / sample_iters, 0.0) for ts, tl, _ in out.values()]))
     one = fixed + per_iter * iterations_full
@@ -224,21 +259,24 @@ def run_reference(args):
         note = "iterations-to-convergence unknown for this configuration: assumed 100"
     vals, ones = [], []
     kind, P = "port", 1
-    for s in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        tot, one, P, kind = cpu_reference_sample(args, args.cpu_sample_iters, iters)
-        if s >= args.warmup:
-            vals.append(tot)
-            ones.append(one)
-        if s == 0 and (time.perf_counter() - t0) * (args.warmup + args.steps) > 240:
-            # keep the whole run within a few minutes: one measured step stands for all
-            vals, ones = [tot], [one]
-            break
+    # First the bounded sample (a few iterations, extrapolated): it tells how long a complete solve takes. If one
+    # complete replica set fits the budget of this arm (a few minutes) it is RUN and reported -- a measured solve, not an
+    # extrapolation; the extrapolated figure is kept next to it.
+    tot_x, one_x, P, kind = cpu_reference_sample(args, args.cpu_sample_iters, iters)
+    full = args.full_reference or one_x <= 150.0
+    if full:
+        tot, one, P, kind = cpu_reference_sample(args, 0, iters if iters != 100 else None)
+        vals, ones = [tot], [one]
+    else:
+        vals, ones = [tot_x], [one_x]
     value = float(np.mean(vals))
     sample = ("%d independent replicas of the reference's single-threaded StandardLargest, one per host core (the "
-              "reference's multicore harness, src/dune-eigensolver.cc:756-773), each timed on %d iterations and "
-              "extrapolated to %d; one replica under full load needs %.1f s per solve, the node completes one solve "
-              "every %.2f s; %s" % (P, args.cpu_sample_iters, iters, float(np.mean(ones)), value, note))
+              "reference's multicore harness, src/dune-eigensolver.cc:756-773); %s; one replica under full load needs "
+              "%.1f s per solve, the node completes one solve every %.2f s (value = node-throughput time per solve, "
+              "NOT the latency of one solve); extrapolation from %d iterations: %.1f s / %.2f s; %s" %
+              (P, ("every replica ran the COMPLETE solve (%d iterations, tol %g): measured, not extrapolated" % (iters, args.tol))
+               if full else ("each timed on %d iterations and extrapolated to %d" % (args.cpu_sample_iters, iters)),
+               float(np.mean(ones)), value, args.cpu_sample_iters, one_x, tot_x, note))
     line = {
         "impl": "reference", "metric": "time-to-m-eigenpairs", "value": value, "unit": "s", "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
@@ -246,7 +284,9 @@ def run_reference(args):
         "config": {"workload": workload_name(args)},
         "cpu_baseline": {"value": value, "unit": "s", "cores": P,
                          "kind": "reference" if kind == "reference" else "port", "sample": sample,
-                         "single_replica_s": float(np.mean(ones))},
+                         "single_replica_s": float(np.mean(ones)), "measured_full_solve": bool(full),
+                         "extrapolated_from_sample": {"value": tot_x, "single_replica_s": one_x,
+                                                      "sample_iterations": args.cpu_sample_iters}},
         "e2e": {"value": value, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -351,6 +391,8 @@ def run_b200(args):
         launches = int(lt.item())
     ms_per_step = ms / args.steps
     iterations = iters_seen[-1]
+    spmm_format = dA.spmm_info()["format"]
+    peer_path = ctx.peer_ready()
 
     # ---- end to end through the reference-facing call with host buffers ------------------------------------
     e2e = None
@@ -386,6 +428,27 @@ def run_b200(args):
         e2e = {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "steps": e2e_steps, "api": "de_matrix_create_csr + de_standard_largest (host CSR in, host eigenvectors out)"}
 
+    # ---- further legs that need every rank: tight tolerance, configs[3] (N > 1), configs[4] (every N) ------------------
+    extra = {}
+    if not args.no_tight:
+        try:
+            extra["tight"] = tight_leg(args, ctx, E, dA, Q, Q0, m)
+        except Exception as e:  # noqa: BLE001  (a failing leg must not cost the main line)
+            extra["tight"] = {"error": repr(e)[:300]}
+    dA.close()
+    Q.close()
+    Q0.close()
+    if world > 1 and not args.no_c4:
+        try:
+            extra["c4"] = c4_leg(args, ctx, dist, rank, world)
+        except Exception as e:  # noqa: BLE001
+            extra["c4"] = {"error": repr(e)[:300]}
+    if not args.no_c5:
+        try:
+            extra["c5"] = c5_leg(args, ctx, dist, rank, world)
+        except Exception as e:  # noqa: BLE001
+            extra["c5"] = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -413,9 +476,9 @@ def run_b200(args):
     }
     roofline = {"bound": "hbm", "kernel": "spmm_brb_kernel (SpMM + fused Rayleigh-quotient dots)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_TRAFFIC_PER_LAUNCH.get((args.grid, args.stencil, m)) if world == 1 else None,
-                "traffic_source": "profiles/r01_ncu_kernels_final.csv (ncu --set full of this command, one launch)",
-                "peak_source": peak_src, "avg_launch_ms": spmm_ms / max(spmm_cnt, 1),
+                "traffic": ncu_traffic(args.grid, args.stencil, m)[0] if world == 1 else None,
+                "traffic_source": ncu_traffic(args.grid, args.stencil, m)[1],
+                "peak_source": peak_src, "frac_of_nominal_8000_GBps": achieved / 8000.0, "avg_launch_ms": spmm_ms / max(spmm_cnt, 1),
                 "algorithmic_bytes_per_launch": spmm_bytes, "kernel_time_shares": shares,
                 "kernel_time_shares_source": "one extra solve after the timed region with all categories timed "
                                              "(sum of kernel time %.2f ms per solve)" % total_kernel_ms,
@@ -445,9 +508,9 @@ def run_b200(args):
                          ((12.0 * nnz_local + 4 * n_loc) / 1e6, 8.0 * n_loc * m / 1e6),
                    "parallelism": "row-partitioned z-slabs x%d" % world if world > 1 else "single GPU",
                    "multi_gpu_data_path": ("NVLink peer memory: halo rows stored into the neighbours' windows, one-shot "
-                                           "peer all-reduce of the Gram matrices / Rayleigh quotients" if ctx.peer_ready()
+                                           "peer all-reduce of the Gram matrices / Rayleigh quotients" if peer_path
                                            else "NCCL send/recv + all-reduce") if world > 1 else None,
-                   "spmm_format": dA.spmm_info()["format"],
+                   "spmm_format": spmm_format,
                    "driver_choice": "headline = StandardLargest, the driver of this path that the reference implements "
                                     "(its CPU run is the reference arm); BASELINE.json configs[1] names StandardLOBPCG, "
                                     "which the reference lacks (SURVEY.md §0): that driver's time on the same matrix is "
@@ -456,6 +519,7 @@ def run_b200(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "eigenvalues_head": [float(x) for x in ev[:4]], "step_ms": [round(x, 3) for x in step_ms],
     }
+    line.update(extra)
     if world == 1 and not args.no_lobpcg:
         line["lobpcg"] = lobpcg_leg(["--grid", str(args.grid), "--stencil", args.stencil, "--nev", str(args.nev), "--tol",
                                      str(args.tol), "--maxiter", str(args.maxiter), "--e2e"], 150)
@@ -472,6 +536,190 @@ def run_b200(args):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def tight_leg(args, ctx, E, dA, Q, Q0, m):
+    """StandardLargest at a tight tolerance on the resident matrix (north_star parity bar: eigenvalues to 1e-10): the
+    reference's ABSOLUTE test max|rayleigh_k - rayleigh_{k-1}| < 1e-10 (eigensolver.hh:101), capped at the ini's maxiter."""
+    import torch
+
+    tol = 1e-10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Q.copy_from(Q0)
+    torch.cuda.synchronize()
+    e0.record()
+    ev, it = E.standard_largest_mv(ctx, dA, 0.0, tol, args.maxiter, Q)
+    e1.record()
+    torch.cuda.synchronize()
+    return {"driver": "StandardLargest", "tol": tol, "maxiter": args.maxiter, "iterations": int(it),
+            "converged": bool(it < args.maxiter - 1), "seconds": e0.elapsed_time(e1) * 1e-3,
+            "ms_per_iteration": e0.elapsed_time(e1) / max(it, 1), "eigenvalues_head": [float(x) for x in ev[:4]],
+            "note": "eigenvalue separation at the top of the 100^3 spectrum is ~1e-3 relative, so subspace iteration needs "
+                    "thousands of iterations for 1e-10; if not converged the run shows the cost of maxiter iterations"}
+
+
+def c4_leg(args, ctx, dist, rank, world):
+    """BASELINE.json configs[3]: high-contrast-coefficient 3D diffusion on grid^3 nodes (Q1, 27-point), row-partitioned
+    into z-slabs over the GPUs of this job, halo rows as NVLink peer stores. The coefficient is kappa in {1e-6, 1} (the
+    deterministic channel pattern of SURVEY.md §8d scaled so that max kappa = 1): the top of the spectrum is then O(10) as
+    for the constant-coefficient matrix and the reference's ABSOLUTE tolerance of the shipped ini (2e-3) keeps its meaning;
+    the small eigenvalues are the GenEO-like near-kernel. Two drivers on the same device matrix:
+      largest : the reference's StandardLargest loop (eigensolver.hh:69-102), 32 pairs, tol 2e-3
+      lobpcg  : StandardLOBPCG (new driver), the 32 SMALLEST pairs, Chebyshev degree 8
+    Eigenpairs of `largest` are verified on the HOST (scipy SpMM of this rank's rows against the downloaded block)."""
+    import torch
+
+    from dune_eigensolver_b200 import eigensolver as E, matrices as M, parallel as P
+
+    G, nev = args.c4_grid, 32
+    m = E.padded_cols(nev)
+    n, plane = G ** 3, G * G
+    contrast = 1e6
+    base_kappa = M.high_contrast_kappa(contrast)
+    t_gen = time.perf_counter()
+    part = P.partition_rows(n, world, align=plane)
+    r0, r1 = int(part[rank]), int(part[rank + 1])
+    nl = r1 - r0
+    rp, cg, v = M.q1_stiffness((G, G, G), kappa=lambda *c: base_kappa(*c) / contrast, rows=(r0, r1))
+    t_gen = time.perf_counter() - t_gen
+    t_up = time.perf_counter()
+    dA = P.build_distributed_matrix(ctx, rp, cg, v, part, rank, dist) if world > 1 else E.Matrix(ctx, (rp, cg, v))
+    t_up = time.perf_counter() - t_up
+    start = np.random.default_rng(123 + rank).standard_normal((nl, m))
+    Q0 = E.MultiVector(ctx, nl, m)
+    Q0.upload_rowmajor(start)
+    del start
+    Q = E.MultiVector(ctx, nl, m)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = {"workload": "Q1 27-point diffusion %d^3 (n=%d), kappa in {1e-6, 1} channels (period 8), %d eigenpairs, z-slabs x%d" %
+                       (G, n, nev, world),
+           "generate_s": maxr(t_gen), "matrix_upload_and_plan_s": maxr(t_up), "rows_per_gpu": nl,
+           "nnz_per_gpu": int(len(cg)), "start_block": "numpy default_rng(123 + rank) N(0,1) per rank (the reference's "
+           "libstdc++ stream for 16.8 M x 32 takes longer to generate than the solve; no reference run exists at this size)",
+           "halo_bytes_per_spmm_per_gpu": int(8 * m * plane * ((rank > 0) + (rank < world - 1))),
+           "data_path": ("NVLink peer memory" if ctx.peer_ready() else "NCCL") if world > 1 else "single GPU"}
+    # ---- StandardLargest: warm the kernels with a 3-iteration solve, then ONE timed solve
+    Q.copy_from(Q0)
+    E.standard_largest_mv(ctx, dA, 0.0, args.tol, 4, Q)
+    Q.copy_from(Q0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    ev, it = E.standard_largest_mv(ctx, dA, 0.0, args.tol, args.maxiter, Q)
+    e1.record()
+    barrier()
+    sec = maxr(e0.elapsed_time(e1) * 1e-3)
+    V = Q.download_rowmajor()
+    # per-kernel shares and the halo wait from a short profiled run (every category timed)
+    Q.copy_from(Q0)
+    ctx.profile(reset=True)
+    ctx.set_profiling(True)
+    prof_iters = 12
+    E.standard_largest_mv(ctx, dA, 0.0, -1.0, prof_iters + 1, Q)
+    barrier()
+    prof = ctx.profile(reset=True)
+    ctx.set_profiling(False)
+    tot = sum(val[0] for val in prof.values())
+    spmm_ms = (prof["spmm"][0] + prof["spmm_boundary"][0]) / prof_iters
+    interior_ms = prof["spmm"][0] / prof_iters
+    wait_ms = prof["halo_wait"][0] / prof_iters
+    spmm_bytes = 12.0 * len(cg) + 4.0 * (nl + 1) + 16.0 * nl * m
+    peak, _ = peaks()
+    out["largest"] = {
+        "driver": "StandardLargest (reference eigensolver.hh:28-112), tol %g, maxiter %d" % (args.tol, args.maxiter),
+        "seconds": sec, "iterations": int(it), "ms_per_iteration": sec * 1e3 / max(it, 1),
+        "eigenvalues_head": [float(x) for x in ev[:4]],
+        "kernel_time_shares": {k: (val[0] / tot if tot > 0 else 0.0) for k, val in prof.items()},
+        "spmm_ms_per_call": maxr(spmm_ms), "spmm_interior_ms": maxr(interior_ms), "halo_wait_ms_per_spmm": maxr(wait_ms),
+        "halo_push_ms_per_spmm": maxr(prof["halo_push"][0] / prof_iters),
+        "halo_hidden_behind_interior_rows": (1.0 - maxr(wait_ms) / max(maxr(interior_ms), 1e-9)) if world > 1 else None,
+        "spmm_GBps_per_gpu": spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0,
+        "spmm_frac_of_hbm_peak": spmm_bytes / (spmm_ms * 1e-3) / 1e9 / peak if spmm_ms > 0 else 0.0,
+    }
+    # ---- host verification: residuals of the first 8 columns on this rank's rows, orthonormality of the block
+    ncheck = 8
+    lo = max(r0 - plane, 0)
+    hi = min(r1 + plane, n)
+    ext = np.zeros((hi - lo, ncheck))
+    ext[r0 - lo:r0 - lo + nl] = V[:, :ncheck]
+    if world > 1:
+        first = torch.from_numpy(np.ascontiguousarray(V[:plane, :ncheck])).cuda()
+        last = torch.from_numpy(np.ascontiguousarray(V[nl - plane:, :ncheck])).cuda()
+        firsts = [torch.empty_like(first) for _ in range(world)]
+        lasts = [torch.empty_like(last) for _ in range(world)]
+        dist.all_gather(firsts, first)
+        dist.all_gather(lasts, last)
+        if rank > 0:
+            ext[:plane] = lasts[rank - 1].cpu().numpy()
+        if rank < world - 1:
+            ext[hi - lo - plane:] = firsts[rank + 1].cpu().numpy()
+    import scipy.sparse as sp
+
+    Aloc = sp.csr_matrix((v, cg - lo, rp), shape=(nl, hi - lo))
+    R = Aloc @ ext - V[:, :ncheck] * ev[:ncheck]
+    res2 = (R * R).sum(axis=0)
+    Gm = V.T @ V
+    if world > 1:
+        t = torch.from_numpy(np.concatenate([res2, Gm.reshape(-1)])).cuda()
+        dist.all_reduce(t)
+        t = t.cpu().numpy()
+        res2, Gm = t[:ncheck], t[ncheck:].reshape(m, m)
+    out["largest"]["host_verified"] = {
+        "residual_norms_first_%d" % ncheck: [float(x) for x in np.sqrt(res2)],
+        "max_abs_QtQ_minus_I": float(np.abs(Gm - np.eye(m)).max()),
+        "how": "scipy CSR SpMM of this rank's rows (global columns, neighbour planes all-gathered) against the downloaded "
+               "eigenvector block; sums all-reduced over the ranks"}
+    del Aloc, ext, R, V
+    # ---- StandardLOBPCG on the same device matrix: the 32 smallest eigenpairs
+    try:
+        Q.copy_from(Q0)
+        E.lobpcg_mv(ctx, dA, Q, args.tol, 2, nev=nev, cheb_degree=8)  # warm-up: 2 iterations
+        Q.copy_from(Q0)
+        barrier()
+        e0.record()
+        lam, rn, it2, restarts, conv = E.lobpcg_mv(ctx, dA, Q, args.tol, 400, nev=nev, cheb_degree=8)
+        e1.record()
+        barrier()
+        out["lobpcg"] = {"driver": "StandardLOBPCG (new; Chebyshev degree 8), tol %g relative residual, maxiter 400" % args.tol,
+                         "seconds": maxr(e0.elapsed_time(e1) * 1e-3), "iterations": int(it2), "converged": bool(conv),
+                         "restarts": int(restarts), "eigenvalues_head": [float(x) for x in lam[:4]],
+                         "max_relative_residual": float(np.max(rn[:nev] / np.maximum(np.abs(lam[:nev]), 1e-300)))}
+    except Exception as e:  # noqa: BLE001
+        out["lobpcg"] = {"error": repr(e)[:300]}
+    Q.close()
+    Q0.close()
+    dA.close()
+    return out
+
+
+def c5_leg(args, ctx, dist, rank, world):
+    """BASELINE.json configs[4]: block-width sweep p = 8/16/32/64 of the SpMM and Gram kernels on the 3D 200^3 Laplacian
+    (7-point FD and 27-point Q1) at this job's GPU count, against N x the measured HBM peak (tools/mg_sweep.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import mg_sweep
+
+    peak, _ = peaks()
+    rows = []
+    for stencil in ("fd", "q1"):
+        rows += mg_sweep.sweep(ctx, dist, rank, world, args.c5_grid, stencil, (8, 16, 32, 64), 8, peak)
+    keep = ("stencil", "m", "kernel", "kernel_ms", "halo_wait_ms", "wall_ms", "frac_kernel", "frac_wall")
+    return {"workload": "3D %d^3, 7-point FD and 27-point Q1, row-partitioned x%d" % (args.c5_grid, world),
+            "columns": "frac_* = aggregate algorithmic GB/s (SURVEY.md §8d bytes) / (N x %.0f GB/s measured HBM peak); kernel_ms = "
+                       "CUDA-event time of the kernels of one call (max over ranks), wall_ms = host time of the call incl. "
+                       "launch gaps, result fetch and the wait for the slowest rank" % peak,
+            "rows": [{k: (round(r[k], 5) if isinstance(r[k], float) else r[k]) for k in keep} for r in rows]}
 
 
 def lobpcg_leg(probe_args, timeout_s):

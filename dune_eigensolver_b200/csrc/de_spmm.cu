@@ -522,7 +522,7 @@ namespace dei
           h.ticket = ctx->dticket;
           const long long total = A->n_send * (m / 2);
           const int grid = (int)std::min<long long>((total + 255) / 256, ctx->sm_count * 4);
-          ProfScope prof(ctx, DE_PROF_MISC);
+          ProfScope prof(ctx, DE_PROF_HALO_PUSH);
           DE_REG(de::halo_push_kernel), de::halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(pa, h);
           DE_LAUNCH_CHECK(ctx);
         }
@@ -580,7 +580,7 @@ namespace dei
         for (int p = 0; p < A->npeers; ++p)
           if (A->recv_count[p] > 0)
             pl.rank[pl.n++] = A->peer[p];
-        ProfScope prof(ctx, DE_PROF_MISC);
+        ProfScope prof(ctx, DE_PROF_HALO_WAIT);
         DE_REG(de::halo_wait_kernel), de::halo_wait_kernel<<<1, 32, 0, ctx->stream>>>(pa, pl);
         DE_LAUNCH_CHECK(ctx);
       }

@@ -68,7 +68,7 @@ class Context:
 
     def set_profiling(self, on=True, only=None):
         """per-kernel CUDA-event timers: all categories, or only those named in `only` (e.g. ["spmm"])"""
-        names = ["spmm", "gram", "update", "small", "dot", "trsv", "misc", "spmm_boundary"]
+        names = ["spmm", "gram", "update", "small", "dot", "trsv", "misc", "spmm_boundary", "halo_push", "halo_wait"]
         code = int(bool(on))
         if on and only:
             code = sum(2 << names.index(c) for c in only)
@@ -76,7 +76,7 @@ class Context:
 
     def profile(self, reset=False):
         """{category: (total_ms, launches)} of the per-kernel CUDA-event timers (synchronises the stream)."""
-        names = ["spmm", "gram", "update", "small", "dot", "trsv", "misc", "spmm_boundary"]
+        names = ["spmm", "gram", "update", "small", "dot", "trsv", "misc", "spmm_boundary", "halo_push", "halo_wait"]
         out = {}
         for c, name in enumerate(names):
             ms, cnt = C.c_double(0.0), C.c_int64(0)

@@ -67,7 +67,9 @@ int de_context_launch_count(const de_context *ctx, int64_t *count);
 #define DE_PROF_TRSV 5    /* permute / level / chain kernels of the factored apply */
 #define DE_PROF_MISC 6    /* layout conversion, halo pack, eigenvector extraction */
 #define DE_PROF_SPMM_BOUNDARY 7 /* boundary-row launches of a distributed SpMM (they wait for the halo rows) */
-#define DE_PROF_CATEGORIES 8
+#define DE_PROF_HALO_PUSH 8 /* halo_push_kernel: halo rows stored into the neighbours' windows (runs in front of the interior rows) */
+#define DE_PROF_HALO_WAIT 9 /* halo_wait_kernel: what the boundary rows wait for; ~0 when the interior rows hide the exchange */
+#define DE_PROF_CATEGORIES 10
 /* enable: 0 = off, 1 = every category, otherwise a bit mask of categories shifted left by one (2 << DE_PROF_SPMM | ...) */
 int de_context_set_profiling(de_context *ctx, int enable);
 int de_context_profile(de_context *ctx, int category, double *total_ms, int64_t *launches, int reset);
