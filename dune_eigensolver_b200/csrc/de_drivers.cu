@@ -459,10 +459,15 @@ extern "C"
     double *Qa, *Qb;
     DE_TRY(blk.alloc(ctx, &Qa, (size_t)n * m));
     DE_TRY(blk.alloc(ctx, &Qb, (size_t)n * m));
+    SetupTrace trace("standard_driver", ctx->rank);
     DE_TRY(upload_panel8_device(ctx, n, m, start_panel8, Qa));
+    trace.lap("start block uploaded");
     std::vector<double> s2;
     DE_TRY(standard_core(ctx, A, F, shift, tol, maxiter, m, Qa, Qb, s2, verbose, iterations));
-    return copy_out(ctx, n, m, nev, Qa, s2, eval, evec);
+    trace.lap("solve");
+    const int rc = copy_out(ctx, n, m, nev, Qa, s2, eval, evec);
+    trace.lap("eigenvectors copied out");
+    return rc;
   }
 
   /** device-resident variant: Q holds the start block on entry and the eigenvector block on return */

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <chrono>
 #include <cstring>
 #include <limits>
@@ -442,6 +443,22 @@ namespace dei
 
   // ---- de_trsv.cu ---------------------------------------------------------------------------------------------
   int factor_apply_device(de_context *ctx, const de_factor *F, const double *X, double *Y, int m);
+
+  /** debugging aid (DE_TRACE_SETUP=1): where the time of a matrix setup goes. No behaviour depends on it. */
+  struct SetupTrace
+  {
+    const char *who;
+    int rank;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    SetupTrace(const char *w, int r) : who(w), rank(r), on(std::getenv("DE_TRACE_SETUP") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char *what)
+    {
+      if (on)
+        std::fprintf(stderr, "[de setup] rank %d %s: %-26s at %8.2f ms\n", rank, who, what,
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() * 1e3);
+    }
+  };
 
   /** Every kernel this library can launch, collected at LOAD time: each launch site names its kernel through DE_REG /
    *  DE_KERNEL, which odr-uses a static member of KernelReg<&kernel> whose initialiser adds the kernel to the registry.

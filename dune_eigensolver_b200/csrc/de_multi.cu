@@ -8,6 +8,8 @@
 //    reference's free functions run row-partitioned without Python, MPI or NCCL: the windows of the NVLink data path
 //    (kernels_peer.cuh) are plain peer-mapped allocations of the same process.
 #include <condition_variable>
+#include <cstdlib>
+#include <memory>
 
 #include "de_internal.hpp"
 
@@ -245,9 +247,26 @@ extern "C"
       return set_error(ctx, DE_ERR_INVALID, "de_matrix_create_rowblock: partition / rowptr do not match the row block");
     if (R == 1)
       return de_matrix_create_csr(ctx, n_owned, nnz, rowptr, col_global, val, out);
-    std::vector<int64_t> col_local((size_t)nnz), halo((size_t)std::max<int64_t>(nnz, 1)), recv((size_t)R, 0);
+    // (no value-initialisation: 2 x 8 nnz bytes of zero fill would cost more than the planning itself)
+    static const bool trace = std::getenv("DE_TRACE_SETUP") != nullptr; // debugging aid: prints where the setup time goes
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+      if (trace)
+        std::fprintf(stderr, "[de setup] rank %d %-28s %8.2f ms\n", me, what,
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count() * 1e3);
+    };
+    std::unique_ptr<int64_t[]> col_local_buf(new int64_t[(size_t)std::max<int64_t>(nnz, 1)]);
+    std::unique_ptr<int64_t[]> halo_buf(new int64_t[(size_t)std::max<int64_t>(nnz, 1)]);
+    struct Span
+    {
+      int64_t *p;
+      int64_t *data() const { return p; }
+      int64_t *begin() const { return p; }
+    } col_local{col_local_buf.get()}, halo{halo_buf.get()};
+    std::vector<int64_t> recv((size_t)R, 0);
     int64_t n_halo = 0;
     DE_TRY(de_halo_plan_local(n_owned, rowptr, col_global, R, me, part, col_local.data(), halo.data(), &n_halo, recv.data()));
+    lap("halo_plan_local");
     // every rank's per-owner halo counts, then every rank's halo list (padded to the longest)
     std::vector<int64_t> counts((size_t)R * R);
     if (allgather(user, recv.data(), counts.data(), (int64_t)sizeof(int64_t) * R) != 0)
@@ -275,8 +294,10 @@ extern "C"
     const int64_t stride = std::max<int64_t>(max_halo, 1);
     DE_TRY(de_halo_plan_peers(R, me, part, counts.data(), lists.data(), stride, &npeers, peers.data(), recv_counts.data(),
                               send_off.data(), send_rows.data(), deposit.data(), &max_halo, &all_symmetric));
+    lap("all-gathers + peer plan");
     DE_TRY(de_matrix_create_distributed(ctx, n_owned, n_halo, nnz, rowptr, col_local.data(), val, npeers, peers.data(),
                                         recv_counts.data(), send_off.data(), send_rows.data(), out));
+    lap("create_distributed");
     // The credit-free flow control of the peer-store halo exchange (kernels_peer.cuh) needs every send peer to be a
     // receive peer as well; an unsymmetric pattern keeps the NCCL path (the same decision on all ranks: it is derived
     // from the all-gathered counts alone).

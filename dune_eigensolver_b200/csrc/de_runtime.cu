@@ -825,14 +825,44 @@ extern "C"
       return set_error(nullptr, DE_ERR_INVALID, "de_halo_plan_local: partition does not match n_owned");
     const int64_t lo = part[rank], hi = part[rank + 1], nglob = part[nranks];
     const int64_t nnz = rowptr[n_owned];
+    // pass 1 (parallel): the columns outside [lo, hi), per thread; stencil matrices have few of them
+    const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(8, nnz >> 20));
     std::vector<int64_t> ext;
-    for (int64_t k = 0; k < nnz; ++k)
     {
-      const int64_t g = col_global[k];
-      if (g < 0 || g >= nglob)
-        return set_error(nullptr, DE_ERR_INVALID, "de_halo_plan_local: column index out of range");
-      if (g < lo || g >= hi)
-        ext.push_back(g);
+      std::vector<std::vector<int64_t>> part_ext((size_t)nth);
+      std::vector<int> bad((size_t)nth, 0);
+      auto scan = [&](int t)
+      {
+        const int64_t k0 = nnz * t / nth, k1 = nnz * (t + 1) / nth;
+        std::vector<int64_t> &e = part_ext[t];
+        int64_t last = -1;
+        for (int64_t k = k0; k < k1; ++k)
+        {
+          const int64_t g = col_global[k];
+          if (g < 0 || g >= nglob)
+          {
+            bad[t] = 1;
+            return;
+          }
+          if ((g < lo || g >= hi) && g != last) // (consecutive duplicates are common: skip them early)
+          {
+            e.push_back(g);
+            last = g;
+          }
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nth; ++t)
+        th.emplace_back(scan, t);
+      scan(0);
+      for (auto &x : th)
+        x.join();
+      for (int t = 0; t < nth; ++t)
+      {
+        if (bad[t])
+          return set_error(nullptr, DE_ERR_INVALID, "de_halo_plan_local: column index out of range");
+        ext.insert(ext.end(), part_ext[t].begin(), part_ext[t].end());
+      }
     }
     std::sort(ext.begin(), ext.end());
     ext.erase(std::unique(ext.begin(), ext.end()), ext.end());
@@ -851,7 +881,6 @@ extern "C"
     for (size_t h = 0; h < ext.size(); ++h)
       halo_global[h] = ext[h];
     {
-      const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(8, nnz >> 20));
       auto work = [&](int t)
       {
         const int64_t k0 = nnz * t / nth, k1 = nnz * (t + 1) / nth;

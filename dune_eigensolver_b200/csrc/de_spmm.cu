@@ -669,11 +669,15 @@ extern "C"
     de_matrix *A = new de_matrix();
     A->ctx = ctx;
     context_retain(ctx);
+    SetupTrace trace("create_csr", ctx->rank);
     int s = matrix_upload(ctx, n, n, nnz, rowptr, col, val, A);
+    trace.lap("matrix upload");
     if (s == DE_OK)
       s = build_staged_all(ctx, A, rowptr);
+    trace.lap("staged row blocks");
     if (s == DE_OK)
       s = build_brb(ctx, A, n, n, rowptr, col, val);
+    trace.lap("BRB form built");
     if (s != DE_OK)
     {
       de_matrix_destroy(A);
@@ -700,9 +704,11 @@ extern "C"
       de_matrix_destroy(A);
       return s;
     };
+    SetupTrace trace("create_distributed", ctx->rank);
     int s = matrix_upload(ctx, n_owned, n_owned + n_halo, nnz, rowptr, col_local, val, A);
     if (s != DE_OK)
       return fail(s);
+    trace.lap("matrix upload");
     A->n_halo = n_halo;
     A->npeers = npeers;
     long long roff = 0;
@@ -728,21 +734,43 @@ extern "C"
       return fail(s);
     // interior rows touch owned columns only and can run while the halo is in flight
     std::vector<int> in, bd;
-    for (long long i = 0; i < n_owned; ++i)
     {
-      bool halo = false;
-      for (int64_t k = rowptr[i]; k < rowptr[i + 1] && !halo; ++k)
-        halo = col_local[k] >= n_owned;
-      (halo ? bd : in).push_back((int)i);
+      const int nth = (int)std::max<long long>(1, std::min<long long>(8, nnz >> 20));
+      std::vector<std::vector<int>> pin((size_t)nth), pbd((size_t)nth);
+      auto scan = [&](int t)
+      {
+        const long long i0 = n_owned * t / nth, i1 = n_owned * (t + 1) / nth;
+        for (long long i = i0; i < i1; ++i)
+        {
+          bool halo = false;
+          for (int64_t k = rowptr[i]; k < rowptr[i + 1] && !halo; ++k)
+            halo = col_local[k] >= n_owned;
+          (halo ? pbd[t] : pin[t]).push_back((int)i);
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nth; ++t)
+        th.emplace_back(scan, t);
+      scan(0);
+      for (auto &x : th)
+        x.join();
+      for (int t = 0; t < nth; ++t) // chunks are ascending row ranges: concatenation keeps the lists sorted
+      {
+        in.insert(in.end(), pin[t].begin(), pin[t].end());
+        bd.insert(bd.end(), pbd[t].begin(), pbd[t].end());
+      }
     }
+    trace.lap("interior / boundary scan");
     A->n_interior = (long long)in.size();
     A->n_boundary = (long long)bd.size();
     if ((s = upload_converted(ctx, &A->interior, in.data(), in.size())) != DE_OK)
       return fail(s);
     if ((s = upload_converted(ctx, &A->boundary, bd.data(), bd.size())) != DE_OK)
       return fail(s);
+    trace.lap("row lists uploaded");
     if ((s = build_brb(ctx, A, n_owned, n_owned + n_halo, rowptr, col_local, val)) != DE_OK)
       return fail(s);
+    trace.lap("BRB form built");
     // the row-permuted CSR copies for the staged kernel are only built when the CSR family can be chosen by the AUTO
     // policy (brb_usable); a forced DE_SPMM_CSR then still works through the row-list kernel
     if (!(A->brb.valid && nnz >= 12 * n_owned))

@@ -20,6 +20,7 @@
  */
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <iostream>
 #include <random>
@@ -152,6 +153,8 @@ void GeneralizedInverse(const ISTLM &inA, const ISTLM &B, double shift, double r
                         std::vector<double> &eval, std::vector<VEC> &evec, int verbose = 0, unsigned int seed = 123)
 {
   ISTLM A(inA); // the driver works on a copy
+  const auto t_begin = std::chrono::steady_clock::now(); // the reference's `timer` (eigensolver.hh:221)
+  auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); };
   de_b200::require_square_blocks<ISTLM>("StandardInverse"); // sic: the reference reuses this text (:218)
   de_b200::require_scalar_blocks<ISTLM>("B_orthonormalize_blocked");
   const std::size_t n = A.N();
@@ -162,6 +165,9 @@ void GeneralizedInverse(const ISTLM &inA, const ISTLM &B, double shift, double r
   if (reg != 0.0)
     de_b200::add_to_diagonal(A, reg);
   UMFPackFactorizedMatrix<ISTLM> F(A, std::max(0, verbose - 1));
+  // the reference reads the timer started at function entry here, not timer_factorization (eigensolver.hh:254-256):
+  // "time_factorization" is the time from entry to the end of the factorisation -- kept, it is what its logs contain
+  const double time_factorization = elapsed();
 
   auto &ctx = de_b200::Context::thread_default();
   de_b200::DeviceMatrix dA(ctx, A), dB(ctx, B);
@@ -186,6 +192,7 @@ void GeneralizedInverse(const ISTLM &inA, const ISTLM &B, double shift, double r
   de_b200::scatter_results(nev, n, values, vectors, eval, evec);
   if (verbose > 0) // the reference's machine-greppable summary line (:344-350)
     std::cout << "GeneralizedInverse: "
+              << " time_total=" << elapsed() << " time_factorization=" << time_factorization
               << " iterations=" << iterations << " relerror=" << relerror << std::endl;
 }
 

@@ -63,6 +63,17 @@ int main(int argc, char **argv)
   // row-partitioned through the single-process multi-GPU front end (ini key parallel.numgpus of the driver program)
   const std::string devs = argc > 5 ? argv[5] : "";
   const std::size_t n = (std::size_t)N * N;
+  if (mode == "costmodel")
+  {
+    // the product header's analytic cost models (kernels_b200.hh; reference kernels_cpp.hh:98-116, :157-175): no GPU needed
+    for (int i = 2; i + 2 < argc; i += 3)
+    {
+      const int n = std::atoi(argv[i]), m = std::atoi(argv[i + 1]), b = std::atoi(argv[i + 2]);
+      std::printf("cost %d %d %d %.17g %.17g %.17g\n", n, m, b, flops_orthonormalize(n, m), bytes_orthonormalize_naive(n, m),
+                  bytes_orthonormalize_blocked(n, m, b));
+    }
+    return 0;
+  }
   try
   {
     if (!devs.empty())

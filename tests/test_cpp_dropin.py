@@ -71,6 +71,10 @@ def test_dropin_drivers_match_oracle(oracle):
     ref, V, it = oracle.generalized_inverse(M.laplacian_neumann_2d(16), M.laplacian_B_2d(16, 3), 1e-3, 0.0, 1e-12, 4000, 8)
     assert np.abs(ev - ref).max() <= 1e-10 * np.abs(ref).max()
     assert "iterations=%d" % it in text or "iterations=%d" % (it + 1) in text or "iterations=%d" % (it - 1) in text
+    # the reference's machine-greppable summary line, all five fields in its order (eigensolver.hh:343-350)
+    import re
+
+    assert re.search(r"GeneralizedInverse:\s+time_total=\S+ time_factorization=\S+ iterations=\d+ relerror=\S+", text)
 
 
 @pytest.mark.gpu
@@ -106,3 +110,26 @@ def test_dropin_multi_gpu_from_cpp(oracle):
             assert rc == 0, text
             ev = np.array([float(x) for x in vals["eval"].split()])
             assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(24)[:8]).max() <= 1e-9 * 8.0
+
+
+def test_dropin_cost_models_match_the_reference(oracles, golden):
+    """flops_orthonormalize / bytes_orthonormalize_{naive,blocked} of the PRODUCT header (include/dune/eigensolver/
+    kernels_b200.hh) against the golden values generated from the reference (kernels_cpp.hh:98-116, :157-175) and, on
+    more shapes, against the reference itself (oracle/_ref) or the port pinned to it."""
+    shapes = [(1000, 24, 8), (40000, 16, 8), (1000000, 32, 8), (2097152, 64, 8), (17, 8, 8), (123, 40, 8)]
+    out = subprocess.run([build_exe(), "costmodel", *[str(x) for sh in shapes for x in sh]], capture_output=True, text=True,
+                         timeout=60)
+    assert out.returncode == 0, out.stdout + out.stderr
+    got = {}
+    for line in out.stdout.splitlines():
+        t = line.split()
+        if t and t[0] == "cost":
+            got[(int(t[1]), int(t[2]), int(t[3]))] = tuple(float(x) for x in t[4:7])
+    assert set(got) == set(shapes)
+    assert got[(1000, 24, 8)] == (float(golden["k_cost_flops"]), float(golden["k_cost_bytes_naive"]),
+                                  float(golden["k_cost_bytes_blocked"]))
+    ref = oracles[0] if oracles[0] is not None else oracles[1]
+    for (n, m, b), (fl, bn, bb) in got.items():
+        assert fl == ref.flops_orthonormalize(n, m)
+        assert bn == ref.bytes_orthonormalize_naive(n, m)
+        assert bb == ref.bytes_orthonormalize_blocked(n, m, b)

@@ -106,3 +106,30 @@ def test_nev_not_multiple_of_eight_and_maxiter(ctx, oracle):
     assert k == 6 and r.iterations == 6
     assert r.eval.shape == (5,) and r.evec.shape == (5, 100)
     assert rel_err(r.eval, ev) <= 1e-9
+
+
+def test_config0_shipped_ini_at_full_size(ctx, oracle):
+    """BASELINE.json configs[0] AS SHIPPED (reference src/dune-eigensolver.ini: N = 200, tol = 2e-3, maxiter = 4000,
+    shift = 1e-3, overlap = 3, seed = 123) with ev.m = 16, through ALL THREE drivers against the reference itself run on
+    the same matrices (oracle/_ref; the factored drivers use the same host factorisation provider on both sides, so only
+    the iteration differs). Bar: iteration count +-1; eigenvalues to 1e-10 relative when the counts agree, else within
+    the run's tolerance; residuals no worse than twice the reference's."""
+    N, nev, shift, tol, maxiter = 200, 16, 1e-3, 2e-3, 4000
+
+    def check(r, ev, V, k, A, B):
+        assert abs(r.iterations - k) <= 1, (r.iterations, k)
+        scale = np.abs(ev).max()
+        assert np.abs(r.eval - ev).max() <= (1e-10 if r.iterations == k else 10 * tol) * scale
+        res_ref, res = residuals(A, B, ev, V), residuals(A, B, r.eval, r.evec)
+        assert np.all(res <= 2.0 * res_ref + 1e-8)
+
+    Ad = M.laplacian_dirichlet_2d(N)
+    ev, V, k = oracle.standard_largest(copy(Ad), 0.0, tol, maxiter, nev)          # src/dune-eigensolver.cc:643 forces shift 0
+    check(E.StandardLargest(ctx, copy(Ad), 0.0, tol, maxiter, nev), ev, V, k, Ad, None)
+    ev, V, k = oracle.standard_inverse(copy(Ad), shift, tol, maxiter, nev)
+    As = copy(Ad)
+    r = E.StandardInverse(ctx, As, shift, tol, maxiter, nev)
+    check(r, ev, V, k, Ad, None)
+    An, Bp = M.laplacian_neumann_2d(N), M.laplacian_B_2d(N, 3)
+    ev, V, k = oracle.generalized_inverse(An, Bp, shift, 0.0, tol, maxiter, nev)
+    check(E.GeneralizedInverse(ctx, An, Bp, shift, 0.0, tol, maxiter, nev), ev, V, k, An, Bp)
