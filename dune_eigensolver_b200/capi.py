@@ -39,6 +39,7 @@ SIGNATURES = {
     "de_context_peer_ready": [_vp, _ip],
     "de_matrix_set_peer_deposit": [_vp, _i64p, C.c_int64],
     "de_matrix_create_csr": [_vp, C.c_int64, C.c_int64, _i64p, _i64p, _dp, _vpp],
+    "de_matrix_create_bcsr": [_vp, C.c_int64, C.c_int64, C.c_int, _i64p, _i64p, _dp, _vpp],
     "de_matrix_create_distributed": [_vp, C.c_int64, C.c_int64, C.c_int64, _i64p, _i64p, _dp, C.c_int, _ip, _i64p,
                                      _i64p, _i64p, _vpp],
     "de_halo_plan_peers": [C.c_int, C.c_int, _i64p, _i64p, _i64p, C.c_int64, _ip, _ip, _i64p, _i64p, _i64p, _i64p, _i64p, _ip],

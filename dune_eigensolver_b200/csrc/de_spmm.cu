@@ -687,6 +687,49 @@ extern "C"
     return DE_OK;
   }
 
+  int de_matrix_create_bcsr(de_context *ctx, int64_t nb, int64_t nnzb, int k, const int64_t *rowptr, const int64_t *col,
+                            const double *val, de_matrix **out)
+  {
+    if (!ctx || !out || nb < 0 || nnzb < 0 || k < 1 || !rowptr || (nnzb > 0 && (!col || !val)))
+      return set_error(ctx, DE_ERR_INVALID, "de_matrix_create_bcsr: bad arguments");
+    if (k == 1)
+      return de_matrix_create_csr(ctx, nb, nnzb, rowptr, col, val, out);
+    if (rowptr[0] != 0 || rowptr[nb] != nnzb)
+      return set_error(ctx, DE_ERR_INVALID, "de_matrix_create_bcsr: rowptr does not match nnzb");
+    // the scalar matrix the blocks denote; one-time host work like the BCRS -> CSR flattening of the 1 x 1 case
+    const int64_t n = nb * k, nnz = nnzb * k * k;
+    std::vector<int64_t> rp((size_t)n + 1), ci((size_t)nnz);
+    std::vector<double> v((size_t)nnz);
+    const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(8, nnz >> 20));
+    auto work = [&](int t)
+    {
+      const int64_t b0 = nb * t / nth, b1 = nb * (t + 1) / nth;
+      for (int64_t ib = b0; ib < b1; ++ib)
+      {
+        const int64_t e0 = rowptr[ib], e1 = rowptr[ib + 1], len = (e1 - e0) * k;
+        for (int r = 0; r < k; ++r)
+        {
+          const int64_t row = ib * k + r, base = e0 * k * k + (int64_t)r * len;
+          rp[row] = base;
+          for (int64_t e = e0; e < e1; ++e)
+            for (int c = 0; c < k; ++c)
+            {
+              ci[base + (e - e0) * k + c] = col[e] * k + c;
+              v[base + (e - e0) * k + c] = val[(e * k + r) * k + c];
+            }
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nth; ++t)
+      th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th)
+      x.join();
+    rp[n] = nnz;
+    return de_matrix_create_csr(ctx, n, nnz, rp.data(), ci.data(), v.data(), out);
+  }
+
   int de_matrix_create_distributed(de_context *ctx, int64_t n_owned, int64_t n_halo, int64_t nnz,
                                    const int64_t *rowptr, const int64_t *col_local, const double *val, int npeers,
                                    const int *peer_ranks, const int64_t *recv_counts, const int64_t *send_offsets,

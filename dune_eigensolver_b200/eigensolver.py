@@ -142,6 +142,18 @@ class Matrix:
         self.n, self.nnz = n.value, nnz.value
 
     @classmethod
+    def bcsr(cls, ctx, rowptr, col, blocks):
+        """BCSR matrix with k x k blocks (BCRSMatrix<FieldMatrix<double,k,k>>): blocks has shape (nnzb, k, k). The result
+        acts on vector blocks with nb*k rows (C ABI de_matrix_create_bcsr)."""
+        rp, ci = i64(rowptr), i64(col)
+        bl = f64(blocks)
+        assert bl.ndim == 3 and bl.shape[1] == bl.shape[2] and bl.shape[0] == len(ci)
+        h = C.c_void_p()
+        check(capi.lib().de_matrix_create_bcsr(ctx._h, len(rp) - 1, len(ci), bl.shape[1], i64ptr(rp), i64ptr(ci), dptr(bl),
+                                               C.byref(h)), ctx._h)
+        return cls(ctx, _handle=h)
+
+    @classmethod
     def distributed(cls, ctx, n_owned, n_halo, rowptr, col_local, val, peers, recv_counts, send_offsets, send_rows):
         rp, ci, v = i64(rowptr), i64(col_local), f64(val)
         peers = capi.i32(peers)

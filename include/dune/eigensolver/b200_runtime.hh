@@ -123,29 +123,67 @@ namespace de_b200
     }
   };
 
-  //! CSR copy of an ISTL-style matrix with 1x1 blocks, taken through its row / column iterators
+  //! (B)CSR copy of an ISTL-style matrix with k x k blocks, taken through its row / column iterators. k = 1: plain CSR.
+  //! For k > 1 the block arrays are kept (C ABI de_matrix_create_bcsr) and scalar() gives the (N k) x (N k) matrix the
+  //! blocks denote -- row i*k + r, column j*k + c -- for the host-side consumers (factorisation, multi-GPU front end).
   struct HostCsr
   {
     std::vector<std::int64_t> rowptr, col;
-    std::vector<double> val;
-    std::int64_t n = 0;
+    std::vector<double> val; // k*k values per stored block, row-major inside a block
+    std::int64_t n = 0;      // SCALAR size: block rows * k
+    int k = 1;
 
     template <class ISTLM>
     explicit HostCsr(const ISTLM &A)
     {
-      n = static_cast<std::int64_t>(A.N());
-      rowptr.assign(n + 1, 0);
+      using block_type = typename ISTLM::block_type;
+      k = block_type::rows;
+      const std::int64_t nb = static_cast<std::int64_t>(A.N());
+      n = nb * k;
+      rowptr.assign(nb + 1, 0);
       col.reserve(A.nonzeroes());
-      val.reserve(A.nonzeroes());
+      val.reserve(A.nonzeroes() * (std::size_t)k * k);
       for (auto row = A.begin(); row != A.end(); ++row)
       {
         for (auto entry = row->begin(); entry != row->end(); ++entry)
         {
           col.push_back(static_cast<std::int64_t>(entry.index()));
-          val.push_back(static_cast<double>((*entry)[0][0]));
+          for (int r = 0; r < block_type::rows; ++r)
+            for (int c = 0; c < block_type::cols; ++c)
+              val.push_back(static_cast<double>((*entry)[r][c]));
         }
         rowptr[row.index() + 1] = static_cast<std::int64_t>(col.size());
       }
+    }
+    HostCsr() = default;
+
+    std::int64_t block_rows() const { return (std::int64_t)rowptr.size() - 1; }
+
+    //! the scalar CSR matrix (a copy for k > 1, *this for k = 1)
+    HostCsr scalar() const
+    {
+      if (k == 1)
+        return *this;
+      HostCsr S;
+      S.k = 1;
+      S.n = n;
+      const std::int64_t nb = block_rows();
+      S.rowptr.assign(n + 1, 0);
+      S.col.resize(col.size() * (std::size_t)k * k);
+      S.val.resize(S.col.size());
+      std::int64_t pos = 0;
+      for (std::int64_t ib = 0; ib < nb; ++ib)
+        for (int r = 0; r < k; ++r)
+        {
+          for (std::int64_t e = rowptr[ib]; e < rowptr[ib + 1]; ++e)
+            for (int c = 0; c < k; ++c)
+            {
+              S.col[pos] = col[e] * k + c;
+              S.val[pos++] = val[(e * k + r) * k + c];
+            }
+          S.rowptr[ib * k + r + 1] = pos;
+        }
+      return S;
     }
   };
 
@@ -156,8 +194,8 @@ namespace de_b200
   public:
     DeviceMatrix(Context &ctx, const HostCsr &A)
     {
-      check(de_matrix_create_csr(ctx.get(), A.n, (std::int64_t)A.col.size(), A.rowptr.data(), A.col.data(),
-                                 A.val.data(), &h_),
+      check(de_matrix_create_bcsr(ctx.get(), A.block_rows(), (std::int64_t)A.col.size(), A.k, A.rowptr.data(), A.col.data(),
+                                  A.val.data(), &h_),
             ctx.get());
     }
     template <class ISTLM>
@@ -204,12 +242,22 @@ namespace de_b200
       throw std::invalid_argument(std::string(who) + ": blocksize must be 8");
   }
 
+  //! The reference's kernels throw "only implemented for FieldMatrix<..,1,1>" for every k != 1 (kernels_cpp.hh:362-363,
+  //! :632-633). Here square blocks of any size are accepted (BCSR): the matrix acts on vector
+  //! blocks with N*k rows. Non-square blocks keep the reference's exception.
   template <class ISTLM>
   inline void require_scalar_blocks(const char *who)
   {
     using block_type = typename ISTLM::block_type;
-    if (block_type::rows != 1 || block_type::cols != 1)
+    if (block_type::rows != block_type::cols)
       throw std::invalid_argument(std::string(who) + ": only implemented for FieldMatrix<..,1,1>");
+  }
+
+  //! scalar size of the problem: block rows times block size
+  template <class ISTLM>
+  inline std::size_t scalar_rows(const ISTLM &A)
+  {
+    return (std::size_t)A.N() * (std::size_t)ISTLM::block_type::rows;
   }
 } // namespace de_b200
 

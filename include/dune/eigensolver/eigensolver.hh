@@ -68,15 +68,30 @@ namespace de_b200
       throw std::invalid_argument(std::string(who) + ": blocks of input matrix must be square");
   }
 
+  //! evec[j][i] = value for scalar entries (the reference's copy-out, eigensolver.hh:109-111); for a block vector type
+  //! (BlockVector<FieldVector<double,k>>, k > 1) scalar row i is component i % k of block entry i / k
+  template <class VEC>
+  inline auto store_entry(VEC &x, std::size_t i, int k, double value, int) -> decltype((void)(x[0] = value))
+  {
+    (void)k;
+    x[i] = value;
+  }
+  template <class VEC>
+  inline void store_entry(VEC &x, std::size_t i, int k, double value, long)
+  {
+    x[i / k][i % k] = value;
+  }
+
   template <class VEC>
   inline void scatter_results(int nev, std::size_t n, const std::vector<double> &values,
-                              const std::vector<double> &vectors, std::vector<double> &eval, std::vector<VEC> &evec)
+                              const std::vector<double> &vectors, std::vector<double> &eval, std::vector<VEC> &evec,
+                              int k = 1)
   {
     for (int j = 0; j < nev; ++j)
       eval[j] = values[j];
     for (int j = 0; j < nev; ++j)
       for (std::size_t i = 0; i < n; ++i)
-        evec[j][i] = vectors[(std::size_t)j * n + i];
+        store_entry(evec[j], i, k, vectors[(std::size_t)j * n + i], 0);
   }
 } // namespace de_b200
 
@@ -88,7 +103,7 @@ void StandardLargest(ISTLM &A, double shift, double tol, int maxiter, int nev, s
 {
   de_b200::require_square_blocks<ISTLM>("StandardLargest");
   de_b200::require_scalar_blocks<ISTLM>("matmul_sparse_tallskinny_blocked");
-  const std::size_t n = A.N();
+  const std::size_t n = de_b200::scalar_rows(A);
   const std::size_t m = de_b200::padded_columns(nev, 8);
   MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
   if (shift != 0.0)
@@ -100,7 +115,7 @@ void StandardLargest(ISTLM &A, double shift, double tol, int maxiter, int nev, s
   if (par.num_gpus() > 1)
   {
     // row-partitioned over the configured GPUs (parallel.numgpus): same arguments, same results to rounding
-    const de_b200::HostCsr H(A);
+    const de_b200::HostCsr H = de_b200::HostCsr(A).scalar();
     par.check_multi(de_multi_standard_largest(par.multi(), H.n, (std::int64_t)H.col.size(), H.rowptr.data(), H.col.data(),
                                               H.val.data(), par.row_align(), shift, tol, maxiter, nev, start.data(),
                                               values.data(), vectors.data(), verbose, &iterations));
@@ -113,7 +128,7 @@ void StandardLargest(ISTLM &A, double shift, double tol, int maxiter, int nev, s
                                        vectors.data(), verbose, &iterations),
                    ctx.get());
   }
-  de_b200::scatter_results(nev, n, values, vectors, eval, evec);
+  de_b200::scatter_results(nev, n, values, vectors, eval, evec, ISTLM::block_type::rows);
 }
 
 /** \brief smallest eigenvalues of a standard eigenproblem by shift-invert subspace iteration
@@ -124,7 +139,7 @@ void StandardInverse(ISTLM &A, double shift, double tol, int maxiter, int nev, s
 {
   de_b200::require_square_blocks<ISTLM>("StandardInverse");
   de_b200::require_scalar_blocks<ISTLM>("matmul_sparse_tallskinny_blocked");
-  const std::size_t n = A.N();
+  const std::size_t n = de_b200::scalar_rows(A);
   const std::size_t m = de_b200::padded_columns(nev, 8);
   MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
   if (shift != 0.0)
@@ -142,7 +157,7 @@ void StandardInverse(ISTLM &A, double shift, double tol, int maxiter, int nev, s
                                          values.data(), vectors.data(), verbose, &iterations);
   de_factor_destroy(dF);
   de_b200::check(status, ctx.get());
-  de_b200::scatter_results(nev, n, values, vectors, eval, evec);
+  de_b200::scatter_results(nev, n, values, vectors, eval, evec, ISTLM::block_type::rows);
 }
 
 /** \brief smallest eigenvalues of A x = lambda B x by shift-invert subspace iteration with B-orthonormalisation
@@ -157,7 +172,7 @@ void GeneralizedInverse(const ISTLM &inA, const ISTLM &B, double shift, double r
   auto elapsed = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); };
   de_b200::require_square_blocks<ISTLM>("StandardInverse"); // sic: the reference reuses this text (:218)
   de_b200::require_scalar_blocks<ISTLM>("B_orthonormalize_blocked");
-  const std::size_t n = A.N();
+  const std::size_t n = de_b200::scalar_rows(A);
   const std::size_t m = de_b200::padded_columns(nev, 8);
   MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
   if (shift != 0.0)
@@ -187,9 +202,9 @@ void GeneralizedInverse(const ISTLM &inA, const ISTLM &B, double shift, double r
   if (evec.size() != (std::size_t)nev)
     evec.resize(nev);
   for (int j = 0; j < nev; ++j)
-    if (evec[j].size() != n)
-      evec[j].resize(n);
-  de_b200::scatter_results(nev, n, values, vectors, eval, evec);
+    if (evec[j].size() != (std::size_t)A.N())
+      evec[j].resize(A.N());
+  de_b200::scatter_results(nev, n, values, vectors, eval, evec, ISTLM::block_type::rows);
   if (verbose > 0) // the reference's machine-greppable summary line (:344-350)
     std::cout << "GeneralizedInverse: "
               << " time_total=" << elapsed() << " time_factorization=" << time_factorization
@@ -207,7 +222,7 @@ void StandardLOBPCG(const ISTLM &A, double tol, int maxiter, int nev, std::vecto
 {
   de_b200::require_square_blocks<ISTLM>("StandardLOBPCG");
   de_b200::require_scalar_blocks<ISTLM>("matmul_sparse_tallskinny_blocked");
-  const std::size_t n = A.N();
+  const std::size_t n = de_b200::scalar_rows(A);
   const std::size_t m = de_b200::padded_columns(nev, 8);
   MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
   std::vector<double> values(nev), vectors((std::size_t)nev * n);
@@ -215,7 +230,7 @@ void StandardLOBPCG(const ISTLM &A, double tol, int maxiter, int nev, std::vecto
   auto &par = de_b200::Parallel::instance();
   if (par.num_gpus() > 1)
   {
-    const de_b200::HostCsr H(A);
+    const de_b200::HostCsr H = de_b200::HostCsr(A).scalar();
     par.check_multi(de_multi_standard_lobpcg(par.multi(), H.n, (std::int64_t)H.col.size(), H.rowptr.data(), H.col.data(),
                                              H.val.data(), par.row_align(), tol, maxiter, nev, start.data(), values.data(),
                                              vectors.data(), verbose, &iterations));
@@ -228,7 +243,7 @@ void StandardLOBPCG(const ISTLM &A, double tol, int maxiter, int nev, std::vecto
                                       verbose, &iterations),
                    ctx.get());
   }
-  de_b200::scatter_results(nev, n, values, vectors, eval, evec);
+  de_b200::scatter_results(nev, n, values, vectors, eval, evec, ISTLM::block_type::rows);
 }
 
 /** \brief nev smallest eigenpairs of A x = lambda B x (B symmetric positive definite) by LOBPCG; B-orthonormal
@@ -239,7 +254,7 @@ void GeneralizedLOBPCG(const ISTLM &A, const ISTLM &B, double tol, int maxiter, 
 {
   de_b200::require_square_blocks<ISTLM>("GeneralizedLOBPCG");
   de_b200::require_scalar_blocks<ISTLM>("B_orthonormalize_blocked");
-  const std::size_t n = A.N();
+  const std::size_t n = de_b200::scalar_rows(A);
   const std::size_t m = de_b200::padded_columns(nev, 8);
   MultiVector<double, 8> start = de_b200::random_start_block(n, m, seed);
   std::vector<double> values(nev), vectors((std::size_t)nev * n);
@@ -247,7 +262,7 @@ void GeneralizedLOBPCG(const ISTLM &A, const ISTLM &B, double tol, int maxiter, 
   auto &par = de_b200::Parallel::instance();
   if (par.num_gpus() > 1)
   {
-    const de_b200::HostCsr HA(A), HB(B);
+    const de_b200::HostCsr HA = de_b200::HostCsr(A).scalar(), HB = de_b200::HostCsr(B).scalar();
     par.check_multi(de_multi_generalized_lobpcg(par.multi(), HA.n, (std::int64_t)HA.col.size(), HA.rowptr.data(),
                                                 HA.col.data(), HA.val.data(), (std::int64_t)HB.col.size(), HB.rowptr.data(),
                                                 HB.col.data(), HB.val.data(), par.row_align(), tol, maxiter, nev,
@@ -266,9 +281,9 @@ void GeneralizedLOBPCG(const ISTLM &A, const ISTLM &B, double tol, int maxiter, 
   if (evec.size() != (std::size_t)nev)
     evec.resize(nev);
   for (int j = 0; j < nev; ++j)
-    if (evec[j].size() != n)
-      evec[j].resize(n);
-  de_b200::scatter_results(nev, n, values, vectors, eval, evec);
+    if (evec[j].size() != (std::size_t)A.N())
+      evec[j].resize(A.N());
+  de_b200::scatter_results(nev, n, values, vectors, eval, evec, ISTLM::block_type::rows);
 }
 
 #endif

@@ -54,29 +54,32 @@ public:
   IntType do_recip = 1;
   double *Rs = nullptr;
 
-  //! factorise A (scalar blocks). `verbose` is accepted for signature compatibility.
+  //! factorise A (square blocks of any size). `verbose` is accepted for signature compatibility.
   explicit UMFPackFactorizedMatrix(const ISTLM &A, int verbose = 0,
                                    de_b200::Ordering ordering = de_b200::Ordering::nested_dissection)
   {
     using block_type = typename ISTLM::block_type;
     if (A.N() != A.M() || block_type::rows != block_type::cols)
       throw std::invalid_argument("UMFPackFactorizedMatrix: input matrix must be square");
-    if (block_type::rows != 1)
-      throw std::invalid_argument("UMFPackFactorizedMatrix: only implemented for FieldMatrix<..,1,1>");
-    std::vector<long> rowptr(A.N() + 1, 0), col;
+    // k x k blocks: the scalar matrix they denote (the reference flattens blocks the same way, umfpacktools.hh:62-95)
+    const int k = block_type::rows;
+    const long ns = static_cast<long>(A.N()) * k;
+    std::vector<long> rowptr(ns + 1, 0), col;
     std::vector<double> val;
-    col.reserve(A.nonzeroes());
-    val.reserve(A.nonzeroes());
+    col.reserve(A.nonzeroes() * (std::size_t)k * k);
+    val.reserve(A.nonzeroes() * (std::size_t)k * k);
     for (auto row = A.begin(); row != A.end(); ++row)
-    {
-      for (auto entry = row->begin(); entry != row->end(); ++entry)
+      for (int r = 0; r < k; ++r)
       {
-        col.push_back(static_cast<long>(entry.index()));
-        val.push_back(static_cast<double>((*entry)[0][0]));
+        for (auto entry = row->begin(); entry != row->end(); ++entry)
+          for (int c = 0; c < k; ++c)
+          {
+            col.push_back(static_cast<long>(entry.index()) * k + c);
+            val.push_back(static_cast<double>((*entry)[r][c]));
+          }
+        rowptr[row.index() * k + r + 1] = static_cast<long>(col.size());
       }
-      rowptr[row.index() + 1] = static_cast<long>(col.size());
-    }
-    de_b200::factorize_csr(static_cast<long>(A.N()), rowptr.data(), col.data(), val.data(), store_, ordering);
+    de_b200::factorize_csr(ns, rowptr.data(), col.data(), val.data(), store_, ordering);
     publish();
     (void)verbose;
   }

@@ -98,6 +98,15 @@ int de_context_peer_ready(const de_context *ctx, int *ready);
  * per solve, AFTER applying shift / axpy / regularisation on the host exactly as the reference does. */
 int de_matrix_create_csr(de_context *ctx, int64_t n, int64_t nnz, const int64_t *rowptr, const int64_t *col,
                          const double *val, de_matrix **out);
+/* BCSR: a BCRSMatrix<FieldMatrix<double,k,k>> with k > 1 -- nb block rows, nnzb stored blocks, val = nnzb * k * k
+ * doubles (block after block, each row-major). The reference's drivers accept such matrices by type
+ * (eigensolver.hh:36-39) but every one of its kernels throws for k != 1 (kernels_cpp.hh:362-363, :632-633); here the
+ * matrix is the scalar (nb*k) x (nb*k) matrix it denotes: row ib*k + r holds val[e][r][c] at column col[e]*k + c for
+ * every block e of block row ib. Vector blocks have nb*k rows (the entries of a BlockVector<FieldVector<double,k>> in
+ * storage order). On the device the dense k x k blocks land in the 8 x 4 tensor-core steps of the BRB form like any
+ * other entries (a block row of k = 2 or 4 fills them better than a stencil row does). k = 1 is de_matrix_create_csr. */
+int de_matrix_create_bcsr(de_context *ctx, int64_t nb, int64_t nnzb, int k, const int64_t *rowptr, const int64_t *col,
+                          const double *val, de_matrix **out);
 /* Row-partitioned matrix: this rank owns `n_owned` consecutive rows. Columns are already renumbered to
  * [0,n_owned) = owned rows of the vector block, [n_owned, n_owned+n_halo) = halo rows received from peers.
  * Peers are listed in ascending rank order; recv_counts[p] halo rows arrive from peer p (they occupy the

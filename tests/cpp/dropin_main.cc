@@ -2,6 +2,7 @@
 // write against the reference's eigensolver.hh, compiled against this repo's headers + libdune_eigensolver_b200.so.
 // The matrix type is the minimal BCRSMatrix stand-in from oracle/shim (test infrastructure; real dune-istl at a
 // user's site). Prints results as "key value..." lines that tests/test_cpp_dropin.py compares with the oracle.
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,6 +44,65 @@ static Matrix laplacian(int N, const char *kind, int overlap)
       ptr.push_back((long)col.size());
     }
   return Matrix((std::size_t)N * N, (std::size_t)N * N, ptr.data(), col.data(), val.data());
+}
+
+static void print(const char *key, const std::vector<double> &v);
+
+// BCSR: the 2D Laplacian with k x k blocks L_ij * C, C = tridiag(0.5, 2 + c, 0.5) -- the matrix kron(L, C)
+template <int K>
+static Dune::BCRSMatrix<Dune::FieldMatrix<double, K, K>> block_laplacian(int N)
+{
+  using Blk = Dune::FieldMatrix<double, K, K>;
+  Blk C;
+  for (int r = 0; r < K; ++r)
+    for (int c = 0; c < K; ++c)
+      C[r][c] = r == c ? 2.0 + r : ((r - c == 1 || c - r == 1) ? 0.5 : 0.0);
+  std::vector<long> ptr(1, 0), col;
+  std::vector<Blk> val;
+  for (int y = 0; y < N; ++y)
+    for (int x = 0; x < N; ++x)
+    {
+      auto put = [&](int xx, int yy, double s) {
+        Blk b;
+        for (int r = 0; r < K; ++r)
+          for (int c = 0; c < K; ++c)
+            b[r][c] = s * C[r][c];
+        col.push_back(yy * N + xx);
+        val.push_back(b);
+      };
+      if (y > 0) put(x, y - 1, -1.0);
+      if (x > 0) put(x - 1, y, -1.0);
+      put(x, y, 4.0);
+      if (x < N - 1) put(x + 1, y, -1.0);
+      if (y < N - 1) put(x, y + 1, -1.0);
+      ptr.push_back((long)col.size());
+    }
+  return Dune::BCRSMatrix<Blk>((std::size_t)N * N, (std::size_t)N * N, ptr.data(), col.data(), val.data());
+}
+
+template <int K>
+static int run_bcsr(int N, int nev, double tol)
+{
+  auto A = block_laplacian<K>(N);
+  const std::size_t nb = (std::size_t)N * N;
+  std::vector<double> eval(nev);
+  // a BlockVector<FieldVector<double,K>> stand-in: nb block entries of K components
+  std::vector<std::vector<std::array<double, K>>> evec(nev, std::vector<std::array<double, K>>(nb));
+  StandardLargest(A, 0.0, tol, 4000, nev, eval, evec, 0, 123);
+  print("eval", eval);
+  std::vector<double> head;
+  for (int j = 0; j < nev; ++j)
+    for (int c = 0; c < K; ++c)
+      head.push_back(evec[j][1][c]); // scalar rows K .. 2K-1
+  print("evec_block1", head);
+  // the kernel-level entry point on the same block matrix: Y = A X for a block with nb * K rows
+  MultiVector<double, 8> X = de_b200::random_start_block(nb * K, 8, 7), Y{nb * K, 8};
+  matmul_sparse_tallskinny_blocked(Y, A, X);
+  std::vector<double> y0;
+  for (int j = 0; j < 8; ++j)
+    y0.push_back(Y(K + 1, j));
+  print("spmm_row", y0);
+  return 0;
 }
 
 static void print(const char *key, const std::vector<double> &v)
@@ -128,6 +188,10 @@ int main(int argc, char **argv)
       eval = ev;
       evec = V;
     }
+    else if (mode == "bcsr2")
+      return run_bcsr<2>(N, nev, tol);
+    else if (mode == "bcsr3")
+      return run_bcsr<3>(N, nev, tol);
     else if (mode == "kernels")
     {
       Matrix A = laplacian(N, "dirichlet", 0);

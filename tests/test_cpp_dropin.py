@@ -133,3 +133,54 @@ def test_dropin_cost_models_match_the_reference(oracles, golden):
         assert fl == ref.flops_orthonormalize(n, m)
         assert bn == ref.bytes_orthonormalize_naive(n, m)
         assert bb == ref.bytes_orthonormalize_blocked(n, m, b)
+
+
+def _block_laplacian(N, k):
+    """kron(L, C) as scalar CSR and as (rowptr, col, blocks): the matrix tests/cpp/dropin_main.cc builds for bcsr<k>"""
+    import scipy.sparse as sp
+
+    L = M.to_scipy(M.laplacian_dirichlet_2d(N)).tocsr()
+    Cm = np.array([[2.0 + r if r == c else (0.5 if abs(r - c) == 1 else 0.0) for c in range(k)] for r in range(k)])
+    S = sp.kron(L, Cm, format="csr")
+    S.sort_indices()
+    blocks = L.data[:, None, None] * Cm[None, :, :]
+    return (S.indptr.astype(np.int64), S.indices.astype(np.int64), S.data.copy()), (L.indptr, L.indices, blocks)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [2, 3])
+def test_dropin_bcsr_blocks(oracle, k):
+    """BCRSMatrix<FieldMatrix<double,k,k>>, k > 1 (every reference kernel throws for it,
+    kernels_cpp.hh:632-633): the drop-in runs it as the scalar matrix the blocks denote, so the reference's own driver on
+    that scalar matrix is the oracle."""
+    N, nev = 14, 8
+    rc, vals, text = run("bcsr%d" % k, N, nev, 1e-10)
+    assert rc == 0, text
+    scalar, _ = _block_laplacian(N, k)
+    ev, V, it = oracle.standard_largest(scalar, 0.0, 1e-10, 4000, nev)
+    got = np.array([float(x) for x in vals["eval"].split()])
+    assert np.abs(got - ev).max() <= 1e-10 * np.abs(ev).max()
+    blk = np.array([float(x) for x in vals["evec_block1"].split()]).reshape(nev, k)
+    assert np.abs(np.abs(blk) - np.abs(V[:, k:2 * k])).max() <= 1e-7
+    X = oracle.start_block(N * N * k, 8, 7)
+    ref = oracle.spmm(scalar, X)
+    row = np.array([float(x) for x in vals["spmm_row"].split()])
+    assert np.abs(row - ref[k + 1]).max() <= 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [2, 4])
+def test_bcsr_matrix_through_the_c_abi(ctx, oracle, k):
+    from dune_eigensolver_b200 import eigensolver as E
+
+    N, m = 20, 16
+    scalar, (rp, ci, blocks) = _block_laplacian(N, k)
+    dA = E.Matrix.bcsr(ctx, rp, ci, blocks)
+    assert dA.n == N * N * k
+    X = oracle.start_block(N * N * k, m, 123)
+    dX, dY = E.MultiVector.from_array(ctx, X), E.MultiVector(ctx, N * N * k, m)
+    E.matmul_sparse_tallskinny_blocked(dY, dA, dX)
+    ref = oracle.spmm(scalar, X)
+    assert np.abs(dY.download() - ref).max() <= 1e-13 * np.abs(ref).max()
+    for h in (dA, dX, dY):
+        h.close()
