@@ -170,8 +170,9 @@ namespace dei
   {
     if constexpr (DO_UPDATE && M == 64 && DO_GRAM && UPPER && SAME)
     {
-      // no fused kernel at this width: block update, then the Gram matrix of the result (two passes, both on the
-      // warp-specialised kernels; the one-pass first-generation kernel at M = 64 is slower than the two together)
+      // no fused kernel at this width (72 Gram accumulators + the result block do not fit the register file: 168
+      // registers with spills when tried): block update, then the Gram matrix of the result -- two passes, both on the
+      // warp-specialised kernels
       de::TsArgs u = a;
       DE_TRY((launch_ts_t<M, true, false, false, true>(ctx, u, nullptr)));
       de::TsArgs g = a;
@@ -300,6 +301,12 @@ namespace dei
                   bool symmetric, double *out)
   {
     const bool same = (X == Y && ldx == ldy);
+    if (!same && gram2_supported(w))
+    {
+      // wide two-operand Gram: tensor-pipe-bound, warp-specialised kernel (kernels_gram2.cuh); all tiles are computed
+      DE_TRY(gram2_device(ctx, w, n, X, ldx, Y, ldy, out));
+      return allreduce_sum(ctx, out, (size_t)w * w);
+    }
     if (ts_supported(w))
     {
       de::TsArgs a{};

@@ -427,6 +427,9 @@ namespace dei
   int diag_dot_device(de_context *ctx, long long n, int m, const double *X, const double *Y, double *out);
   int gram_device(de_context *ctx, int w, long long n, const double *X, int ldx, const double *Y, int ldy, bool symmetric,
                   double *out);
+  /** de_dense64.cu: G = X^T Y on the warp-specialised tensor-core kernel (widths where it beats the first-generation one) */
+  bool gram2_supported(int w);
+  int gram2_device(de_context *ctx, int w, long long n, const double *X, int ldx, const double *Y, int ldy, double *out);
   /** mode 0: Y = X R ; mode 1: Y -= X R (projection) */
   int update_device(de_context *ctx, int mode, int w, long long n, const double *X, int ldx, const double *R, double *Y,
                     int ldy, int upper, const int *skip_flag = nullptr);

@@ -42,7 +42,8 @@ namespace de
     static constexpr int KS = M / 4;                           // k steps of the update
     static constexpr int LDT = M + 4;                          // staged row stride (doubles)
     static constexpr bool RSMEM = (M == 64);                    // factor fragments from shared memory instead of registers
-    static constexpr int NCW = (M >= 32) ? 8 : 12;              // consumer warps (M >= 32: up to 167 registers per thread)
+    static constexpr int NCW = (M == 32) ? 8 : 12;              // consumer warps (M = 32: up to 167 registers per thread; M = 64
+                                                                // has no fused Gram and its factor in shared memory: 12 fit)
     static constexpr int THREADS = 32 * (kTs2ProducerWarps + NCW);
     static constexpr int TR = 8 * NCW * (M == 64 ? 1 : (M == 32 ? 2 : (M == 16 ? 4 : 8))); // rows per tile
     static constexpr int NBLK = TR / 8;                        // 8-row blocks per tile

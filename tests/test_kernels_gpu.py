@@ -374,3 +374,19 @@ def test_empty_inputs(ctx):
     dA = E.Matrix(ctx, (np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int64), np.zeros(0)))
     E.matmul_sparse_tallskinny_blocked(dY, dA, dX)
     assert dY.download().shape == (0, 8)
+
+
+@pytest.mark.parametrize("n", [1, 59, 60, 61, 7777, 250000])
+def test_two_operand_gram_wide_block(ctx, oracle, n):
+    """G = X^T Y at m = 64 runs on the warp-specialised tensor-core kernel (csrc/kernels_gram2.cuh); against the reference's
+    dot_products_all_blocked (kernels_cpp.hh:58-96) including blocks shorter than one tile and ragged tails"""
+    rng = np.random.default_rng(n)
+    X, Y = rng.standard_normal((n, 64)), rng.standard_normal((n, 64))
+    dX, dY = E.MultiVector.from_array(ctx, X), E.MultiVector.from_array(ctx, Y)
+    G = E.dot_products_all_blocked(dX, dY)
+    ref = oracle.gram(X, Y)
+    scale = np.sqrt(n) * 4.0
+    assert np.abs(G - ref).max() <= 1e-13 * scale * max(1.0, np.abs(ref).max() / scale)
+    assert np.abs(G - X.T @ Y).max() <= 1e-12 * n
+    dX.close()
+    dY.close()
