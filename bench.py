@@ -88,6 +88,10 @@ def parse():
     ap.add_argument("--no-c5", action="store_true", help="skip the configs[4] leg (block-width sweep on 200^3)")
     ap.add_argument("--c5-grid", type=int, default=200)
     ap.add_argument("--no-tight", action="store_true", help="skip the tight-tolerance StandardLargest leg")
+    ap.add_argument("--c3-grid", type=int, default=80,
+                    help="grid of the configs[2] leg (Q1 stiffness + mass pencil, GeneralizedInverse with the factored solve, 64 "
+                         "pairs); the one-time host factorisation grows like grid^6 (80: ~25 s, 96: ~70 s, 128: ~7 min on 16 "
+                         "cores; profiles/ holds a 128^3 run); 0 skips it")
     ap.add_argument("--full-reference", action="store_true",
                     help="--impl reference: every replica runs the COMPLETE solve (default: bounded sample, extrapolated)")
     return ap.parse_args()
@@ -528,6 +532,11 @@ def run_b200(args):
             # without the 3D factorisation the reference's GeneralizedInverse would need (UMFPACK, absent here)
             line["lobpcg_pencil"] = lobpcg_leg(["--grid", str(args.lobpcg_pencil_grid), "--mass", "--nev", "64", "--tol",
                                                 str(args.tol), "--maxiter", "400", "--steps", "1"], 200)
+        if args.c3_grid > 0:
+            # configs[2] with the driver the reference would use: GeneralizedInverse + factored solve (supernodal Cholesky
+            # of A + shift B on the host, one-time; supernodal apply on the GPU)
+            line["c3"] = lobpcg_leg(["--grid", str(args.c3_grid), "--nev", "64", "--tol", str(args.tol)], 400,
+                                    script="factor_probe.py")
         if args.lobpcg_contrast > 0.0:
             # configs[3]'s matrix type on one GPU: high-contrast diffusion, same grid and block as the headline
             line["lobpcg_high_contrast"] = lobpcg_leg(["--grid", str(args.grid), "--contrast", str(args.lobpcg_contrast),
@@ -722,14 +731,14 @@ def c5_leg(args, ctx, dist, rank, world):
             "rows": [{k: (round(r[k], 5) if isinstance(r[k], float) else r[k]) for k in keep} for r in rows]}
 
 
-def lobpcg_leg(probe_args, timeout_s):
+def lobpcg_leg(probe_args, timeout_s, script="lobpcg_probe.py"):
     """BASELINE.json configs[1] names StandardLOBPCG; the reference has none, so the headline above
     stays on the driver the reference arm can run and this object reports the new driver next to it: the nev SMALLEST
     eigenpairs of the same matrix. Runs tools/lobpcg_probe.py as a child process (after everything else was measured)
     so that no failure in the new driver can cost the main line."""
     import subprocess
 
-    cmd = [sys.executable, os.path.join(ROOT, "tools", "lobpcg_probe.py")] + list(probe_args)
+    cmd = [sys.executable, os.path.join(ROOT, "tools", script)] + list(probe_args)
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s)
         for ln in reversed(out.stdout.splitlines()):

@@ -104,6 +104,9 @@ SIGNATURES = {
                               C.POINTER(_lp), C.POINTER(_lp), C.POINTER(_dp), C.POINTER(_lp), C.POINTER(_lp),
                               C.POINTER(_dp), _lp],
     "de_host_factor_destroy": [_vp],
+    "de_host_factorize_spd": [C.c_int64, _i64p, _i64p, _dp, C.c_int, C.c_int, _vpp],
+    "de_host_factor_info": [_vp, _ip, _i64p, _i64p, _i64p, _dp, _dp],
+    "de_factor_upload_host": [_vp, _vp, _vpp],
 }
 _RESTYPES = {"de_last_error_string": C.c_char_p, "de_multi_last_error": C.c_char_p}
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)

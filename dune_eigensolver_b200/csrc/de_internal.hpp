@@ -18,6 +18,7 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -247,15 +248,22 @@ struct de_factor
   double *rowscale = nullptr;
   double *W = nullptr;
   int W_m = 0;
+  struct de_sn_device *sn = nullptr; // supernodal form (de_snode.cu); the level schedules L / U are then empty
+  double *W2 = nullptr;              // second work block of the supernodal apply
   // the two triangular sweeps (hundreds of dependent launches on the fixed work block W) captured once per width
   cudaGraphExec_t sweep_graph = nullptr;
   int sweep_graph_m = 0;
   long long sweep_graph_nodes = 0;
 };
 
+namespace de_b200
+{
+  struct SupernodalFactor; // supernodal_cholesky.hh (only de_snode.cu needs the definition)
+}
 struct de_host_factor
 {
-  de_b200::FactorArrays F;
+  de_b200::FactorArrays F;                       // the UMFPACK field contract (sparse_lu.hh), or ...
+  std::shared_ptr<de_b200::SupernodalFactor> sn; // ... a supernodal Cholesky factor (F is then filled on demand)
 };
 
 namespace dei
@@ -443,6 +451,12 @@ namespace dei
   // ---- de_spmm.cu ---------------------------------------------------------------------------------------------
   /** Y = A X; dot: also dp = diag(X^T Y) into ctx->dDP(); gram_out (dot only): may receive G = Y^T Y, see spmm_device */
   int spmm_device(de_context *ctx, const de_matrix *A, const double *X, double *Y, int m, bool dot, bool *gram_out = nullptr);
+
+  // ---- de_snode.cu --------------------------------------------------------------------------------------------
+  int sn_apply_device(de_context *ctx, de_factor *F, const double *X, double *Y, int m);
+  void sn_release(struct de_sn_device *S);
+  /** fill H->F (UMFPACK field contract) from the supernodal factor H->sn */
+  int sn_expand_contract(de_host_factor *H);
 
   // ---- de_trsv.cu ---------------------------------------------------------------------------------------------
   int factor_apply_device(de_context *ctx, const de_factor *F, const double *X, double *Y, int m);

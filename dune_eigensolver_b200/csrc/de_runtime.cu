@@ -1068,6 +1068,8 @@ extern "C"
   {
     if (!F)
       return set_error(nullptr, DE_ERR_INVALID, "null host factor");
+    if (F->sn && F->F.n == 0 && sn_expand_contract(const_cast<de_host_factor *>(F)) != DE_OK)
+      return DE_ERR_UNSUPPORTED;
     const de_b200::FactorArrays &A = F->F;
     if (n)
       *n = A.n;

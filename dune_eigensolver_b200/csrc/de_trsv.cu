@@ -142,6 +142,8 @@ namespace dei
     de_factor *F = const_cast<de_factor *>(Fc);
     if (ctx->nranks > 1)
       return set_error(ctx, DE_ERR_UNSUPPORTED, "factored apply is single-GPU (triangular solves do not row-shard)");
+    if (F->sn)
+      return sn_apply_device(ctx, F, X, Y, m);
     DE_TRY(ensure_factor_work(ctx, F, m));
     const long long total = F->n * (m / 2);
     const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 8));
@@ -316,6 +318,8 @@ extern "C"
     dev_free(F->Q);
     dev_free(F->rowscale);
     dev_free(F->W);
+    dev_free(F->W2);
+    sn_release(F->sn);
     delete F;
     context_release(ctx);
     return DE_OK;

@@ -25,7 +25,7 @@ namespace de
 {
 
   /** W(k,:) = scale[k] * X(perm[k],:)   or (scatter != 0)   Y(perm[k],:) = W(k,:) */
-  __global__ void __launch_bounds__(256) permute_rows_kernel(long long n, int m, const int *__restrict__ perm,
+  static __global__ void __launch_bounds__(256) permute_rows_kernel(long long n, int m, const int *__restrict__ perm,
                                                              const double *__restrict__ scale,
                                                              const double *__restrict__ src,
                                                              double *__restrict__ dst, int scatter)
@@ -100,7 +100,7 @@ namespace de
   /** One level, one warp per row. LC lanes cover the column pairs (LC = pow2 >= m/2, <= 32), the remaining
    *  32/LC lane groups split the row's nonzeros and are combined with shuffles. */
   template <int LC>
-  __global__ void __launch_bounds__(256) trsv_level_kernel(const TrsvArgs a, int first, int count)
+  static __global__ void __launch_bounds__(256) trsv_level_kernel(const TrsvArgs a, int first, int count)
   {
     constexpr int NS = 32 / LC;
     const int lane = threadIdx.x & 31;
@@ -138,7 +138,7 @@ namespace de
    *  gives each row 32/R warps (rounded down to a power of two); partial sums meet in shared memory.
    *  W is read with plain (coherent) loads: rows written before the barrier are consumed after it. */
   template <int LC>
-  __global__ void __launch_bounds__(1024) trsv_chain_kernel(const TrsvArgs a, const int *__restrict__ level_ptr,
+  static __global__ void __launch_bounds__(1024) trsv_chain_kernel(const TrsvArgs a, const int *__restrict__ level_ptr,
                                                             int lev_begin, int lev_end)
   {
     constexpr int NS = 32 / LC;

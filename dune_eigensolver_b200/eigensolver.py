@@ -371,11 +371,28 @@ class HostFactorization:
     """One-time host factorisation filling the UMFPACK field contract (reference umfpacktools.hh:26-44):
     stand-in for UMFPackFactorizedMatrix's constructor where UMFPACK is not installed."""
 
-    def __init__(self, A, ordering=1, scale_rows=False):
+    def __init__(self, A, ordering=1, scale_rows=False, spd=False, nthreads=0, arrays=True):
+        """spd: supernodal multifrontal Cholesky (C ABI de_host_factorize_spd; the matrix must be symmetric positive
+        definite) instead of the scalar LU; arrays=False skips the expansion into the explicit L / U arrays of the
+        UMFPACK contract (large factors: upload with Factor.from_host)."""
         rp, ci, v = _csr(A)
         self._h = C.c_void_p()
-        check(capi.lib().de_host_factorize(len(rp) - 1, i64ptr(rp), i64ptr(ci), dptr(v), ordering, int(scale_rows),
-                                           C.byref(self._h)))
+        self.supernodal = bool(spd)
+        if spd:
+            check(capi.lib().de_host_factorize_spd(len(rp) - 1, i64ptr(rp), i64ptr(ci), dptr(v), ordering, int(nthreads),
+                                                   C.byref(self._h)))
+            sn, n_, lnz_, st_, fl_ = C.c_int(0), C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
+            sec = (C.c_double * 3)()
+            check(capi.lib().de_host_factor_info(self._h, C.byref(sn), C.byref(n_), C.byref(lnz_), C.byref(st_),
+                                                 C.byref(fl_), sec))
+            self.info = {"n": n_.value, "lnz": lnz_.value, "stored": st_.value, "flops": fl_.value,
+                         "seconds_ordering": sec[0], "seconds_symbolic": sec[1], "seconds_numeric": sec[2]}
+            self.n, self.lnz, self.unz = n_.value, lnz_.value, lnz_.value
+            if not arrays:
+                return
+        else:
+            check(capi.lib().de_host_factorize(len(rp) - 1, i64ptr(rp), i64ptr(ci), dptr(v), ordering, int(scale_rows),
+                                               C.byref(self._h)))
         n, lnz, unz, rec = C.c_int64(), C.c_int64(), C.c_int64(), C.c_long()
         ptrs = [C.POINTER(C.c_long)(), C.POINTER(C.c_long)(), C.POINTER(C.c_double)(), C.POINTER(C.c_long)(),
                 C.POINTER(C.c_long)(), C.POINTER(C.c_double)(), C.POINTER(C.c_long)(), C.POINTER(C.c_long)(),
@@ -409,10 +426,15 @@ class Factor:
 
     def __init__(self, ctx, F):
         """F: HostFactorization or dict with Lp,Lj,Lx,Up,Ui,Ux,P,Q,Rs,do_recip."""
-        if isinstance(F, HostFactorization):
-            F = F.arrays()
         self.ctx = ctx
         self._h = C.c_void_p()
+        if isinstance(F, HostFactorization) and F.supernodal:
+            # supernodal Cholesky factor: uploaded in its own form (dense panels; csrc/kernels_snode.cuh)
+            check(capi.lib().de_factor_upload_host(ctx._h, F._h, C.byref(self._h)), ctx._h)
+            self.n = F.n
+            return
+        if isinstance(F, HostFactorization):
+            F = F.arrays()
         ia = {k: np.ascontiguousarray(F[k], dtype=np.int64) for k in ("Lp", "Lj", "Up", "Ui", "P", "Q")}
         da = {k: f64(F[k]) for k in ("Lx", "Ux", "Rs")}
         n = len(ia["Lp"]) - 1
@@ -575,9 +597,12 @@ def StandardInverse(ctx, A, shift, tol, maxiter, nev, verbose=0, seed=123, start
     return Result(ev, V, it.value)
 
 
-def GeneralizedInverse(ctx, inA, B, shift, reg, tol, maxiter, nev, verbose=0, seed=123, start=None, ordering=1):
+def GeneralizedInverse(ctx, inA, B, shift, reg, tol, maxiter, nev, verbose=0, seed=123, start=None, ordering=1,
+                       factorization="lu", nthreads=0):
     """reference GeneralizedInverse (eigensolver.hh:204-351): A x = lambda B x by shift-invert subspace iteration.
-    The input matrix is copied (eigensolver.hh:208); pattern(B) must be contained in pattern(A)."""
+    The input matrix is copied (eigensolver.hh:208); pattern(B) must be contained in pattern(A).
+    factorization: "lu" (scalar sparse LU filling the UMFPACK contract) or "cholesky" (supernodal multifrontal Cholesky
+    for symmetric positive definite A + shift B: the provider for 3D problems)."""
     import time
 
     rpa, cia, va = inA if isinstance(inA, tuple) else (inA.indptr, inA.indices, inA.data)
@@ -601,7 +626,8 @@ def GeneralizedInverse(ctx, inA, B, shift, reg, tol, maxiter, nev, verbose=0, se
     if reg != 0.0:
         _add_to_diagonal(rpa, cia, va, reg)
     t0 = time.perf_counter()
-    hF = HostFactorization((rpa, cia, va), ordering)
+    hF = HostFactorization((rpa, cia, va), ordering, spd=(factorization == "cholesky"), nthreads=nthreads, arrays=False) \
+        if factorization == "cholesky" else HostFactorization((rpa, cia, va), ordering)
     t_fact = time.perf_counter() - t0
     dA, dB = Matrix(ctx, (rpa, cia, va)), Matrix(ctx, (rpb, cib, vb))
     dF = Factor(ctx, hF)
@@ -617,7 +643,9 @@ def GeneralizedInverse(ctx, inA, B, shift, reg, tol, maxiter, nev, verbose=0, se
         hF.close()
     if verbose > 0:  # the reference's summary line (eigensolver.hh:344-350)
         print("GeneralizedInverse:  time_factorization=%g iterations=%d relerror=%g" % (t_fact, it.value, rel.value))
-    return Result(ev, V, it.value, rel.value, t_fact)
+    res = Result(ev, V, it.value, rel.value, t_fact)
+    res.factor_info = getattr(hF, "info", None)
+    return res
 
 
 # ---- LOBPCG drivers (new: the reference has none; SURVEY.md §8f rank 1, BASELINE.json configs[1]) ----------------

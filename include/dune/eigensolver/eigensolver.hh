@@ -149,7 +149,7 @@ void StandardInverse(ISTLM &A, double shift, double tol, int maxiter, int nev, s
   auto &ctx = de_b200::Context::thread_default();
   de_b200::DeviceMatrix dA(ctx, A);
   de_factor *dF = nullptr;
-  de_b200::check(de_factor_upload(ctx.get(), F.n, F.Lp, F.Lj, F.Lx, F.Up, F.Ui, F.Ux, F.P, F.Q, F.Rs, F.do_recip, &dF),
+  de_b200::check(F.upload(ctx.get(), &dF),
                  ctx.get());
   std::vector<double> values(nev), vectors((std::size_t)nev * n);
   int iterations = 0;
@@ -187,7 +187,7 @@ void GeneralizedInverse(const ISTLM &inA, const ISTLM &B, double shift, double r
   auto &ctx = de_b200::Context::thread_default();
   de_b200::DeviceMatrix dA(ctx, A), dB(ctx, B);
   de_factor *dF = nullptr;
-  de_b200::check(de_factor_upload(ctx.get(), F.n, F.Lp, F.Lj, F.Lx, F.Up, F.Ui, F.Ux, F.P, F.Q, F.Rs, F.do_recip, &dF),
+  de_b200::check(F.upload(ctx.get(), &dF),
                  ctx.get());
   std::vector<double> values(nev), vectors((std::size_t)nev * n);
   int iterations = 0;

@@ -131,7 +131,7 @@ void matmul_inverse_tallskinny_blocked(MV &Qout, UMFPackFactorizedMatrix<MAT> &F
     throw std::invalid_argument("matmul_inverse_tallskinny_blocked: Factorization does not match size of Qout/Qin");
   auto &ctx = de_b200::Context::thread_default();
   de_factor *dF = nullptr;
-  de_b200::check(de_factor_upload(ctx.get(), F.n, F.Lp, F.Lj, F.Lx, F.Up, F.Ui, F.Ux, F.P, F.Q, F.Rs, F.do_recip, &dF),
+  de_b200::check(F.upload(ctx.get(), &dF),
                  ctx.get());
   try
   {

@@ -356,6 +356,21 @@ int de_host_factor_arrays(const de_host_factor *F, int64_t *n, int64_t *lnz, int
                           const long **Lj, const double **Lx, const long **Up, const long **Ui, const double **Ux,
                           const long **P, const long **Q, const double **Rs, long *do_recip);
 int de_host_factor_destroy(de_host_factor *F);
+/* Second host provider, for LARGE symmetric positive definite matrices (3D pencils, BASELINE.json configs[2]): supernodal
+ * multifrontal Cholesky P A P^T = L L^T with nested dissection (include/dune/eigensolver/supernodal_cholesky.hh),
+ * multi-threaded (nthreads <= 0: all cores). The factor stays in supernodal form -- dense column blocks, 8 bytes per
+ * entry -- which is also what the device apply uses (dense panels instead of scalar level schedules, csrc/kernels_snode.cuh).
+ * DE_ERR_SINGULAR if the matrix is not positive definite (use de_host_factorize). de_host_factor_arrays works on such a
+ * factor too: the UMFPACK field contract (L unit lower by rows, U = D L^T by columns, P = Q, Rs = 1) is expanded on
+ * first use -- meant for factors of moderate size (parity tests against the reference's own apply). */
+int de_host_factorize_spd(int64_t n, const int64_t *rowptr, const int64_t *col, const double *val, int ordering, int nthreads,
+                          de_host_factor **out);
+/* supernodal: 1 for a de_host_factorize_spd factor; lnz: entries of L; stored: doubles held (explicit zeros of the
+ * supernodal blocks included); flops of the numeric factorisation; seconds3 = {ordering, symbolic, numeric}. Any may be NULL. */
+int de_host_factor_info(const de_host_factor *F, int *supernodal, int64_t *n, int64_t *lnz, int64_t *stored, double *flops,
+                        double *seconds3);
+/* device copy of a host factorisation of either kind, ready for de_factor_apply and the drivers */
+int de_factor_upload_host(de_context *ctx, const de_host_factor *F, de_factor **out);
 
 #ifdef __cplusplus
 }

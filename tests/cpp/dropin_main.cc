@@ -192,6 +192,25 @@ int main(int argc, char **argv)
       return run_bcsr<2>(N, nev, tol);
     else if (mode == "bcsr3")
       return run_bcsr<3>(N, nev, tol);
+    else if (mode == "cholesky")
+    {
+      // the second factorisation provider through the header: supernodal Cholesky inside the library, factored apply on
+      // the GPU (dense panels), public UMFPACK-contract members expanded from it
+      Matrix A = laplacian(N, "dirichlet", 0);
+      UMFPackFactorizedMatrix<Matrix> F(A, 0, de_b200::Ordering::nested_dissection, de_b200::Provider::cholesky);
+      MultiVector<double, 8> X = de_b200::random_start_block(n, 16, 5), B{n, 16}, Y{n, 16};
+      matmul_sparse_tallskinny_blocked(B, A, X);
+      matmul_inverse_tallskinny_blocked(Y, F, B);
+      double err = 0.0;
+      for (std::size_t i = 0; i < n; ++i)
+        for (std::size_t j = 0; j < 16; ++j)
+          err = std::max(err, std::abs(Y(i, j) - X(i, j)));
+      std::printf("supernodal %d\n", (int)F.supernodal());
+      std::printf("contract %d %ld %ld\n", (int)(F.Lp != nullptr && F.Ux != nullptr), (long)F.n, (long)F.lnz);
+      std::printf("solve_error %.3e\n", err);
+      // Provider::automatic picks it for large symmetric matrices: shift-invert driver on the same grid
+      StandardInverse(A, 1e-3, tol, 4000, nev, eval, evec, 0, 123);
+    }
     else if (mode == "kernels")
     {
       Matrix A = laplacian(N, "dirichlet", 0);

@@ -184,3 +184,18 @@ def test_bcsr_matrix_through_the_c_abi(ctx, oracle, k):
     assert np.abs(dY.download() - ref).max() <= 1e-13 * np.abs(ref).max()
     for h in (dA, dX, dY):
         h.close()
+
+
+@pytest.mark.gpu
+def test_dropin_cholesky_provider():
+    """UMFPackFactorizedMatrix with Provider::cholesky (explicit) and Provider::automatic (n >= 50 000, symmetric: N = 230)"""
+    rc, vals, text = run("cholesky", 40, 8, 1e-10)
+    assert rc == 0, text
+    assert vals["supernodal"] == "1" and vals["contract"].split()[0] == "1" and int(vals["contract"].split()[1]) == 1600
+    assert float(vals["solve_error"]) < 1e-11
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(40)[:8]).max() < 1e-9
+    rc, vals, text = run("inverse", 230, 8, 1e-9)  # automatic: supernodal Cholesky of the shifted Laplacian
+    assert rc == 0, text
+    ev = np.array([float(x) for x in vals["eval"].split()])
+    assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(230)[:8]).max() < 1e-8
