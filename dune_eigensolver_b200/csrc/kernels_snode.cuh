@@ -28,7 +28,7 @@ namespace de
 {
 
   constexpr int kSnPanel = 32; // columns per panel
-  constexpr int kSnTile = 64;  // rows below the panel per CTA
+  constexpr int kSnTile = 64;  // rows below the panel per CTA (128: 1.6x slower -- the top levels are latency-bound and want many short CTAs)
   constexpr int kSnThreads = 256;
 
   struct SnPanel
