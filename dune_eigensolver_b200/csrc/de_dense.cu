@@ -506,13 +506,13 @@ namespace dei
     if (count > 0)
       DE_CUDA(ctx, cudaMemcpyAsync(ctx->hsmall, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     DE_CUDA(ctx, cudaMemcpyAsync(ctx->hstatus, ctx->dstatus, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->hflags[7] = 0;
+    ctx->hflags[8] = 0;
     if (ctx->peer_ready)
-      DE_CUDA(ctx, cudaMemcpyAsync(ctx->hflags + 7, ctx->dticket + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      DE_CUDA(ctx, cudaMemcpyAsync(ctx->hflags + 8, ctx->dticket + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->hflags[7] != 0)
+    if (ctx->hflags[8] != 0)
     {
-      const int w = ctx->hflags[7];
+      const int w = ctx->hflags[8];
       return set_error(ctx, DE_ERR_NCCL,
                        std::string("NVLink peer window: rank ") + std::to_string(ctx->rank) + " gave up waiting for the " +
                            ((w & 15) == 2 ? "halo rows" : "all-reduce contribution") + " of rank " + std::to_string((w >> 4) & 15) +

@@ -317,17 +317,18 @@ extern "C"
     const auto t_enq0 = std::chrono::steady_clock::now();
     double t_wait = 0.0;
     int slot = 0;
-    for (int k = 1; k < maxiter && !finished; ++k)
-    {
+    // one iteration of the loop as a sequence of launches. The iteration number is kept on the device (dflags[3], see
+    // convergence_body): the same sequence can then be replayed from a CUDA graph.
+    auto iteration = [&]() -> int {
       if (!have_product)
         DE_TRY(spmm_device(ctx, A, Qa, Qb, m, false)); // Qb = A Qa (:78)
       DE_TRY(orthonormalize_device(ctx, n, m, Qb, have_gram ? ctx->dDG() + m : nullptr)); // (:81)
-      // Qa = A Qb, dp = diag(Qb^T Qa) (:84-85) and, in the same pass, G = Qa^T Qa for the next orthonormalisation
-      // ... and the convergence test as the tail of the reduction of the dot-product partials
+      // Qa = A Qb, dp = diag(Qb^T Qa) (:84-85) and the convergence test as the tail of the reduction of the dot-product
+      // partials -- or, deferred, of the next iteration's first Gram reduction
       ctx->tail = de::TailArgs{};
       ctx->tail.kind = de::kTailConv;
       ctx->tail.m = m;
-      ctx->tail.k = k;
+      ctx->tail.k = -1;
       ctx->tail.shift = shift;
       ctx->tail.tol = tol;
       ctx->tail.s_prev = s_prev;
@@ -342,31 +343,89 @@ extern "C"
         ctx->tail_did_op = false;
       else
       {
-        DE_REG(de::convergence_kernel), de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(k, m, shift, tol, ctx->dDP(), s_prev, hist, ctx->dflags);
+        DE_REG(de::convergence_kernel), de::convergence_kernel<<<1, 64, 0, ctx->stream>>>(-1, m, shift, tol, ctx->dDP(), s_prev, hist, ctx->dflags);
         DE_LAUNCH_CHECK(ctx);
       }
       ctx->tail_armed = false;
       std::swap(Qa, Qb); // now Qa orthonormal, Qb = A*Qa
       have_product = true;
+      return DE_OK;
+    };
+    auto poll = [&]() -> int {
+      // look at the copy requested one batch ago (it has almost always landed), then request a new one
+      const int prev = slot ^ 1;
+      if (pending[prev])
+      {
+        const auto tw0 = std::chrono::steady_clock::now();
+        DE_CUDA(ctx, cudaEventSynchronize(ctx->ev_poll[prev]));
+        t_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count();
+        pending[prev] = 0;
+        if (ctx->hflags[4 * prev + 1] != 0)
+          finished = true;
+      }
+      DE_CUDA(ctx, cudaMemcpyAsync(ctx->hflags + 4 * slot, ctx->dflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      DE_CUDA(ctx, cudaEventRecord(ctx->ev_poll[slot], ctx->stream));
+      pending[slot] = 1;
+      slot ^= 1;
+      return DE_OK;
+    };
+    // Steady state = kPollEvery iterations (an even number: the blocks swap roles every iteration) captured ONCE in a CUDA
+    // graph and replayed: one launch call instead of ~28, and graph-internal launch latency between the dependent
+    // kernels. Only on one GPU (the peer epochs of the multi-GPU path are baked into the launches) and without the
+    // per-kernel timers. The first two iterations run as plain launches (the first one has an extra SpMM).
+    static_assert(kPollEvery % 2 == 0, "a graph of the loop must leave the two blocks in their original roles");
+    cudaGraphExec_t loop_graph = nullptr;
+    long long graph_nodes = 0;
+    struct GraphGuard
+    {
+      cudaGraphExec_t &g;
+      ~GraphGuard()
+      {
+        if (g)
+          cudaGraphExecDestroy(g);
+      }
+    } graph_guard{loop_graph};
+    const bool want_graph = ctx->nranks <= 1 && !ctx->profiling && ctx->use_loop_graph && ctx->defer_dot;
+    int k = 1;
+    while (k < maxiter && !finished)
+    {
+      if (want_graph && loop_graph == nullptr && k == 3 && k + kPollEvery <= maxiter)
+      {
+        cudaGraph_t graph = nullptr;
+        const long long before = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess)
+        {
+          int rc = DE_OK;
+          for (int q = 0; q < kPollEvery && rc == DE_OK; ++q)
+            rc = iteration();
+          const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+          graph_nodes = ctx->launches - before;
+          ctx->launches = before;
+          if (rc != DE_OK || ce != cudaSuccess || graph == nullptr || cudaGraphInstantiate(&loop_graph, graph, 0) != cudaSuccess)
+            loop_graph = nullptr;
+          if (graph)
+            cudaGraphDestroy(graph);
+          cudaGetLastError();
+          if (rc != DE_OK)
+            return rc;
+          if (loop_graph == nullptr)
+            return set_error(ctx, DE_ERR_CUDA, "StandardLargest: capturing the iteration graph failed");
+        }
+      }
+      if (loop_graph != nullptr && k + kPollEvery <= maxiter)
+      {
+        DE_CUDA(ctx, cudaGraphLaunch(loop_graph, ctx->stream));
+        ctx->launches += graph_nodes;
+        k += kPollEvery;
+        enqueued += kPollEvery;
+        DE_TRY(poll());
+        continue;
+      }
+      DE_TRY(iteration());
+      ++k;
       ++enqueued;
       if (enqueued % kPollEvery == 0)
-      {
-        // look at the copy requested one batch ago (it has almost always landed), then request a new one
-        const int prev = slot ^ 1;
-        if (pending[prev])
-        {
-          const auto tw0 = std::chrono::steady_clock::now();
-          DE_CUDA(ctx, cudaEventSynchronize(ctx->ev_poll[prev]));
-          t_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw0).count();
-          pending[prev] = 0;
-          if (ctx->hflags[4 * prev + 1] != 0)
-            finished = true;
-        }
-        DE_CUDA(ctx, cudaMemcpyAsync(ctx->hflags + 4 * slot, ctx->dflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        DE_CUDA(ctx, cudaEventRecord(ctx->ev_poll[slot], ctx->stream));
-        pending[slot] = 1;
-        slot ^= 1;
-      }
+        DE_TRY(poll());
     }
     DE_TRY(flush_pending_dot(ctx)); // the last iteration's Rayleigh quotients have no following Gram reduction
     ctx->defer_dot = false;

@@ -77,13 +77,14 @@ struct de_context
   int *dstatus = nullptr;     // sticky Cholesky status
   int *dflags = nullptr;      // device flags: [0] second CholQR sweep not needed, [1] driver loop converged, [2] last iteration
   const int *done_ptr = nullptr; // = dflags + 1 while an asynchronous driver loop is enqueuing, else null
-  int *hflags = nullptr;      // pinned: 2 slots x 4 ints, polled copies of dflags
+  int *hflags = nullptr;      // pinned: 2 slots x 4 ints, polled copies of dflags; [8] = copy of the peer error flag (fetch_small)
   cudaEvent_t ev_poll[2] = {nullptr, nullptr};
   double *dconv = nullptr;    // s_prev[64] | hist[dconv_cap]
   void *xfer = nullptr;       // XferEngine: pinned staging buffers and copy streams (created on first use)
   // NVLink peer window (kernels_peer.cuh); peer_ready once every rank's window is mapped
   bool peer_ready = false;
   bool pdl = true;      // programmatic dependent launch of the loop kernels (off when ranks share a device)
+  bool use_loop_graph = true; // StandardLargest: replay the steady-state iterations from a CUDA graph (one GPU)
   long long peer_timeout_cycles = 60000000000LL; // spins on peer flags give up after this many clocks (~30 s)
   bool peer_ipc = true; // peer windows were opened from CUDA IPC handles (else: same-process allocations, de_multi.cu)
   unsigned char *window = nullptr;

@@ -517,6 +517,8 @@ extern "C"
     if (!ctx)
       return set_error(nullptr, DE_ERR_ALLOC, "de_context_create: out of host memory");
     ctx->device = device;
+    if (const char *g = std::getenv("DE_B200_LOOP_GRAPH")) // "0": plain launches in the StandardLargest loop (A/B measurements)
+      ctx->use_loop_graph = g[0] != '0';
     auto bail = [&](int code) {
       std::string msg = ctx->err;
       de_context_destroy(ctx);
@@ -550,7 +552,7 @@ extern "C"
               cudaMemset(ctx->dflags, 0, 4 * sizeof(int)) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->hsmall, kSmall * sizeof(double)) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->hstatus, sizeof(int)) == cudaSuccess &&
-              cudaMallocHost((void **)&ctx->hflags, 8 * sizeof(int)) == cudaSuccess &&
+              cudaMallocHost((void **)&ctx->hflags, 12 * sizeof(int)) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_poll[0], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_poll[1], cudaEventDisableTiming) == cudaSuccess &&
               cudaMemset(ctx->dstatus, 0, sizeof(int)) == cudaSuccess;

@@ -518,6 +518,11 @@ namespace de
       double mx = 0.0;
       for (int q = 0; q < 64; ++q)
         mx = fmax(mx, red[q]);
+      if (k < 0) // the iteration number lives on the device (flags[3]): launches replayed from a CUDA graph carry no number
+      {
+        k = flags[3] + 1;
+        flags[3] = k;
+      }
       hist[k] = mx;
       flags[2] = k;
       if (k > 1 && mx < tol)

@@ -421,6 +421,31 @@ class HostFactorization:
             pass
 
 
+AUTO_CHOLESKY_FROM_ROWS = 10000
+
+
+def host_factorization(A, ordering=1, factorization="auto", nthreads=0):
+    """the host provider the drivers use: see GeneralizedInverse"""
+    rp, ci, v = _csr(A)
+    n = len(rp) - 1
+    if factorization == "auto":
+        factorization = "lu"
+        if n >= AUTO_CHOLESKY_FROM_ROWS:
+            import scipy.sparse as sp
+
+            S = sp.csr_matrix((v, ci, rp), shape=(n, n))
+            D = abs(S - S.T)
+            if D.nnz == 0 or D.max() <= 1e-13 * abs(S).max():
+                try:
+                    return HostFactorization((rp, ci, v), ordering, spd=True, nthreads=nthreads, arrays=False)
+                except DeError as e:
+                    if e.status != capi.DE_ERR_SINGULAR:
+                        raise
+    if factorization == "cholesky":
+        return HostFactorization((rp, ci, v), ordering, spd=True, nthreads=nthreads, arrays=False)
+    return HostFactorization((rp, ci, v), ordering)
+
+
 class Factor:
     """Device copy of a factorisation in the UMFPACK field contract, with its level schedules."""
 
@@ -574,7 +599,7 @@ def standard_inverse_mv(ctx, dA, dF, shift, tol, maxiter, Q, verbose=0):
     return ev, it.value
 
 
-def StandardInverse(ctx, A, shift, tol, maxiter, nev, verbose=0, seed=123, start=None, ordering=1):
+def StandardInverse(ctx, A, shift, tol, maxiter, nev, verbose=0, seed=123, start=None, ordering=1, factorization="auto"):
     """reference StandardInverse (eigensolver.hh:116-198)."""
     rp, ci, v = A if isinstance(A, tuple) else (A.indptr, A.indices, A.data)
     n = len(rp) - 1
@@ -583,7 +608,7 @@ def StandardInverse(ctx, A, shift, tol, maxiter, nev, verbose=0, seed=123, start
         start = start_block(n, m, seed)
     if shift != 0.0:
         _add_to_diagonal(np.asarray(rp), np.asarray(ci), v, shift)
-    hF = HostFactorization((rp, ci, v), ordering)
+    hF = host_factorization((rp, ci, v), ordering, factorization)
     dA = Matrix(ctx, (rp, ci, v))
     dF = Factor(ctx, hF)
     try:
@@ -598,11 +623,12 @@ def StandardInverse(ctx, A, shift, tol, maxiter, nev, verbose=0, seed=123, start
 
 
 def GeneralizedInverse(ctx, inA, B, shift, reg, tol, maxiter, nev, verbose=0, seed=123, start=None, ordering=1,
-                       factorization="lu", nthreads=0):
+                       factorization="auto", nthreads=0):
     """reference GeneralizedInverse (eigensolver.hh:204-351): A x = lambda B x by shift-invert subspace iteration.
     The input matrix is copied (eigensolver.hh:208); pattern(B) must be contained in pattern(A).
-    factorization: "lu" (scalar sparse LU filling the UMFPACK contract) or "cholesky" (supernodal multifrontal Cholesky
-    for symmetric positive definite A + shift B: the provider for 3D problems)."""
+    factorization: "lu" (scalar sparse LU filling the UMFPACK contract), "cholesky" (supernodal multifrontal Cholesky
+    for symmetric positive definite A + shift B: the provider for 3D problems) or "auto" (Cholesky for symmetric
+    matrices with at least 10 000 rows, falling back to LU if a pivot is not positive -- what the C++ header does)."""
     import time
 
     rpa, cia, va = inA if isinstance(inA, tuple) else (inA.indptr, inA.indices, inA.data)
@@ -626,8 +652,7 @@ def GeneralizedInverse(ctx, inA, B, shift, reg, tol, maxiter, nev, verbose=0, se
     if reg != 0.0:
         _add_to_diagonal(rpa, cia, va, reg)
     t0 = time.perf_counter()
-    hF = HostFactorization((rpa, cia, va), ordering, spd=(factorization == "cholesky"), nthreads=nthreads, arrays=False) \
-        if factorization == "cholesky" else HostFactorization((rpa, cia, va), ordering)
+    hF = host_factorization((rpa, cia, va), ordering, factorization, nthreads)
     t_fact = time.perf_counter() - t0
     dA, dB = Matrix(ctx, (rpa, cia, va)), Matrix(ctx, (rpb, cib, vb))
     dF = Factor(ctx, hF)

@@ -40,7 +40,7 @@ namespace de_b200
     lu,
     cholesky
   };
-  constexpr long kCholeskyFromRows = 50000;         // automatic: below this size the LU provider is used
+  constexpr long kCholeskyFromRows = 10000;         // automatic: below this size the LU provider is used
   constexpr long kContractMaxEntries = 150000000L;  // explicit L / U arrays are only materialised up to this many entries
 } // namespace de_b200
 

@@ -188,14 +188,14 @@ def test_bcsr_matrix_through_the_c_abi(ctx, oracle, k):
 
 @pytest.mark.gpu
 def test_dropin_cholesky_provider():
-    """UMFPackFactorizedMatrix with Provider::cholesky (explicit) and Provider::automatic (n >= 50 000, symmetric: N = 230)"""
+    """UMFPackFactorizedMatrix with Provider::cholesky (explicit) and Provider::automatic (n >= 10 000, symmetric: N = 110)"""
     rc, vals, text = run("cholesky", 40, 8, 1e-10)
     assert rc == 0, text
     assert vals["supernodal"] == "1" and vals["contract"].split()[0] == "1" and int(vals["contract"].split()[1]) == 1600
     assert float(vals["solve_error"]) < 1e-11
     ev = np.array([float(x) for x in vals["eval"].split()])
     assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(40)[:8]).max() < 1e-9
-    rc, vals, text = run("inverse", 230, 8, 1e-9)  # automatic: supernodal Cholesky of the shifted Laplacian
+    rc, vals, text = run("inverse", 110, 8, 1e-9)  # automatic (n = 12 100 >= 10 000): supernodal Cholesky of the shifted Laplacian
     assert rc == 0, text
     ev = np.array([float(x) for x in vals["eval"].split()])
-    assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(230)[:8]).max() < 1e-8
+    assert np.abs(ev - M.eigenvalues_laplace_dirichlet_2d(110)[:8]).max() < 1e-8

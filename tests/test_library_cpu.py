@@ -201,3 +201,25 @@ def test_c_abi_from_plain_c99(oracle):
         has_gpu = False
     if not has_gpu:
         assert f[8] == "3" and "no CPU fallback" in out.stdout
+
+
+def test_lu_provider_rejects_what_static_pivoting_cannot_factor():
+    """the LU provider has no numerical pivoting; an indefinite matrix (shift inside the spectrum) must
+    raise instead of silently returning an inaccurate factor. [[eps, 1], [1, eps]]-like 2 x 2 blocks need pivoting."""
+    import scipy.sparse as sp
+
+    from dune_eigensolver_b200 import eigensolver as E
+
+    n = 40
+    blocks = [np.array([[1e-14, 1.0], [1.0, 1e-14]])] * (n // 2)
+    S = sp.block_diag(blocks, format="csr") + 1e-3 * sp.diags([np.ones(n - 1), np.ones(n - 1)], [-1, 1], format="csr")
+    S = S.tocsr()
+    S.sort_indices()
+    with pytest.raises(E.DeError) as e:
+        E.HostFactorization((S.indptr, S.indices, S.data), ordering=0)
+    assert "backward-error" in str(e.value) or "singular" in str(e.value)
+    # a well-posed shifted Laplacian still factors, and its backward error is at round-off
+    A = M.laplacian_dirichlet_2d(12)
+    hF = E.HostFactorization(A)
+    assert hF.lnz > 0
+    hF.close()
