@@ -190,6 +190,9 @@ namespace dei
       const int grid2 = (int)std::max<long long>(1, std::min<long long>(nt2, (long long)ctx->sm_count));
       a.partials = reduction_partials(ctx);
       a.done = ctx->done_ptr;
+      a.push = de::PushRanges{};
+      if (ctx->push_pending.n > 0 && a.ldo == M) // orthonormalize_device(..., next_spmm): halo rows go out with the update
+        a.push = ctx->push_pending;
       {
         ProfScope prof(ctx, DE_PROF_UPDATE);
         DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::ts2_update_kernel<M, DO_GRAM>), dim3(grid2), dim3(C2::THREADS), C2::SMEM, ctx->stream, a));
@@ -437,10 +440,23 @@ namespace dei
    *  kernels_cpp.hh:180-351). Two CholQR sweeps over the WHOLE block: G = X^T X, R = chol(G), X <- X R^-1.
    *  The triangular factor of a full-rank block is unique, so the result equals the reference's block
    *  Gram-Schmidt up to round-off; the second sweep restores orthogonality to O(eps) for cond(X) < ~1e7. */
-  int orthonormalize_device(de_context *ctx, long long n, int m, double *X, const double *G_ready)
+  int orthonormalize_device(de_context *ctx, long long n, int m, double *X, const double *G_ready, const de_matrix *next_spmm)
   {
     if (ts_supported(m))
     {
+      // next_spmm: the caller's next distributed SpMM is A X with this X -- its halo rows leave with the block updates
+      struct PushGuard
+      {
+        de_context *c;
+        ~PushGuard() { c->push_pending.n = 0; }
+      } push_guard{ctx};
+      if (next_spmm != nullptr && next_spmm->n == n && plan_fused_push(ctx, next_spmm, m))
+      {
+        ctx->prepushed_X = X;
+        ctx->prepushed_A = next_spmm;
+        ctx->prepushed_epoch = ctx->halo_epoch + 1;
+        ctx->prepushed_m = m;
+      }
       // sweep 1: G = X^T X (already known if the SpMM that produced X ran its Gram epilogue) ; R1 = chol(G) ;
       // X <- X R1^-1 fused with G2 = X^T X of the result
       if (G_ready == nullptr)

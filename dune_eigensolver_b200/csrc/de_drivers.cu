@@ -322,7 +322,7 @@ extern "C"
     auto iteration = [&]() -> int {
       if (!have_product)
         DE_TRY(spmm_device(ctx, A, Qa, Qb, m, false)); // Qb = A Qa (:78)
-      DE_TRY(orthonormalize_device(ctx, n, m, Qb, have_gram ? ctx->dDG() + m : nullptr)); // (:81)
+      DE_TRY(orthonormalize_device(ctx, n, m, Qb, have_gram ? ctx->dDG() + m : nullptr, A)); // (:81)
       // Qa = A Qb, dp = diag(Qb^T Qa) (:84-85) and the convergence test as the tail of the reduction of the dot-product
       // partials -- or, deferred, of the next iteration's first Gram reduction
       ctx->tail = de::TailArgs{};

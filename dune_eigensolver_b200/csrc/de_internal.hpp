@@ -91,6 +91,15 @@ struct de_context
   size_t window_bytes = 0, halo_cap = 0;
   unsigned char *peer_base[de::kPeerMaxRanks] = {};
   unsigned long long ar_epoch = 0, halo_epoch = 0;
+  // halo rows stored by the block-update kernels of an orthonormalisation (plan_fused_push, de_spmm.cu): push_pending is
+  // what the next ts2_update launches add to their arguments; prepushed_* say which SpMM call finds its halo rows already
+  // in the neighbours' windows (that call only releases the flags)
+  de::PushRanges push_pending{};
+  bool fused_push = true;
+  const double *prepushed_X = nullptr;
+  const de_matrix *prepushed_A = nullptr;
+  unsigned long long prepushed_epoch = 0;
+  int prepushed_m = 0;
   int *dticket = nullptr; // [0] ticket of halo_push_kernel, [1] peer error flag
   // fused tail of the NEXT partial-sum reduction (kernels_tail.cuh): set by the caller, consumed by reduce_partials
   de::TailArgs tail{};
@@ -220,6 +229,7 @@ struct de_matrix
   BrbDevice brb;
   bool peer_halo = false;            // halo rows travel as peer stores into the neighbours' windows
   std::vector<long long> deposit;    // [npeers] first row of this rank's rows in peer p's halo block
+  std::vector<long long> send_first; // [npeers] first of the CONSECUTIVE rows sent to peer p, -1 if they are not consecutive
   long long halo_rows_max = 0;       // largest halo block over ALL ranks: peer path or NCCL must be the same decision everywhere
   int spmm_format = DE_SPMM_AUTO; // which SpMM kernel family to use (de_matrix_set_spmm_format)
 };
@@ -444,7 +454,9 @@ namespace dei
                     int ldy, int upper, const int *skip_flag = nullptr);
   int chol_inverse(de_context *ctx, int m, const double *G, double *Rinv, double *info, int *identity_flag = nullptr);
   void arm_chol_tail(de_context *ctx, int m, double *Rinv, double *info, int *identity_flag);
-  int orthonormalize_device(de_context *ctx, long long n, int m, double *X, const double *G_ready = nullptr);
+  int orthonormalize_device(de_context *ctx, long long n, int m, double *X, const double *G_ready = nullptr,
+                            const de_matrix *next_spmm = nullptr);
+  bool plan_fused_push(de_context *ctx, const de_matrix *A, int m);
   int b_orthonormalize_device(de_context *ctx, const de_matrix *B, long long n, int m, double *X, double *BX, bool want_info);
   int reset_status(de_context *ctx);
   int fetch_small(de_context *ctx, const double *dsrc, double *hdst, size_t count);

@@ -517,6 +517,8 @@ extern "C"
     if (!ctx)
       return set_error(nullptr, DE_ERR_ALLOC, "de_context_create: out of host memory");
     ctx->device = device;
+    if (const char *g = std::getenv("DE_B200_FUSED_PUSH")) // "0": halo rows always pushed by halo_push_kernel (A/B measurements)
+      ctx->fused_push = g[0] != '0';
     if (const char *g = std::getenv("DE_B200_LOOP_GRAPH")) // "0": plain launches in the StandardLargest loop (A/B measurements)
       ctx->use_loop_graph = g[0] != '0';
     auto bail = [&](int code) {

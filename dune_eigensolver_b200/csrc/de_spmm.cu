@@ -477,6 +477,11 @@ namespace dei
     const bool peer_path = ctx->nranks > 1 && ctx->peer_ready && A->peer_halo &&
                            (size_t)A->halo_rows_max * m * sizeof(double) <= ctx->halo_cap && A->npeers <= de::kPeerMaxRanks;
     const unsigned long long halo_epoch = peer_path ? ++ctx->halo_epoch : 0ull;
+    struct ClearPrepushed
+    {
+      de_context *c;
+      ~ClearPrepushed() { c->prepushed_X = nullptr; }
+    } clear_prepushed{ctx};
     // GRAM epilogue: the caller can use G = Y^T Y (in ctx->dDG() + m); only the tensor-core kernel has it
     const bool gram = DOT && gram_out != nullptr && brb_usable(A, m) && brb_gram_epilogue(m);
     if (gram_out)
@@ -520,8 +525,14 @@ namespace dei
           h.m = m;
           h.halo_cap_bytes = ctx->halo_cap;
           h.ticket = ctx->dticket;
-          const long long total = A->n_send * (m / 2);
-          const int grid = (int)std::min<long long>((total + 255) / 256, ctx->sm_count * 4);
+          // rows already stored by the block-update kernels of the orthonormalisation that produced X (plan_fused_push)?
+          const bool prepushed = ctx->prepushed_X == X && ctx->prepushed_A == A && ctx->prepushed_epoch == halo_epoch &&
+                                 ctx->prepushed_m == m;
+          if (prepushed)
+            for (int p = 0; p <= A->npeers; ++p)
+              h.send_off[p] = 0; // nothing to copy: the launch only releases the flags
+          const long long total = prepushed ? 0 : A->n_send * (m / 2);
+          const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 4));
           ProfScope prof(ctx, DE_PROF_HALO_PUSH);
           DE_REG(de::halo_push_kernel), de::halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(pa, h);
           DE_LAUNCH_CHECK(ctx);
@@ -622,6 +633,39 @@ namespace dei
       DE_TRY(allreduce_sum(ctx, ctx->dDG(), (size_t)len));
     }
     return DE_OK;
+  }
+
+  /** Can the block-update kernels of an orthonormalisation store the halo rows of the NEXT SpMM with A (width m)
+   *  straight into the neighbours' windows? Needs the peer path, at most two neighbours and consecutive send rows (what a
+   *  slab partition gives). Fills ctx->push_pending for halo epoch ctx->halo_epoch + 1. The decision depends on this
+   *  rank's lists only: a rank that pushes early and one that pushes in its SpMM call interoperate (the receiver only
+   *  looks at the flag). */
+  bool plan_fused_push(de_context *ctx, const de_matrix *A, int m)
+  {
+    ctx->push_pending.n = 0;
+    if (!ctx->fused_push || !A || ctx->nranks <= 1 || !ctx->peer_ready || !A->peer_halo || A->n_send <= 0 ||
+        (size_t)A->halo_rows_max * m * sizeof(double) > ctx->halo_cap || A->npeers > de::kPeerMaxRanks)
+      return false;
+    int cnt = 0;
+    for (int p = 0; p < A->npeers; ++p)
+      if (A->send_count[p] > 0)
+      {
+        if (cnt == 2 || (size_t)p >= A->send_first.size() || A->send_first[p] < 0)
+          return false;
+        ++cnt;
+      }
+    const unsigned long long epoch = ctx->halo_epoch + 1;
+    de::PushRanges &r = ctx->push_pending;
+    for (int p = 0; p < A->npeers; ++p)
+      if (A->send_count[p] > 0)
+      {
+        r.lo[r.n] = A->send_first[p];
+        r.hi[r.n] = A->send_first[p] + A->send_count[p];
+        r.dst[r.n] = reinterpret_cast<double *>(ctx->peer_base[A->peer[p]] + de::kPeerHaloOff + (size_t)(epoch & 1ull) * ctx->halo_cap) +
+                     (size_t)A->deposit[p] * m;
+        ++r.n;
+      }
+    return r.n > 0;
   }
 
   int spmm_device(de_context *ctx, const de_matrix *A, const double *X, double *Y, int m, bool dot, bool *gram_out)
@@ -775,6 +819,14 @@ extern "C"
         return fail(set_error(ctx, DE_ERR_INVALID, "de_matrix_create_distributed: send row out of range"));
     if ((s = upload_converted(ctx, &A->send_rows, send_rows, (size_t)A->n_send)) != DE_OK)
       return fail(s);
+    for (int p = 0; p < npeers; ++p) // slab partitions send whole planes: consecutive rows (plan_fused_push)
+    {
+      long long first = send_offsets[p + 1] > send_offsets[p] ? send_rows[send_offsets[p]] : -1;
+      for (int64_t k = send_offsets[p]; k < send_offsets[p + 1] && first >= 0; ++k)
+        if (send_rows[k] != first + (k - send_offsets[p]))
+          first = -1;
+      A->send_first.push_back(first);
+    }
     // interior rows touch owned columns only and can run while the halo is in flight
     std::vector<int> in, bd;
     {

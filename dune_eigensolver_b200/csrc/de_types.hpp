@@ -37,6 +37,16 @@ namespace de
     int *ticket;
   };
 
+  /** rows of an updated block that neighbours need as halo rows, when they form (at most two) contiguous ranges: the
+   *  block-update kernel stores those rows into the neighbours' halo buffers while it writes them (kernels_tallskinny2.cuh),
+   *  so the SpMM that follows only has to release the flags. dst[p] = first deposit row in peer p's buffer, row stride M. */
+  struct PushRanges
+  {
+    int n;
+    long long lo[2], hi[2];
+    double *dst[2];
+  };
+
   struct PeerList
   {
     int n;

@@ -25,6 +25,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "de_types.hpp"
 #include "kernels_sparse.cuh"
 
 namespace de
@@ -87,6 +88,7 @@ namespace de
     const int *skip_flag; // optional: if *skip_flag != 0 the kernel returns immediately (second CholQR sweep)
     const int *done;      // optional: a driver loop has converged, the launch is a no-op
     double *partials;     // DO_GRAM: [gridDim.x][M*M]
+    PushRanges push;      // ts2_update_kernel: rows also stored into the neighbours' halo buffers (n = 0: none)
   };
 
   /** see file comment. Template switches:

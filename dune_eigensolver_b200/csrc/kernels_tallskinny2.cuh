@@ -171,6 +171,21 @@ namespace de
             if (row0 + 1 < a.n)
               a.Out[(size_t)(row0 + 1) * a.ldo + 8 * jb + g] = c[jb][1];
           }
+          // halo rows of the neighbours: stored into their windows from the same registers (NVLink peer stores)
+          for (int p = 0; p < a.push.n; ++p)
+          {
+            if (row0 + 1 < a.push.lo[p] || row0 >= a.push.hi[p] || row0 >= a.n)
+              continue;
+            double *d0 = a.push.dst[p] + (size_t)(row0 - a.push.lo[p]) * M + g;
+#pragma unroll
+            for (int jb = 0; jb < C::NB; ++jb)
+            {
+              if (row0 >= a.push.lo[p])
+                d0[8 * jb] = c[jb][0];
+              if (row0 + 1 < a.push.hi[p] && row0 + 1 < a.n)
+                d0[M + 8 * jb] = c[jb][1];
+            }
+          }
           if (DO_GRAM)
           {
             // rows past the end of the block were staged as zeros: they add nothing
