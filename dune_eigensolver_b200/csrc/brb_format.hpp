@@ -25,6 +25,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <thread>
@@ -324,6 +325,8 @@ namespace de
       return true;
     }
 
+    constexpr long long kPlanePointsInL2 = 16384; // grid planes larger than this are swept in y chunks (grid_order)
+
     /** tiles of tw x th x td points cut into row blocks of bw x bh x bd points (bw bh bd == 8) */
     inline void grid_order(long long n, long long S1, long long S2, int tw, int th, int td, int bw, int bh, int bd, Order &o)
     {
@@ -332,8 +335,24 @@ namespace de
       const long long nz = S2 > 0 ? (n + S2 - 1) / S2 : 1;
       o.rows.clear();
       o.tilecut.assign(1, 0);
+      // Large planes: the tiles of one sweep over (x, y) at fixed z0 touch td + 2 planes of X, and the two halo planes are
+      // needed again one sweep later -- after td planes' worth of X rows, Y rows and matrix stream (~3 KB per grid point of
+      // the plane at m = 32) went through the L2. Beyond ~16 k points per plane that exceeds what the L2 keeps (measured:
+      // SpMM at 0.74 of HBM peak on 100^3, 0.70 on 200^3, 0.60 on 256^3), so y is cut into chunks and the sweep over z runs
+      // inside a chunk: the rows between two uses of a halo plane shrink to nx * ychunk * td.
+      long long ychunk = ny;
+      long long limit = kPlanePointsInL2;
+      if (const char *e = std::getenv("DE_B200_BRB_PLANE_POINTS")) // tuning aid (tools/ychunk_probe.py)
+        limit = std::max<long long>(64, std::atoll(e));
+      if (nz > 1 && nx * ny > limit)
+      {
+        const long long want = std::max<long long>(th, limit * 3 / 4 / nx);
+        const long long nchunks = (ny + want - 1) / want;
+        ychunk = ((ny + nchunks - 1) / nchunks + th - 1) / th * th;
+      }
+      for (long long yc = 0; yc < ny; yc += ychunk)
       for (long long z0 = 0; z0 < nz; z0 += td)
-        for (long long y0 = 0; y0 < ny; y0 += th)
+        for (long long y0 = yc; y0 < std::min<long long>(yc + ychunk, ny); y0 += th)
           for (long long x0 = 0; x0 < nx; x0 += tw)
           {
             const long long x1 = std::min<long long>(x0 + tw, nx), y1 = std::min<long long>(y0 + th, ny),

@@ -38,6 +38,9 @@ GRIDS = {
     "q1_3d_21x13x10": (lambda: M.q1_stiffness((21, 13, 10)), 3),
     "q1_hc_12": (lambda: M.q1_stiffness((12, 12, 12), kappa=M.high_contrast_kappa(1e6, 2)), 3),
     "q1_mass_9": (lambda: M.q1_mass((9, 9, 9)), 3),
+    # a plane of more than 16384 points: the tile order sweeps z inside chunks of y (brb::grid_order), ragged last chunk
+    "fd3d_150x131x5": (lambda: M.laplacian_fd((150, 131, 5)), 3),
+    "q1_3d_140x122x6": (lambda: M.q1_stiffness((140, 122, 6)), 3),
 }
 
 
