@@ -193,6 +193,13 @@ namespace dei
       a.push = de::PushRanges{};
       if (ctx->push_pending.n > 0 && a.ldo == M) // orthonormalize_device(..., next_spmm): halo rows go out with the update
         a.push = ctx->push_pending;
+      if (a.push.n > 0)
+      {
+        DE_TRY(ensure_func_smem(ctx, (const void *)de::ts2_update_kernel<M, DO_GRAM, true>, C2::SMEM));
+        ProfScope prof(ctx, DE_PROF_UPDATE);
+        DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::ts2_update_kernel<M, DO_GRAM, true>), dim3(grid2), dim3(C2::THREADS), C2::SMEM, ctx->stream, a));
+      }
+      else
       {
         ProfScope prof(ctx, DE_PROF_UPDATE);
         DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::ts2_update_kernel<M, DO_GRAM>), dim3(grid2), dim3(C2::THREADS), C2::SMEM, ctx->stream, a));
@@ -397,6 +404,13 @@ namespace dei
   int update_device(de_context *ctx, int mode, int w, long long n, const double *X, int ldx, const double *R, double *Y,
                     int ldy, int upper, const int *skip_flag)
   {
+    if (mode == 1 && ts_supported(w) && ldx == w && ldy == w && skip_flag == nullptr && ctx->use_lincomb2)
+    {
+      // projection Y -= X R (kernels_cpp.hh:335-348) on the tensor-core kernel: Y = Y + (-1) * X R
+      const double *S[2] = {Y, X};
+      const double *Cm[2] = {nullptr, R};
+      return lincomb2_device(ctx, w, n, 2, S, Cm, Y, nullptr, true, -1.0);
+    }
     return mode == 0 ? update_device_t<0>(ctx, w, n, X, ldx, R, Y, ldy, upper, skip_flag)
                      : update_device_t<1>(ctx, w, n, X, ldx, R, Y, ldy, upper, skip_flag);
   }

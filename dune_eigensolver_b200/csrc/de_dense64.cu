@@ -3,6 +3,7 @@
 #include "de_internal.hpp"
 #include "kernels_sparse.cuh"
 #include "kernels_gram2.cuh"
+#include "kernels_lincomb2.cuh"
 
 using namespace dei;
 
@@ -23,6 +24,55 @@ namespace dei
     }
     DE_LAUNCH_CHECK(ctx);
     return reduce_partials(ctx, a.partials, grid, M * M, out);
+  }
+
+  template <int M>
+  static int launch_lincomb2_t(de_context *ctx, const de::Lc2Args &a)
+  {
+    using C = de::Lc2Cfg<M>;
+    DE_TRY(ensure_func_smem(ctx, (const void *)de::ts2_lincomb_kernel<M>, C::SMEM));
+    const long long nt = (a.n + C::TR - 1) / C::TR;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(nt, (long long)ctx->sm_count));
+    {
+      ProfScope prof(ctx, DE_PROF_UPDATE);
+      DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::ts2_lincomb_kernel<M>), dim3(grid), dim3(C::THREADS), C::SMEM, ctx->stream, a));
+    }
+    DE_LAUNCH_CHECK(ctx);
+    return DE_OK;
+  }
+
+  /** out = sum_s S_s C_s, out2 = sum_{s >= 1} S_s C_s (identity0: out = S_0 + alpha * sum_{s >= 1} S_s C_s) on the tensor-core
+   *  kernel of kernels_lincomb2.cuh; widths 8 / 16 / 32 / 64, blocks with leading dimension w */
+  int lincomb2_device(de_context *ctx, int w, long long n, int ns, const double *const *S, const double *const *Cm, double *out,
+                      double *out2, bool identity0, double alpha)
+  {
+    if (ns < 1 || ns > de::kLc2MaxSrc)
+      return set_error(ctx, DE_ERR_INVALID, "lincomb: 1 to 3 sources");
+    de::Lc2Args a{};
+    a.n = n;
+    a.ns = ns;
+    for (int s = 0; s < ns; ++s)
+    {
+      a.S[s] = S[s];
+      a.C[s] = Cm[s];
+    }
+    a.out = out;
+    a.out2 = ns > 1 ? out2 : nullptr;
+    a.identity0 = identity0 ? 1 : 0;
+    a.alpha = alpha;
+    a.done = ctx->done_ptr;
+    switch (w)
+    {
+    case 8:
+      return launch_lincomb2_t<8>(ctx, a);
+    case 16:
+      return launch_lincomb2_t<16>(ctx, a);
+    case 32:
+      return launch_lincomb2_t<32>(ctx, a);
+    case 64:
+      return launch_lincomb2_t<64>(ctx, a);
+    }
+    return set_error(ctx, DE_ERR_UNSUPPORTED, "tensor-core lincomb kernel: unsupported width");
   }
 
   bool gram2_supported(int w) { return w == 64; }

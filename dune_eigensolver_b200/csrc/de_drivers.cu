@@ -35,6 +35,11 @@ namespace dei
   int lincomb_device(de_context *ctx, int m, long long n, int ns, const double *const *S, const double *C, double *out,
                      double *out2)
   {
+    if (ts_supported(m) && ctx->use_lincomb2)
+    {
+      const double *Cm[3] = {C, C + (size_t)m * m, C + (size_t)2 * m * m};
+      return lincomb2_device(ctx, m, n, ns, S, Cm, out, out2, false, 1.0);
+    }
     switch (m)
     {
     case 8:

@@ -84,6 +84,7 @@ struct de_context
   // NVLink peer window (kernels_peer.cuh); peer_ready once every rank's window is mapped
   bool peer_ready = false;
   bool pdl = true;      // programmatic dependent launch of the loop kernels (off when ranks share a device)
+  bool use_lincomb2 = true;   // LOBPCG combination / projection on the tensor-core kernel (kernels_lincomb2.cuh); DE_B200_LINCOMB2=0: first version
   bool use_loop_graph = true; // StandardLargest: replay the steady-state iterations from a CUDA graph (one GPU)
   long long peer_timeout_cycles = 60000000000LL; // spins on peer flags give up after this many clocks (~30 s)
   bool peer_ipc = true; // peer windows were opened from CUDA IPC handles (else: same-process allocations, de_multi.cu)
@@ -447,6 +448,8 @@ namespace dei
   int gram_device(de_context *ctx, int w, long long n, const double *X, int ldx, const double *Y, int ldy, bool symmetric,
                   double *out);
   /** de_dense64.cu: G = X^T Y on the warp-specialised tensor-core kernel (widths where it beats the first-generation one) */
+  int lincomb2_device(de_context *ctx, int w, long long n, int ns, const double *const *S, const double *const *Cm, double *out,
+                      double *out2, bool identity0, double alpha);
   bool gram2_supported(int w);
   int gram2_device(de_context *ctx, int w, long long n, const double *X, int ldx, const double *Y, int ldy, double *out);
   /** mode 0: Y = X R ; mode 1: Y -= X R (projection) */

@@ -519,6 +519,8 @@ extern "C"
     ctx->device = device;
     if (const char *g = std::getenv("DE_B200_FUSED_PUSH")) // "0": halo rows always pushed by halo_push_kernel (A/B measurements)
       ctx->fused_push = g[0] != '0';
+    if (const char *g = std::getenv("DE_B200_LINCOMB2")) // "0": first-generation FMA kernels (A/B measurements)
+      ctx->use_lincomb2 = g[0] != '0';
     if (const char *g = std::getenv("DE_B200_LOOP_GRAPH")) // "0": plain launches in the StandardLargest loop (A/B measurements)
       ctx->use_loop_graph = g[0] != '0';
     auto bail = [&](int code) {

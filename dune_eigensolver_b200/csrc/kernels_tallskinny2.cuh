@@ -57,7 +57,7 @@ namespace de
    *  DO_GRAM: per-CTA partial of Out^T Out at a.partials[cta * M * M + i * M + j] (full symmetric matrix).
    *  M = 64: the 128 factor fragments do not fit the register file next to the accumulators; the factor is staged in
    *  shared memory (row stride M + 4: the fragment load of a half warp is conflict-free) and DO_GRAM is not offered. */
-  template <int M, bool DO_GRAM>
+  template <int M, bool DO_GRAM, bool PUSH = false>
   __global__ void __launch_bounds__(Ts2Cfg<M>::THREADS, 1) ts2_update_kernel(const TsArgs a)
   {
     using C = Ts2Cfg<M>;
@@ -172,7 +172,8 @@ namespace de
               a.Out[(size_t)(row0 + 1) * a.ldo + 8 * jb + g] = c[jb][1];
           }
           // halo rows of the neighbours: stored into their windows from the same registers (NVLink peer stores)
-          for (int p = 0; p < a.push.n; ++p)
+          // (a template switch: with the test in the loop the single-GPU kernel was 18 % slower, 101 -> 120 us at m = 32)
+          for (int p = 0; PUSH && p < a.push.n; ++p)
           {
             if (row0 + 1 < a.push.lo[p] || row0 >= a.push.hi[p] || row0 >= a.n)
               continue;
