@@ -470,6 +470,7 @@ namespace dei
         ctx->prepushed_A = next_spmm;
         ctx->prepushed_epoch = ctx->halo_epoch + 1;
         ctx->prepushed_m = m;
+        ctx->prepushed_released = false;
       }
       // sweep 1: G = X^T X (already known if the SpMM that produced X ran its Gram epilogue) ; R1 = chol(G) ;
       // X <- X R1^-1 fused with G2 = X^T X of the result
@@ -494,6 +495,11 @@ namespace dei
       DE_TRY((launch_ts<true, true, true, true>(ctx, m, a, ctx->dG())));
       DE_TRY(allreduce_sum(ctx, ctx->dG(), (size_t)m * m));
       DE_TRY(chol_inverse(ctx, m, ctx->dG(), ctx->dR(), nullptr, ctx->dflags));
+      if (ctx->push_pending.n > 0)
+      {
+        ctx->push_pending.release = 1; // the last launch that can change X: it also raises the halo flags
+        ctx->prepushed_released = true;
+      }
       return update_device(ctx, 0, m, n, X, m, ctx->dR(), X, m, 1, ctx->dflags);
     }
     for (int sweep = 0; sweep < 2; ++sweep)

@@ -96,11 +96,15 @@ struct de_context
   // what the next ts2_update launches add to their arguments; prepushed_* say which SpMM call finds its halo rows already
   // in the neighbours' windows (that call only releases the flags)
   de::PushRanges push_pending{};
-  bool fused_push = true;
+  // OFF by default -- measured on B200 (profiles/README.md, round 2): the 64-byte row segments a warp of the update kernel
+  // stores from its registers cross NVLink far less efficiently than halo_push_kernel's coalesced 16-byte-per-thread rows:
+  // 100^3 on 2 GPUs 13.17 -> 13.04 ms (-1 %), 256^3 on 2 GPUs 0.1065 -> 0.111 s (+4 %). DE_B200_FUSED_PUSH=1 enables it.
+  bool fused_push = false;
   const double *prepushed_X = nullptr;
   const de_matrix *prepushed_A = nullptr;
   unsigned long long prepushed_epoch = 0;
   int prepushed_m = 0;
+  bool prepushed_released = false; // ... and the flags were raised by the last update launch (PushRanges::release)
   int *dticket = nullptr; // [0] ticket of halo_push_kernel, [1] peer error flag
   // fused tail of the NEXT partial-sum reduction (kernels_tail.cuh): set by the caller, consumed by reduce_partials
   de::TailArgs tail{};

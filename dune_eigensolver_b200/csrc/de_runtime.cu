@@ -517,7 +517,7 @@ extern "C"
     if (!ctx)
       return set_error(nullptr, DE_ERR_ALLOC, "de_context_create: out of host memory");
     ctx->device = device;
-    if (const char *g = std::getenv("DE_B200_FUSED_PUSH")) // "0": halo rows always pushed by halo_push_kernel (A/B measurements)
+    if (const char *g = std::getenv("DE_B200_FUSED_PUSH")) // "1": halo rows leave with the block updates (A/B measurements; see de_internal.hpp)
       ctx->fused_push = g[0] != '0';
     if (const char *g = std::getenv("DE_B200_LINCOMB2")) // "0": first-generation FMA kernels (A/B measurements)
       ctx->use_lincomb2 = g[0] != '0';

@@ -533,9 +533,12 @@ namespace dei
               h.send_off[p] = 0; // nothing to copy: the launch only releases the flags
           const long long total = prepushed ? 0 : A->n_send * (m / 2);
           const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, ctx->sm_count * 4));
-          ProfScope prof(ctx, DE_PROF_HALO_PUSH);
-          DE_REG(de::halo_push_kernel), de::halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(pa, h);
-          DE_LAUNCH_CHECK(ctx);
+          if (!(prepushed && ctx->prepushed_released)) // else: the last update launch has raised the flags already
+          {
+            ProfScope prof(ctx, DE_PROF_HALO_PUSH);
+            DE_REG(de::halo_push_kernel), de::halo_push_kernel<<<grid, 256, 0, ctx->stream>>>(pa, h);
+            DE_LAUNCH_CHECK(ctx);
+          }
         }
       }
       else
@@ -663,8 +666,20 @@ namespace dei
         r.hi[r.n] = A->send_first[p] + A->send_count[p];
         r.dst[r.n] = reinterpret_cast<double *>(ctx->peer_base[A->peer[p]] + de::kPeerHaloOff + (size_t)(epoch & 1ull) * ctx->halo_cap) +
                      (size_t)A->deposit[p] * m;
+        // = peer_halo_flag(base of the peer, parity, this rank), kernels_peer.cuh
+        r.flag[r.n] = reinterpret_cast<unsigned long long *>(ctx->peer_base[A->peer[p]]) + 2 * de::kPeerMaxRanks +
+                      (int)(epoch & 1ull) * de::kPeerMaxRanks + ctx->rank;
         ++r.n;
       }
+    r.release = 0;
+    r.first_row = 0;
+    for (int q = 0; q < r.n; ++q)
+      if (r.lo[q] > r.first_row && r.hi[q] >= A->n - 8) // a range at the end of the slab: the sweep starts there
+        r.first_row = r.lo[q];
+    r.epoch = epoch;
+    r.ticket = ctx->dticket;
+    // the flags of ALL send peers must be raised by whoever releases: with a peer that receives no rows from this rank
+    // (send_count 0) but is listed, halo_push_kernel raises its flag too -- nobody waits for it, so it can be left out
     return r.n > 0;
   }
 

@@ -65,10 +65,19 @@ namespace de
     constexpr int NPW = kTs2ProducerWarps, NCW = C::NCW;
     extern __shared__ __align__(128) unsigned char dyn2[];
     pdl_prologue();
-    if (a.skip_flag != nullptr && *a.skip_flag != 0)
-      return;
     if (a.done != nullptr && *a.done != 0)
       return;
+    if (a.skip_flag != nullptr && *a.skip_flag != 0)
+    {
+      // nothing changes: the rows the previous update launch stored into the neighbours' windows are final (its stores
+      // are complete: the launch has ended), so the flags can go up at once
+      if (PUSH && a.push.release && blockIdx.x == 0 && (int)threadIdx.x < a.push.n)
+      {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(a.push.flag[threadIdx.x]), "l"(a.push.epoch) : "memory");
+      }
+      return;
+    }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned bar0 = smem_u32(dyn2); // full[s] at +8 s, empty[s] at +8 (kTs2Stages + s)
     double *Rs = reinterpret_cast<double *>(dyn2 + 128);                  // RSMEM: M x LDT
@@ -88,6 +97,7 @@ namespace de
     __syncthreads();
 
     const long long ntiles = (a.n + C::TR - 1) / C::TR;
+    const long long trot = PUSH ? a.push.first_row / C::TR : 0; // sweep starts here (PushRanges::first_row)
     double gacc[DO_GRAM ? C::NT : 1][2];
 #pragma unroll
     for (int i = 0; i < (DO_GRAM ? C::NT : 1); ++i)
@@ -99,8 +109,9 @@ namespace de
       constexpr int CPR = M / 2;
       const int ptid = warp * 32 + lane;
       int s = 0, use = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
+      for (long long tq = blockIdx.x; tq < ntiles; tq += gridDim.x)
       {
+        const long long t = (PUSH && tq + trot >= ntiles) ? tq + trot - ntiles : tq + trot;
         if (use > 0)
           mbar_wait(bar0 + 8 * (kTs2Stages + s), (unsigned)((use - 1) & 1));
         double *dst = tiles + (size_t)s * C::TR * C::LDT;
@@ -139,8 +150,9 @@ namespace de
       const double *rs = Rs + k * C::LDT + g; // RSMEM: fragment (ks, jb) = rs[4 ks LDT + 8 jb]
 
       int s = 0, use = 0;
-      for (long long t = blockIdx.x; t < ntiles; t += gridDim.x)
+      for (long long tq = blockIdx.x; tq < ntiles; tq += gridDim.x)
       {
+        const long long t = (PUSH && tq + trot >= ntiles) ? tq + trot - ntiles : tq + trot;
         mbar_wait(bar0 + 8 * s, (unsigned)(use & 1));
         const double *Xs = tiles + (size_t)s * C::TR * C::LDT;
         const long long r0 = t * C::TR;
@@ -225,6 +237,24 @@ namespace de
       }
     }
 
+    if (PUSH && a.push.release)
+    {
+      // the CTA that finishes last releases the halo flags: every CTA's peer stores are fenced before its ticket
+      __threadfence_system();
+      __syncthreads();
+      __shared__ int last_cta;
+      if (tid == 0)
+        last_cta = (atomicAdd(a.push.ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+      __syncthreads();
+      if (last_cta)
+      {
+        __threadfence_system();
+        if (tid < a.push.n)
+          asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(a.push.flag[tid]), "l"(a.push.epoch) : "memory");
+        if (tid == 0)
+          *a.push.ticket = 0;
+      }
+    }
     if (DO_GRAM)
     {
       // fold the consumer warps in fixed order into one M x M matrix, mirror the strict lower block triangle

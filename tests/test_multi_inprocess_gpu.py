@@ -45,6 +45,22 @@ def test_partitioned_standard_largest_matches_the_reference(oracle, ranks, shape
     assert (res <= 2.0 * res_ref + 1e-8).all()
 
 
+def test_halo_rows_stored_by_the_update_kernel(oracle, monkeypatch):
+    """DE_B200_FUSED_PUSH=1 (off by default, see de_internal.hpp): the block-update kernels of the orthonormalisation store
+    the halo rows of the next SpMM into the neighbours' windows and the last of them raises the flags -- same result"""
+    monkeypatch.setenv("DE_B200_FUSED_PUSH", "1")
+    shape = (7, 6, 9)
+    A = M.q1_stiffness(shape)
+    mg = E.Multi(_devices(3), timeout_s=5)
+    try:
+        r = mg.StandardLargest((A[0], A[1], A[2].copy()), 0.0, 1e-9, 3000, 32, row_align=shape[0] * shape[1])
+    finally:
+        mg.close()
+    evr, _, k = oracle.standard_largest((A[0], A[1], A[2].copy()), 0.0, 1e-9, 3000, 32)
+    assert abs(r.iterations - k) <= 1
+    assert np.abs(r.eval - evr).max() <= 1e-8 * np.abs(evr).max()
+
+
 def test_unaligned_partition_and_shift(oracle):
     """cuts inside grid planes (row_align = 1): halo lists are no longer whole planes; shift != 0 (eigensolver.hh:57-66)"""
     A = M.q1_stiffness((5, 6, 7))
