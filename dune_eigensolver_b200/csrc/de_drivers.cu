@@ -297,7 +297,7 @@ extern "C"
         c->pending_dot.valid = false;
       }
     } guard{ctx};
-    const size_t need = 64 + (size_t)std::max(maxiter, 2) + 1;
+    const size_t need = 64 + (size_t)std::min(std::max(maxiter, 2), de::kConvHistory) + 1; // s_prev | capped history
     if (ctx->dconv_cap < need)
     {
       dev_free(ctx->dconv);
@@ -454,9 +454,10 @@ extern "C"
                   std::chrono::duration<double>(std::chrono::steady_clock::now() - t_enq0).count() * 1e3 - t_enq * 1e3);
     if (verbose > 0 && k_exit > 1)
     {
-      std::vector<double> h((size_t)k_exit + 1);
+      const int k_listed = std::min(k_exit, de::kConvHistory - 1);
+      std::vector<double> h((size_t)k_listed + 1);
       DE_CUDA(ctx, cudaMemcpy(h.data(), hist, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
-      for (int k = 2; k <= k_exit; ++k)
+      for (int k = 2; k <= k_listed; ++k)
         std::printf("Iter=%d %g\n", k, h[k]);
     }
     if (k_exit_out)

@@ -496,6 +496,8 @@ namespace de
    *  s_j = dp_j - shift, distance = max_j |s_j - s_prev_j|, s_prev <- s; iteration k > 1 with distance < tol raises
    *  the `done` flag, after which every kernel of the iterations already enqueued returns at once.
    *  state: flags[1] = done, flags[2] = last completed iteration; hist[k] = distance of iteration k. One CTA of 64. */
+  constexpr int kConvHistory = 1 << 20; // distances of the first 2^20 iterations are kept for the verbose listing
+
   __device__ __forceinline__ void convergence_body(int tid, int nthreads, int k, int m, double shift, double tol,
                                                    const double *__restrict__ dp, double *__restrict__ s_prev,
                                                    double *__restrict__ hist, int *__restrict__ flags)
@@ -523,7 +525,8 @@ namespace de
         k = flags[3] + 1;
         flags[3] = k;
       }
-      hist[k] = mx;
+      if (k < kConvHistory) // a "run until converged" maxiter of 1e9 must not size a buffer (de_drivers.cu)
+        hist[k] = mx;
       flags[2] = k;
       if (k > 1 && mx < tol)
         flags[1] = 1;

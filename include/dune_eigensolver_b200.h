@@ -195,7 +195,9 @@ int de_mv_download_panel8(const de_mv *X, double *host_panel8);
 int de_mv_upload_rowmajor(de_mv *X, const double *host_rowmajor);
 int de_mv_download_rowmajor(const de_mv *X, double *host_rowmajor);
 int de_mv_copy(de_mv *dst, const de_mv *src);
-/* raw device pointer (row-major, leading dimension m) for zero-copy interop */
+/* raw device pointer (row-major, leading dimension m) for zero-copy interop. The pointer is INVALIDATED by
+ * de_standard_largest_mv / de_standard_inverse_mv on the same block: those drivers alternate between the block's buffer
+ * and a work buffer and leave the result in whichever holds it (no copy of n x m doubles); ask again afterwards. */
 int de_mv_device_ptr(de_mv *X, void **dptr);
 
 /* ---- kernels --------------------------------------------------------------------------------------*/

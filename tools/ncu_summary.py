@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Condense an .ncu-rep (read here, no GPU needed) into a small per-launch CSV for profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_ncu_kernels.csv
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_ncu_kernels.csv [100_q1_32 "spmm_brb_kernel<4, 1"]
 """
 import csv
 import io
@@ -27,6 +27,34 @@ KEEP = [
 ]
 
 
+def traffic(rows, idx, units, key, pattern, source):
+    """profiles/ncu_traffic.json[key] = mean DRAM read + write bytes per launch of the kernels matching `pattern` (bench.py's
+    roofline.traffic reads it), with the commit the capture was taken at"""
+    import json
+    import os
+    import re
+
+    def to_bytes(v, u):
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+        return float(v.replace(",", "")) * scale
+
+    tot, cnt = 0.0, 0
+    for r in rows[2:]:
+        if re.search(pattern, r[idx["Kernel Name"]]):
+            tot += to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + \
+                   to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+            cnt += 1
+    if cnt == 0:
+        raise SystemExit("no launch matches " + pattern)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "profiles", "ncu_traffic.json")
+    d = json.load(open(path)) if os.path.exists(path) else {}
+    commit = subprocess.run(["git", "-C", root, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    d[key] = {"dram_bytes_per_launch": tot / cnt, "launches": cnt, "kernel": pattern, "source": source, "commit": commit}
+    json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+    print("wrote", path, d[key])
+
+
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
@@ -39,6 +67,8 @@ def main():
         for r in rows[2:]:
             w.writerow([r[idx["Kernel Name"]]] + [r[idx[name]] for name, _ in KEEP if name in idx])
     print("wrote", out)
+    if len(sys.argv) >= 5:  # ... <traffic key, e.g. 100_q1_32> <kernel regex>
+        traffic(rows, idx, units, sys.argv[3], sys.argv[4], out)
 
 
 if __name__ == "__main__":
