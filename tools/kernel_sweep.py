@@ -16,6 +16,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+FP64_TENSOR_TFLOPS = 37.0  # measured DMMA rate of one B200 (tools/micro/fp64_peak.cu)
+
+
+def tensor_flops(kernel, n, m):
+    """flops the kernel issues on the FP64 tensor pipe (what bounds the wide-block kernels): Gram X^T X computes the 8 x 8 tiles
+    on or above the diagonal only, a triangular factor skips the zero half; None for the streaming / sparse kernels"""
+    nb = m // 8
+    full = 2.0 * n * m * m
+    tri = full * (nb * (nb + 1) / 2) / (nb * nb)
+    # (the "update" row calls de_block_update with a general factor: full product; the orthonormalisation's updates are triangular)
+    return {"gram_xx": tri, "gram_xy": full, "update": full, "ortho": 4.0 * tri, "lincomb3": 3.0 * full}.get(kernel)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=200)
@@ -91,9 +104,11 @@ def main():
         Z.close()
     if args.csv:
         with open(args.csv, "w") as f:
-            f.write("grid,stencil,n,nnz,m,kernel,avg_ms,GBps,frac_of_measured_hbm_peak\n")
+            f.write("grid,stencil,n,nnz,m,kernel,avg_ms,GBps,frac_of_measured_hbm_peak,frac_of_fp64_tensor_peak\n")
             for r in rows:
-                f.write("%d,%s,%d,%d,%d,%s,%.5f,%.1f,%.4f\n" % (args.grid, args.stencil, n, nnz, *r))
+                fl = tensor_flops(r[1], n, r[0])
+                ft = "%.4f" % (fl / (r[2] * 1e-3) / 1e12 / FP64_TENSOR_TFLOPS) if fl else ""
+                f.write("%d,%s,%d,%d,%d,%s,%.5f,%.1f,%.4f,%s\n" % (args.grid, args.stencil, n, nnz, *r, ft))
 
 
 if __name__ == "__main__":
