@@ -211,7 +211,7 @@ def test_lu_provider_rejects_what_static_pivoting_cannot_factor():
     from dune_eigensolver_b200 import eigensolver as E
 
     n = 40
-    blocks = [np.array([[1e-14, 1.0], [1.0, 1e-14]])] * (n // 2)
+    blocks = [sp.coo_array(np.array([[1e-14, 1.0], [1.0, 1e-14]]))] * (n // 2)
     S = sp.block_diag(blocks, format="csr") + 1e-3 * sp.diags([np.ones(n - 1), np.ones(n - 1)], [-1, 1], format="csr")
     S = S.tocsr()
     S.sort_indices()
