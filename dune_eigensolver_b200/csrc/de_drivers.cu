@@ -161,6 +161,17 @@ namespace dei
       DE_LAUNCH_CHECK(ctx);
       return DE_OK;
     }
+    /** one Chebyshev step: AZ = A Z ; Zold <- Z + alpha (Z - Zold) + beta D^-1 (R - AZ) -- as the epilogue of the SpMM kernel
+     *  where the matrix has its tensor-core form (AZ is then not touched), else as two passes */
+    int apply_A_cheb(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta)
+    {
+      bool fused = false;
+      DE_TRY(spmm_cheb_device(ctx, A, Z, Zold, R, ddinv, alpha, beta, m, &fused));
+      if (fused)
+        return DE_OK;
+      DE_TRY(apply_A(AZ, Z));
+      return cheb_step(Zold, Z, R, AZ, alpha, beta);
+    }
     int project(Blk W, Blk X, Blk BX)
     {
       DE_TRY(gram_device(ctx, m, n, BX, m, W, m, false, ctx->dG()));

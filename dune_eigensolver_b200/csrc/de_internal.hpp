@@ -84,6 +84,15 @@ struct de_context
   // NVLink peer window (kernels_peer.cuh); peer_ready once every rank's window is mapped
   bool peer_ready = false;
   bool pdl = true;      // programmatic dependent launch of the loop kernels (off when ranks share a device)
+  // Chebyshev epilogue of the next BRB SpMM launch (spmm_cheb_device, de_spmm.cu)
+  struct SpmmEpilogue
+  {
+    bool valid = false;
+    double *zold = nullptr;
+    const double *r = nullptr, *dinv = nullptr;
+    double alpha = 0.0, beta = 0.0;
+  } epi;
+  bool use_cheb_epilogue = true; // DE_B200_CHEB_EPILOGUE=0: SpMM + cheb_step_kernel as two passes (A/B measurements)
   bool use_lincomb2 = true;   // LOBPCG combination / projection on the tensor-core kernel (kernels_lincomb2.cuh); DE_B200_LINCOMB2=0: first version
   bool use_loop_graph = true; // StandardLargest: replay the steady-state iterations from a CUDA graph (one GPU)
   long long peer_timeout_cycles = 60000000000LL; // spins on peer flags give up after this many clocks (~30 s)
@@ -471,6 +480,8 @@ namespace dei
   // ---- de_spmm.cu ---------------------------------------------------------------------------------------------
   /** Y = A X; dot: also dp = diag(X^T Y) into ctx->dDP(); gram_out (dot only): may receive G = Y^T Y, see spmm_device */
   int spmm_device(de_context *ctx, const de_matrix *A, const double *X, double *Y, int m, bool dot, bool *gram_out = nullptr);
+  int spmm_cheb_device(de_context *ctx, const de_matrix *A, const double *Z, double *Zold, const double *R, const double *dinv,
+                       double alpha, double beta, int m, bool *fused);
 
   // ---- de_snode.cu --------------------------------------------------------------------------------------------
   int sn_apply_device(de_context *ctx, de_factor *F, const double *X, double *Y, int m);

@@ -519,6 +519,8 @@ extern "C"
     ctx->device = device;
     if (const char *g = std::getenv("DE_B200_FUSED_PUSH")) // "1": halo rows leave with the block updates (A/B measurements; see de_internal.hpp)
       ctx->fused_push = g[0] != '0';
+    if (const char *g = std::getenv("DE_B200_CHEB_EPILOGUE")) // "0": SpMM and Chebyshev update as two passes (A/B measurements)
+      ctx->use_cheb_epilogue = g[0] != '0';
     if (const char *g = std::getenv("DE_B200_LINCOMB2")) // "0": first-generation FMA kernels (A/B measurements)
       ctx->use_lincomb2 = g[0] != '0';
     if (const char *g = std::getenv("DE_B200_LOOP_GRAPH")) // "0": plain launches in the StandardLargest loop (A/B measurements)

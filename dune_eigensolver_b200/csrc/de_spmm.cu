@@ -367,12 +367,12 @@ namespace dei
 
   constexpr int kBrbMaxSmem = 227 * 1024;
 
-  template <int NP, bool DOT, bool HALO, bool GRAM>
+  template <int NP, bool DOT, bool HALO, bool GRAM, int EPI = 0>
   int launch_brb_pass(de_context *ctx, const de::BrbArgs &a, int grid)
   {
-    DE_TRY(ensure_func_smem(ctx, (const void *)de::spmm_brb_kernel<NP, DOT, HALO, GRAM>, kBrbMaxSmem));
+    DE_TRY(ensure_func_smem(ctx, (const void *)de::spmm_brb_kernel<NP, DOT, HALO, GRAM, EPI>, kBrbMaxSmem));
     const size_t smem = de::spmm_brb_smem_bytes(NP, a.blob_cap16, a.xs_cap, a.stages);
-    DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::spmm_brb_kernel<NP, DOT, HALO, GRAM>), dim3(grid), dim3(de::brb_threads(GRAM)), smem, ctx->stream, a));
+    DE_CUDA(ctx, launch_pdl(ctx->pdl, DE_KERNEL(de::spmm_brb_kernel<NP, DOT, HALO, GRAM, EPI>), dim3(grid), dim3(de::brb_threads(GRAM)), smem, ctx->stream, a));
     DE_LAUNCH_CHECK(ctx);
     return DE_OK;
   }
@@ -422,6 +422,23 @@ namespace dei
       a.blob_cap16 = B.max_len16;
       a.xs_cap = B.max_u;
       a.done = ctx->done_ptr;
+      a.E0 = nullptr;
+      a.E1 = nullptr;
+      a.edinv = nullptr;
+      a.ealpha = a.ebeta = 0.0;
+      bool epi = false;
+      if constexpr (!DOT && !GRAM)
+      {
+        if (ctx->epi.valid) // spmm_cheb_device: the launch updates the Chebyshev iterate instead of storing Y
+        {
+          epi = true;
+          a.E0 = ctx->epi.zold + c0;
+          a.E1 = ctx->epi.r + c0;
+          a.edinv = ctx->epi.dinv;
+          a.ealpha = ctx->epi.alpha;
+          a.ebeta = ctx->epi.beta;
+        }
+      }
       int stages = de::kBrbMaxStages;
       while (stages > 2 && de::spmm_brb_smem_bytes(np, a.blob_cap16, a.xs_cap, stages) > (size_t)kBrbMaxSmem)
         --stages;
@@ -430,7 +447,16 @@ namespace dei
         return set_error(ctx, DE_ERR_UNSUPPORTED, "BRB tile does not fit in shared memory");
 #define DE_BRB(NPV)                                                             \
   {                                                                             \
-    if (halo)                                                                   \
+    if constexpr (!DOT && !GRAM)                                                \
+    {                                                                           \
+      if (epi && halo)                                                          \
+        DE_TRY((launch_brb_pass<NPV, false, true, false, 1>(ctx, a, grid)));    \
+      else if (epi)                                                             \
+        DE_TRY((launch_brb_pass<NPV, false, false, false, 1>(ctx, a, grid)));   \
+    }                                                                           \
+    if (epi)                                                                    \
+      ;                                                                         \
+    else if (halo)                                                              \
       DE_TRY((launch_brb_pass<NPV, DOT, true, GRAM>(ctx, a, grid)));            \
     else                                                                        \
       DE_TRY((launch_brb_pass<NPV, DOT, false, GRAM>(ctx, a, grid)));           \
@@ -681,6 +707,27 @@ namespace dei
     // the flags of ALL send peers must be raised by whoever releases: with a peer that receives no rows from this rank
     // (send_count 0) but is listed, halo_push_kernel raises its flag too -- nobody waits for it, so it can be left out
     return r.n > 0;
+  }
+
+  /** Zold <- Z + alpha (Z - Zold) + beta D^-1 (R - A Z) in ONE pass when A has its tensor-core (BRB) form for this width:
+   *  the Chebyshev update is the epilogue of the SpMM kernel (BrbArgs::E0 ...). *fused says whether that happened; if not the
+   *  caller runs the SpMM into a scratch block and cheb_step_kernel. */
+  int spmm_cheb_device(de_context *ctx, const de_matrix *A, const double *Z, double *Zold, const double *R, const double *dinv,
+                       double alpha, double beta, int m, bool *fused)
+  {
+    *fused = false;
+    if (!ctx->use_cheb_epilogue || !brb_usable(A, m))
+      return DE_OK;
+    ctx->epi.valid = true;
+    ctx->epi.zold = Zold;
+    ctx->epi.r = R;
+    ctx->epi.dinv = dinv;
+    ctx->epi.alpha = alpha;
+    ctx->epi.beta = beta;
+    const int rc = spmm_device_t<false>(ctx, A, Z, Zold /* never written as Y */, m, nullptr);
+    ctx->epi.valid = false;
+    *fused = rc == DE_OK;
+    return rc;
   }
 
   int spmm_device(de_context *ctx, const de_matrix *A, const double *X, double *Y, int m, bool dot, bool *gram_out)

@@ -180,6 +180,13 @@ namespace de
     int xs_cap;               // ... and staged X rows
     int stages;               // pipeline depth (2..kBrbMaxStages)
     const int *done;          // optional device flag: a driver loop has converged, the launch is a no-op
+    // EPI = 1 (Chebyshev epilogue, LOBPCG's polynomial preconditioner): instead of storing Y = A X the kernel updates
+    //   E0(i,:) <- X(i,:) + ealpha (X(i,:) - E0(i,:)) + ebeta edinv[i] (E1(i,:) - Y(i,:))
+    // (cheb_step_kernel, kernels_lobpcg.cuh, with Z = X, Zold = E0, R = E1): A z never travels to HBM and back.
+    double *E0;
+    const double *E1;
+    const double *edinv;
+    double ealpha, ebeta;
   };
 
   /** bytes of dynamic shared memory for a pass of 8 NP columns */
@@ -198,10 +205,11 @@ namespace de
    *    B fragment   b[p]   = X(step column k, NP g + p), p < NP                   (NP/2 128-bit shared loads)
    *    accumulators c[p]   = Y(row g, 2 k NP + p), Y(row g, (2 k + 1) NP + p)     -> the lane owns 2 NP contiguous columns
    *  i.e. panel p of the tensor product covers the X columns {NP j + p : j < 8}. */
-  template <int NP, bool DOT, bool HALO, bool GRAM>
+  template <int NP, bool DOT, bool HALO, bool GRAM, int EPI = 0>
   __global__ void __launch_bounds__(brb_threads(GRAM), 1) spmm_brb_kernel(const BrbArgs a)
   {
     static_assert(!GRAM || DOT, "the Gram epilogue is only built together with the dot epilogue");
+    static_assert(EPI == 0 || (!DOT && !GRAM), "the Chebyshev epilogue replaces the plain store");
     constexpr int NPW = kBrbProducerWarps, NCW = GRAM ? kBrbConsumerWarpsGram : kBrbConsumerWarps;
     constexpr int NT = NP * (NP + 1) / 2; // Gram tiles (p <= p') of the column groups {NP j + p}
     constexpr int M = 8 * NP;
@@ -336,6 +344,16 @@ namespace de
 #pragma unroll
           for (int p = 0; p < NP; ++p)
             c[p][0] = c[p][1] = 0.0;
+          if (EPI == 1)
+          {
+            // the epilogue's operands of this lane's row: on their way while the steps run (no registers held)
+            const long long prow = (long long)blkrows[8 * blk + g];
+            if (prow >= 0 && prow < a.n)
+            {
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(a.E0 + (size_t)prow * a.ldx + 2 * k * NP));
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(a.E1 + (size_t)prow * a.ldx + 2 * k * NP));
+            }
+          }
 #pragma unroll 4
           for (int st = s0; st < s1; ++st)
           {
@@ -368,9 +386,50 @@ namespace de
                 lo[p] = c[p][0];
                 hi[p] = c[p][1];
               }
-              double *yr = a.Y + (size_t)row * a.ldx + 2 * k * NP;
-              stg_row<NP>(yr, lo);
-              stg_row<NP>(yr + NP, hi);
+              if (EPI == 1)
+              {
+                // z = X(row, :) from the staged tile (the row's own column is among the tile's columns for any matrix with a
+                // stored diagonal), else from global memory; zo, r from global memory (prefetched at the top of the block)
+                double zl[NP], zh[NP], ol[NP], oh[NP], rl[NP], rh[NP];
+                const unsigned self = blkself[8 * blk + g];
+                if (self != 0xffffu)
+                {
+                  const double *zr = xs + self * LDR + 2 * k * NP;
+#pragma unroll
+                  for (int p = 0; p < NP; ++p)
+                  {
+                    zl[p] = zr[p];
+                    zh[p] = zr[NP + p];
+                  }
+                }
+                else
+                {
+                  const double *xr = a.X + (size_t)row * a.ldx + 2 * k * NP;
+                  ldg_row_if<NP>(zl, xr, true);
+                  ldg_row_if<NP>(zh, xr + NP, true);
+                }
+                double *er = a.E0 + (size_t)row * a.ldx + 2 * k * NP;
+                const double *rr = a.E1 + (size_t)row * a.ldx + 2 * k * NP;
+                ldg_row_if<NP>(ol, er, true);
+                ldg_row_if<NP>(oh, er + NP, true);
+                ldg_row_if<NP>(rl, rr, true);
+                ldg_row_if<NP>(rh, rr + NP, true);
+                const double bd = a.ebeta * __ldg(a.edinv + row);
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+                {
+                  lo[p] = zl[p] + a.ealpha * (zl[p] - ol[p]) + bd * (rl[p] - lo[p]);
+                  hi[p] = zh[p] + a.ealpha * (zh[p] - oh[p]) + bd * (rh[p] - hi[p]);
+                }
+                stg_row<NP>(er, lo);
+                stg_row<NP>(er + NP, hi);
+              }
+              else
+              {
+                double *yr = a.Y + (size_t)row * a.ldx + 2 * k * NP;
+                stg_row<NP>(yr, lo);
+                stg_row<NP>(yr + NP, hi);
+              }
               if (DOT)
               {
                 // X(row, :) -- from the staged tile when the row's own column is among the tile's columns (any matrix with

@@ -31,6 +31,7 @@
 //                                                      of the spectrum of D^-1 A (Gershgorin); +inf if some a_ii <= 0
 //   int cheb_start(Blk Z, Blk Zold, Blk R, double s);  Z = s D^-1 R ; Zold = 0
 //   int cheb_step(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta);
+//   int apply_A_cheb(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta);  AZ = A Z, then cheb_step (may be fused: AZ untouched)
 //                                                      Zold <- Z + alpha (Z - Zold) + beta D^-1 (R - AZ)   (next iterate)
 //   int project(Blk W, Blk X, Blk BX);                 W <- W - X (BX^T W)
 //   int grams(int count, const Blk *L, const Blk *R, const char *sym, double *out);   out[i] = L_i^T R_i (m x m row-major)
@@ -218,9 +219,9 @@ namespace de
         DE_LOBPCG_TRY(ops.cheb_start(CZ, CD, W, 1.0 / cheb_theta));
         for (int i = 0; i < prm.cheb_degree; ++i)
         {
-          DE_LOBPCG_TRY(ops.apply_A(CAD, CZ));
           const double rho_new = 1.0 / (2.0 * sigma1 - rho);
-          DE_LOBPCG_TRY(ops.cheb_step(CD, CZ, W, CAD, rho_new * rho, 2.0 * rho_new / cheb_delta));
+          // CAD = A CZ ; CD <- CZ + rho' rho (CZ - CD) + (2 rho' / delta) D^-1 (W - CAD)   (one fused pass where the ops can)
+          DE_LOBPCG_TRY(ops.apply_A_cheb(CD, CZ, W, CAD, rho_new * rho, 2.0 * rho_new / cheb_delta));
           std::swap(CD, CZ); // CZ = newest iterate
           rho = rho_new;
         }

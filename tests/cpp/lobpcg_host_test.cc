@@ -229,6 +229,11 @@ struct HostOps
       }
     return 0;
   }
+  int apply_A_cheb(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta)
+  {
+    apply_A(AZ, Z);
+    return cheb_step(Zold, Z, R, AZ, alpha, beta);
+  }
   int cheb_step(Blk Zold, Blk Z, Blk R, Blk AZ, double alpha, double beta)
   {
     for (int i = 0; i < n; ++i)
