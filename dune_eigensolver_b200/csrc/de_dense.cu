@@ -90,7 +90,12 @@ namespace dei
       // reduce -> (all-reduce) -> Cholesky / convergence test in ONE launch
       de::TailArgs t = ctx->tail;
       t.do_allreduce = multi ? 1 : 0;
-      if (multi)
+      if (multi && t.channel == 1)
+      {
+        t.pa = peer_args(ctx, ++ctx->ar_epoch_b); // the skippable all-reduce of the second CholQR sweep: its own channel
+        t.pa.channel = 1;
+      }
+      else if (multi)
         t.pa = peer_args(ctx, ++ctx->ar_epoch);
       t.ticket = ctx->dtail_ticket;
       ctx->tail_armed = false;
@@ -178,7 +183,7 @@ namespace dei
       de::TsArgs g = a;
       g.X = a.Out;
       g.ldx = a.ldo;
-      g.skip_flag = nullptr;
+      g.skip_flag = a.skip_flag; // (null except for the second sweep of a one-sweep-capable orthonormalisation)
       return launch_ts_t<M, false, true, true, true>(ctx, g, gram_out);
     }
     if constexpr (DO_UPDATE && (M <= 32 || !DO_GRAM) && (!DO_GRAM || (UPPER && SAME)))
@@ -474,10 +479,25 @@ namespace dei
       }
       // sweep 1: G = X^T X (already known if the SpMM that produced X ran its Gram epilogue) ; R1 = chol(G) ;
       // X <- X R1^-1 fused with G2 = X^T X of the result
+      // One sweep where one is enough (round 2): the tail of the first Gram reduction decides ON THE DEVICE, from the scaled
+      // Gram matrix, whether cond is so small that X chol(G)^-1 is orthonormal to the accuracy the second sweep's own test
+      // would accept (kernels_dense.cuh, kWellCond). If so a plain update runs, and the fused update + Gram, its reduction /
+      // all-reduce / Cholesky tail and the last update all skip themselves -- in the steady state of the subspace iteration
+      // that is every iteration. The launch sequence is the same either way (CUDA graph, several ranks in lock step).
+      const bool multi = ctx->nranks > 1;
+      const bool one_sweep_ok = ctx->use_one_sweep && ctx->dwell != nullptr && ctx->dtail_ticket != nullptr && G_ready == nullptr &&
+                                (!multi || (ctx->peer_ready && (size_t)m * m + m <= (size_t)de::kPeerSlotDoubles));
+      bool one_sweep = false;
       if (G_ready == nullptr)
       {
         arm_chol_tail(ctx, m, ctx->dR(), nullptr, nullptr);
+        if (one_sweep_ok)
+        {
+          ctx->tail.wellcond = ctx->dwell;
+          ctx->tail.flags_identity = ctx->dflags;
+        }
         DE_TRY(gram_device(ctx, m, n, X, m, X, m, true, ctx->dG()));
+        one_sweep = one_sweep_ok && ctx->tail_did_op; // the decision exists only if the fused tail ran
       }
       DE_TRY(chol_inverse(ctx, m, G_ready ? G_ready : ctx->dG(), ctx->dR(), nullptr, nullptr));
       de::TsArgs a{};
@@ -488,10 +508,22 @@ namespace dei
       a.Out = X;
       a.ldo = m;
       a.upper = 1;
+      if (one_sweep)
+      {
+        de::TsArgs u = a;
+        u.skip_flag = ctx->dwell + 1; // runs iff one sweep is enough
+        DE_TRY((launch_ts<true, false, false, true>(ctx, m, u, nullptr)));
+        a.skip_flag = ctx->dwell;     // the fused update + Gram runs iff it is not
+      }
       // sweep 2: R2 = chol(G2) ; X <- X R2^-1, skipped on the device when G2 = I to working precision. The factor of
       // sweep 1 is read at the start of the update kernel and overwritten by the tail of its reduction: the factor
       // fragments are in registers long before the last CTA of the reduction runs (it is a later launch).
       arm_chol_tail(ctx, m, ctx->dR(), nullptr, ctx->dflags);
+      if (one_sweep)
+      {
+        ctx->tail.skip = ctx->dwell;
+        ctx->tail.channel = 1;
+      }
       DE_TRY((launch_ts<true, true, true, true>(ctx, m, a, ctx->dG())));
       DE_TRY(allreduce_sum(ctx, ctx->dG(), (size_t)m * m));
       DE_TRY(chol_inverse(ctx, m, ctx->dG(), ctx->dR(), nullptr, ctx->dflags));

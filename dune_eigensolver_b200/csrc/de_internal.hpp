@@ -101,6 +101,9 @@ struct de_context
   size_t window_bytes = 0, halo_cap = 0;
   unsigned char *peer_base[de::kPeerMaxRanks] = {};
   unsigned long long ar_epoch = 0, halo_epoch = 0;
+  unsigned long long ar_epoch_b = 0; // all-reduce channel 1 (de::PeerArgs::channel)
+  int *dwell = nullptr;              // device int[2]: one CholQR sweep is enough / is not (chol_inverse2_body)
+  bool use_one_sweep = true;         // DE_B200_ONE_SWEEP=0: always two sweeps with the a-posteriori test (A/B measurements)
   // halo rows stored by the block-update kernels of an orthonormalisation (plan_fused_push, de_spmm.cu): push_pending is
   // what the next ts2_update launches add to their arguments; prepushed_* say which SpMM call finds its halo rows already
   // in the neighbours' windows (that call only releases the flags)

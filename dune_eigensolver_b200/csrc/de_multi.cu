@@ -438,7 +438,7 @@ extern "C"
       for (int q = 0; q < ndev; ++q)
         c->peer_base[q] = M->ctx[q]->window;
       c->peer_ipc = false;
-      c->ar_epoch = c->halo_epoch = 0;
+      c->ar_epoch = c->ar_epoch_b = c->halo_epoch = 0;
       c->peer_ready = true;
     }
     *out = M;

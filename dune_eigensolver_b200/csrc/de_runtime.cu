@@ -519,6 +519,8 @@ extern "C"
     ctx->device = device;
     if (const char *g = std::getenv("DE_B200_FUSED_PUSH")) // "1": halo rows leave with the block updates (A/B measurements; see de_internal.hpp)
       ctx->fused_push = g[0] != '0';
+    if (const char *g = std::getenv("DE_B200_ONE_SWEEP")) // "0": CholQR2 always runs its second sweep's test (A/B measurements)
+      ctx->use_one_sweep = g[0] != '0';
     if (const char *g = std::getenv("DE_B200_CHEB_EPILOGUE")) // "0": SpMM and Chebyshev update as two passes (A/B measurements)
       ctx->use_cheb_epilogue = g[0] != '0';
     if (const char *g = std::getenv("DE_B200_LINCOMB2")) // "0": first-generation FMA kernels (A/B measurements)
@@ -554,6 +556,8 @@ extern "C"
               cudaMalloc((void **)&ctx->dstatus, sizeof(int)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->dflags, 4 * sizeof(int)) == cudaSuccess &&
               cudaMalloc((void **)&ctx->dtail_ticket, sizeof(int)) == cudaSuccess &&
+              cudaMalloc((void **)&ctx->dwell, 2 * sizeof(int)) == cudaSuccess &&
+              cudaMemset(ctx->dwell, 0, 2 * sizeof(int)) == cudaSuccess &&
               cudaMemset(ctx->dtail_ticket, 0, sizeof(int)) == cudaSuccess &&
               cudaMemset(ctx->dflags, 0, 4 * sizeof(int)) == cudaSuccess &&
               cudaMallocHost((void **)&ctx->hsmall, kSmall * sizeof(double)) == cudaSuccess &&
@@ -597,6 +601,8 @@ extern "C"
     dev_free(ctx->dstatus);
     dev_free(ctx->dflags);
     dev_free(ctx->dtail_ticket);
+    if (ctx->dwell)
+      cudaFree(ctx->dwell);
     dev_free(ctx->stage);
     if (ctx->hsmall)
       cudaFreeHost(ctx->hsmall);
@@ -793,7 +799,7 @@ extern "C"
       }
       ctx->peer_base[q] = (unsigned char *)p;
     }
-    ctx->ar_epoch = ctx->halo_epoch = 0;
+    ctx->ar_epoch = ctx->ar_epoch_b = ctx->halo_epoch = 0;
     ctx->peer_ready = true; // the caller runs a barrier before the first collective (every window must be zeroed)
     return DE_OK;
   }

@@ -693,8 +693,7 @@ namespace dei
         r.dst[r.n] = reinterpret_cast<double *>(ctx->peer_base[A->peer[p]] + de::kPeerHaloOff + (size_t)(epoch & 1ull) * ctx->halo_cap) +
                      (size_t)A->deposit[p] * m;
         // = peer_halo_flag(base of the peer, parity, this rank), kernels_peer.cuh
-        r.flag[r.n] = reinterpret_cast<unsigned long long *>(ctx->peer_base[A->peer[p]]) + 2 * de::kPeerMaxRanks +
-                      (int)(epoch & 1ull) * de::kPeerMaxRanks + ctx->rank;
+        r.flag[r.n] = de::peer_halo_flag(ctx->peer_base[A->peer[p]], (int)(epoch & 1ull), ctx->rank);
         ++r.n;
       }
     r.release = 0;

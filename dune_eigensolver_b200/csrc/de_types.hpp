@@ -12,13 +12,18 @@ namespace de
   constexpr int kPeerSlotDoubles = 4224; // >= 64 + 64 * 64
   constexpr size_t kPeerFlagBytes = 4096;
   constexpr size_t kPeerArOff = kPeerFlagBytes;
-  constexpr size_t kPeerHaloOff = kPeerArOff + (size_t)2 * kPeerMaxRanks * kPeerSlotDoubles * sizeof(double);
+  constexpr int kPeerArChannels = 2; // all-reduce channels, each with two slot / flag sets (parity of its own epoch counter)
+  constexpr size_t kPeerHaloOff = kPeerArOff + (size_t)kPeerArChannels * 2 * kPeerMaxRanks * kPeerSlotDoubles * sizeof(double);
 
   struct PeerArgs
   {
     int rank, nranks;
     unsigned char *base[kPeerMaxRanks]; // window of every rank (own: local pointer)
     unsigned long long epoch;           // of this operation; parity = epoch & 1
+    int channel;                        // all-reduces: 0 = every all-reduce that always executes, 1 = the reduction of the second
+                                        // CholQR sweep, which skips itself on the device when one sweep is enough (the epochs of
+                                        // a channel advance on the host whether or not the launch executes; an executed all-reduce
+                                        // of channel 0 lies between any two of channel 1, so a skipped epoch cannot alias a slot)
     const int *done;                    // converged driver loop: no-op (the same on every rank)
     int *err;                           // device error flag: a peer did not arrive
     long long timeout;                  // clocks after which a spin on a peer flag gives up
@@ -84,6 +89,10 @@ namespace de
     double *info;
     int *identity_flag;
     int *done;
+    int *wellcond;       // optional int[2]: chol_inverse2_body's one-sweep decision (kernels_dense.cuh)
+    int *flags_identity; // ... which also sets this flag (the second sweep's last update skips itself on it)
+    const int *skip;     // optional: the whole launch is a no-op when *skip != 0 (second sweep after a one-sweep decision)
+    int channel;         // all-reduce channel of this tail (PeerArgs::channel)
     // convergence
     int k;
     double shift, tol;

@@ -264,10 +264,19 @@ namespace de
    *    factorisation   scaled row k -> shared; barrier; a_ij -= r_ki r_kj          (i > k)
    *    inverse         Gauss-Jordan from the bottom: x_k /= r_kk; x_i -= r_ik x_k   (i < k), X starts as I
    *  1024 threads: element (i, j) = (w + 32 a, l + 32 b) belongs to warp w, lane l, slot (a, b). */
+  /** wellcond (optional, int[2]) and wc_identity (int[1]): the caller asks whether ONE CholQR sweep with this Gram matrix is
+   *  enough. With C = D^-1/2 G D^-1/2 (unit diagonal; Cholesky is invariant under this scaling to first order) the eigenvalues
+   *  of C lie within ||C - I||_F of 1, so ||C - I||_F <= kWellCond bounds cond(C) by (1 + d) / (1 - d) = 3: the orthogonality
+   *  defect of X chol(G)^-1 is then a small multiple of the rounding error of G itself -- what the second sweep's own test
+   *  (max |G2 - I| <= 1e-14 on a computed G2) would accept. wellcond[0] = yes, wellcond[1] = no, wc_identity[0] = yes (the
+   *  flag the second sweep's update skips itself on). */
+  constexpr double kWellCond = 0.5;
+
   template <int MP>
   __device__ __forceinline__ void chol_inverse2_body(int tid, int m, const double *__restrict__ G, double *__restrict__ Rinv,
                                                      int *__restrict__ status, double *__restrict__ info,
-                                                     int *__restrict__ identity_flag, int *__restrict__ done)
+                                                     int *__restrict__ identity_flag, int *__restrict__ done,
+                                                     int *__restrict__ wellcond = nullptr, int *__restrict__ wc_identity = nullptr)
   {
     constexpr int E = MP / 32;
     __shared__ double rowk[2][MP];
@@ -331,6 +340,41 @@ namespace de
       bad = (identity_flag != nullptr && u <= 1.0e-14) ? -1 : 0; // -1: G = I to working precision, nothing to factor
     }
     __syncthreads();
+    if (wellcond != nullptr)
+    {
+      // ||C - I||_F^2 = 2 sum_{i < j} G_ij^2 / (G_ii G_jj); dorig[] was filled above, redmx[] is free again
+      double off = 0.0;
+#pragma unroll
+      for (int a = 0; a < E; ++a)
+#pragma unroll
+        for (int b = 0; b < E; ++b)
+        {
+          const int i = warp + 32 * a, j = lane + 32 * b;
+          if (i < j && j < m)
+          {
+            const double den = dorig[i] * dorig[j];
+            off += (den > 0.0) ? 2.0 * r[a][b] * r[a][b] / den : 1.0e300;
+          }
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        off += __shfl_xor_sync(0xffffffffu, off, o);
+      __syncthreads(); // everyone has read redmx / reddev of the first reduction
+      if (lane == 0)
+        redmx[warp] = off;
+      __syncthreads();
+      if (tid == 0)
+      {
+        double t = 0.0;
+        for (int q = 0; q < 32; ++q)
+          t += redmx[q];
+        const int ok = (t == t && t <= kWellCond * kWellCond) ? 1 : 0;
+        wellcond[0] = ok;
+        wellcond[1] = 1 - ok;
+        if (wc_identity != nullptr)
+          wc_identity[0] = ok;
+      }
+    }
     if (bad == -1)
     {
       // the update that would use the factor skips itself on the same flag; leave Rinv = I for any other reader

@@ -1,8 +1,8 @@
 // Multi-GPU data path over NVLink peer memory (one process per GPU; the windows are exchanged as CUDA IPC handles).
 //
 // Every rank owns a WINDOW in its HBM that all peers map:
-//     [0, 4 KB)            flags      ar_flag[2][8] | halo_flag[2][8] (64-bit epochs, written by the peers)
-//     [4 KB, +2*8 slots)   all-reduce slots, one per (parity, sender rank), kPeerSlotDoubles doubles each
+//     [0, 4 KB)            flags      ar_flag[2 channels][2][8] | halo_flag[2][8] (64-bit epochs, written by the peers)
+//     [4 KB, +2*2*8 slots) all-reduce slots, one per (channel, parity, sender rank), kPeerSlotDoubles doubles each
 //     [halo_off, +2*cap)   two halo buffers (parity of the SpMM call), laid out like the matrix's halo block
 //
 //  * peer_allreduce_kernel: one-shot all-reduce of a short vector (the m Rayleigh quotients and the m x m Gram
@@ -58,24 +58,25 @@ namespace de
     return true;
   }
 
-  __device__ __forceinline__ unsigned long long *peer_ar_flag(unsigned char *base, int parity, int sender)
+  // set = 2 * channel + parity
+  __host__ __device__ __forceinline__ unsigned long long *peer_ar_flag(unsigned char *base, int set, int sender)
   {
-    return reinterpret_cast<unsigned long long *>(base) + parity * kPeerMaxRanks + sender;
+    return reinterpret_cast<unsigned long long *>(base) + set * kPeerMaxRanks + sender;
   }
-  __device__ __forceinline__ unsigned long long *peer_halo_flag(unsigned char *base, int parity, int sender)
+  __host__ __device__ __forceinline__ unsigned long long *peer_halo_flag(unsigned char *base, int parity, int sender)
   {
-    return reinterpret_cast<unsigned long long *>(base) + 2 * kPeerMaxRanks + parity * kPeerMaxRanks + sender;
+    return reinterpret_cast<unsigned long long *>(base) + (2 * kPeerArChannels + parity) * kPeerMaxRanks + sender;
   }
-  __device__ __forceinline__ double *peer_ar_slot(unsigned char *base, int parity, int sender)
+  __device__ __forceinline__ double *peer_ar_slot(unsigned char *base, int set, int sender)
   {
-    return reinterpret_cast<double *>(base + kPeerArOff) + (size_t)(parity * kPeerMaxRanks + sender) * kPeerSlotDoubles;
+    return reinterpret_cast<double *>(base + kPeerArOff) + (size_t)(set * kPeerMaxRanks + sender) * kPeerSlotDoubles;
   }
 
   /** buf[0..len) <- sum over ranks, identical bits on every rank; executed by one CTA of 1024 threads (tid).
    *  buf may have been written by other CTAs of the same launch: it is read through L2. */
   __device__ __forceinline__ void peer_allreduce_body(const PeerArgs &pa, int tid, double *__restrict__ buf, int len)
   {
-    const int parity = (int)(pa.epoch & 1ull);
+    const int parity = 2 * pa.channel + (int)(pa.epoch & 1ull); // the slot / flag set
     for (int q = 0; q < pa.nranks; ++q)
     {
       double *dst = peer_ar_slot(pa.base[q], parity, pa.rank);

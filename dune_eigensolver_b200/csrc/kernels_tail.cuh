@@ -28,6 +28,8 @@ namespace de
     pdl_prologue();
     if (done_in != nullptr && *done_in != 0)
       return;
+    if (t.skip != nullptr && *t.skip != 0)
+      return; // one CholQR sweep was enough: the kernel that would have written the partials skipped itself too
     __shared__ double red[32][33];
     __shared__ int last;
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -74,9 +76,11 @@ namespace de
     if (t.kind & kTailChol)
     {
       if (t.m <= 32)
-        chol_inverse2_body<32>(tid, t.m, out + t.len2, t.Rinv, t.status, t.info, t.identity_flag, t.done);
+        chol_inverse2_body<32>(tid, t.m, out + t.len2, t.Rinv, t.status, t.info, t.identity_flag, t.done, t.wellcond,
+                               t.wellcond ? t.flags_identity : nullptr);
       else
-        chol_inverse2_body<64>(tid, t.m, out + t.len2, t.Rinv, t.status, t.info, t.identity_flag, t.done);
+        chol_inverse2_body<64>(tid, t.m, out + t.len2, t.Rinv, t.status, t.info, t.identity_flag, t.done, t.wellcond,
+                               t.wellcond ? t.flags_identity : nullptr);
     }
   }
 

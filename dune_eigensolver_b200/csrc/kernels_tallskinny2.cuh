@@ -327,6 +327,8 @@ namespace de
     constexpr int NPW = kTs2ProducerWarps, NCW = kTg2ConsumerWarps;
     extern __shared__ __align__(128) unsigned char dyn3[];
     pdl_prologue();
+    if (a.skip_flag != nullptr && *a.skip_flag != 0)
+      return; // (one-sweep CholQR: the second sweep's Gram matrix is not needed)
     if (a.done != nullptr && *a.done != 0)
       return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
