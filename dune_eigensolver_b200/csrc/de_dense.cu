@@ -120,6 +120,7 @@ namespace dei
     for (int q = 0; q < de::kPeerMaxRanks; ++q)
       pa.base[q] = ctx->peer_base[q];
     pa.epoch = epoch;
+    pa.channel = 0;
     pa.done = ctx->done_ptr;
     pa.err = ctx->dticket + 1;
     pa.timeout = ctx->peer_timeout_cycles;
