@@ -263,6 +263,38 @@ def test_block_update_and_project(ctx, n, m):
             E.block_project(dX, 0, 0, S)
 
 
+@pytest.mark.parametrize("n,m", [(20000, 32), (9000, 64), (5000, 8)])
+def test_orthonormalize_one_sweep_decision(ctx, oracle, monkeypatch, n, m):
+    """a block whose scaled Gram matrix is close to I (the steady state of the subspace iteration: X = A Q): the tail of the
+    first Gram reduction decides that ONE CholQR sweep is enough (kernels_dense.cuh, kWellCond). The result must be as
+    orthonormal as the two-sweep one, equal to it to rounding, and equal to the reference's Gram-Schmidt"""
+    Q0, _ = np.linalg.qr(rnd(n, m, 11))
+    X = Q0 * np.linspace(1.0, 1.3, m) + 1e-3 * rnd(n, m, 12) / np.sqrt(n)
+    dX = E.MultiVector.from_array(ctx, X)
+    c0 = ctx.launch_count()
+    E.orthonormalize_blocked(dX)
+    launches_one = ctx.launch_count() - c0
+    Q1 = dX.download()
+    dX.close()
+    assert np.abs(Q1.T @ Q1 - np.eye(m)).max() <= 1e-13
+    ref = oracle.orthonormalize(X)
+    assert np.abs(Q1 - ref).max() <= 1e-10
+    monkeypatch.setenv("DE_B200_ONE_SWEEP", "0")
+    ctx2 = E.Context(0)
+    try:
+        dX2 = E.MultiVector.from_array(ctx2, X)
+        c0 = ctx2.launch_count()
+        E.orthonormalize_blocked(dX2)
+        launches_two = ctx2.launch_count() - c0
+        Q2 = dX2.download()
+        dX2.close()
+    finally:
+        ctx2.close()
+    assert np.abs(Q2.T @ Q2 - np.eye(m)).max() <= 1e-13
+    assert np.abs(Q1 - Q2).max() <= 1e-12
+    assert launches_one > launches_two  # the extra launch is the plain update that replaces the fused update + Gram
+
+
 @pytest.mark.parametrize("n,m", [(36, 16), (64, 64), (3000, 8), (3000, 24), (50000, 32), (20000, 48), (100003, 64)])
 def test_orthonormalize_matches_oracle(ctx, oracle, n, m):
     X = rnd(n, m, 7)
