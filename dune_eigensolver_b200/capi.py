@@ -30,6 +30,7 @@ SIGNATURES = {
     "de_context_synchronize": [_vp],
     "de_context_launch_count": [_vp, _i64p],
     "de_context_set_profiling": [_vp, C.c_int],
+    "de_context_set_option": [_vp, C.c_char_p, C.c_int64],
     "de_context_profile": [_vp, C.c_int, _dp, _i64p, C.c_int],
     "de_comm_unique_id": [_vp],
     "de_context_init_comm": [_vp, C.c_int, C.c_int, _vp],

@@ -326,6 +326,11 @@ namespace de
     }
 
     constexpr long long kPlanePointsInL2 = 16384; // grid planes larger than this are swept in y chunks (grid_order)
+    inline long long &plane_points_setting()
+    {
+      static long long v = kPlanePointsInL2;
+      return v;
+    }
 
     /** tiles of tw x th x td points cut into row blocks of bw x bh x bd points (bw bh bd == 8) */
     inline void grid_order(long long n, long long S1, long long S2, int tw, int th, int td, int bw, int bh, int bd, Order &o)
@@ -341,9 +346,7 @@ namespace de
       // SpMM at 0.74 of HBM peak on 100^3, 0.70 on 200^3, 0.60 on 256^3), so y is cut into chunks and the sweep over z runs
       // inside a chunk: the rows between two uses of a halo plane shrink to nx * ychunk * td.
       long long ychunk = ny;
-      long long limit = kPlanePointsInL2;
-      if (const char *e = std::getenv("DE_B200_BRB_PLANE_POINTS")) // tuning aid (tools/ychunk_probe.py)
-        limit = std::max<long long>(64, std::atoll(e));
+      const long long limit = plane_points_setting(); // (de_context_set_option "brb_plane_points"; tools/ychunk_probe.py)
       if (nz > 1 && nx * ny > limit)
       {
         const long long want = std::max<long long>(th, limit * 3 / 4 / nx);

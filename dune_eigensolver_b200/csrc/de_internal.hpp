@@ -92,8 +92,8 @@ struct de_context
     const double *r = nullptr, *dinv = nullptr;
     double alpha = 0.0, beta = 0.0;
   } epi;
-  bool use_cheb_epilogue = true; // DE_B200_CHEB_EPILOGUE=0: SpMM + cheb_step_kernel as two passes (A/B measurements)
-  bool use_lincomb2 = true;   // LOBPCG combination / projection on the tensor-core kernel (kernels_lincomb2.cuh); DE_B200_LINCOMB2=0: first version
+  bool use_cheb_epilogue = true; // option "cheb_epilogue" 0: SpMM + cheb_step_kernel as two passes (A/B measurements)
+  bool use_lincomb2 = true;   // LOBPCG combination / projection on the tensor-core kernel (kernels_lincomb2.cuh); option "lincomb2" 0: first version
   bool use_loop_graph = true; // StandardLargest: replay the steady-state iterations from a CUDA graph (one GPU)
   long long peer_timeout_cycles = 60000000000LL; // spins on peer flags give up after this many clocks (~30 s)
   bool peer_ipc = true; // peer windows were opened from CUDA IPC handles (else: same-process allocations, de_multi.cu)
@@ -103,14 +103,14 @@ struct de_context
   unsigned long long ar_epoch = 0, halo_epoch = 0;
   unsigned long long ar_epoch_b = 0; // all-reduce channel 1 (de::PeerArgs::channel)
   int *dwell = nullptr;              // device int[2]: one CholQR sweep is enough / is not (chol_inverse2_body)
-  bool use_one_sweep = true;         // DE_B200_ONE_SWEEP=0: always two sweeps with the a-posteriori test (A/B measurements)
+  bool use_one_sweep = true;         // option "one_sweep" 0: always two sweeps with the a-posteriori test (A/B measurements)
   // halo rows stored by the block-update kernels of an orthonormalisation (plan_fused_push, de_spmm.cu): push_pending is
   // what the next ts2_update launches add to their arguments; prepushed_* say which SpMM call finds its halo rows already
   // in the neighbours' windows (that call only releases the flags)
   de::PushRanges push_pending{};
   // OFF by default -- measured on B200 (profiles/README.md, round 2): the 64-byte row segments a warp of the update kernel
   // stores from its registers cross NVLink far less efficiently than halo_push_kernel's coalesced 16-byte-per-thread rows:
-  // 100^3 on 2 GPUs 13.17 -> 13.04 ms (-1 %), 256^3 on 2 GPUs 0.1065 -> 0.111 s (+4 %). DE_B200_FUSED_PUSH=1 enables it.
+  // 100^3 on 2 GPUs 13.17 -> 13.04 ms (-1 %), 256^3 on 2 GPUs 0.1065 -> 0.111 s (+4 %). de_context_set_option("fused_push", 1) enables it.
   bool fused_push = false;
   const double *prepushed_X = nullptr;
   const de_matrix *prepushed_A = nullptr;
@@ -482,6 +482,7 @@ namespace dei
 
   // ---- de_spmm.cu ---------------------------------------------------------------------------------------------
   /** Y = A X; dot: also dp = diag(X^T Y) into ctx->dDP(); gram_out (dot only): may receive G = Y^T Y, see spmm_device */
+  void brb_set_plane_points(long long points); // process-wide: brb::plane_points_setting() (brb_format.hpp)
   int spmm_device(de_context *ctx, const de_matrix *A, const double *X, double *Y, int m, bool dot, bool *gram_out = nullptr);
   int spmm_cheb_device(de_context *ctx, const de_matrix *A, const double *Z, double *Zold, const double *R, const double *dinv,
                        double alpha, double beta, int m, bool *fused);

@@ -517,16 +517,6 @@ extern "C"
     if (!ctx)
       return set_error(nullptr, DE_ERR_ALLOC, "de_context_create: out of host memory");
     ctx->device = device;
-    if (const char *g = std::getenv("DE_B200_FUSED_PUSH")) // "1": halo rows leave with the block updates (A/B measurements; see de_internal.hpp)
-      ctx->fused_push = g[0] != '0';
-    if (const char *g = std::getenv("DE_B200_ONE_SWEEP")) // "0": CholQR2 always runs its second sweep's test (A/B measurements)
-      ctx->use_one_sweep = g[0] != '0';
-    if (const char *g = std::getenv("DE_B200_CHEB_EPILOGUE")) // "0": SpMM and Chebyshev update as two passes (A/B measurements)
-      ctx->use_cheb_epilogue = g[0] != '0';
-    if (const char *g = std::getenv("DE_B200_LINCOMB2")) // "0": first-generation FMA kernels (A/B measurements)
-      ctx->use_lincomb2 = g[0] != '0';
-    if (const char *g = std::getenv("DE_B200_LOOP_GRAPH")) // "0": plain launches in the StandardLargest loop (A/B measurements)
-      ctx->use_loop_graph = g[0] != '0';
     auto bail = [&](int code) {
       std::string msg = ctx->err;
       de_context_destroy(ctx);
@@ -641,6 +631,32 @@ extern "C"
       return set_error(nullptr, DE_ERR_INVALID, "null context");
     DE_TRY(bind_device(ctx));
     DE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DE_OK;
+  }
+
+  int de_context_set_option(de_context *ctx, const char *name, int64_t value)
+  {
+    if (!ctx || !name)
+      return set_error(ctx, DE_ERR_INVALID, "de_context_set_option: bad arguments");
+    const std::string key(name);
+    if (key == "one_sweep")
+      ctx->use_one_sweep = value != 0;
+    else if (key == "cheb_epilogue")
+      ctx->use_cheb_epilogue = value != 0;
+    else if (key == "lincomb2")
+      ctx->use_lincomb2 = value != 0;
+    else if (key == "loop_graph")
+      ctx->use_loop_graph = value != 0;
+    else if (key == "fused_push")
+      ctx->fused_push = value != 0;
+    else if (key == "brb_plane_points")
+    {
+      if (value < 64)
+        return set_error(ctx, DE_ERR_INVALID, "de_context_set_option: brb_plane_points must be at least 64");
+      brb_set_plane_points((long long)value);
+    }
+    else
+      return set_error(ctx, DE_ERR_INVALID, "de_context_set_option: unknown option '" + key + "'");
     return DE_OK;
   }
 

@@ -729,6 +729,8 @@ namespace dei
     return rc;
   }
 
+  void brb_set_plane_points(long long points) { de::brb::plane_points_setting() = points; }
+
   int spmm_device(de_context *ctx, const de_matrix *A, const double *X, double *Y, int m, bool dot, bool *gram_out)
   {
     return dot ? spmm_device_t<true>(ctx, A, X, Y, m, gram_out) : spmm_device_t<false>(ctx, A, X, Y, m, nullptr);

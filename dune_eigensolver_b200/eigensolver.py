@@ -39,6 +39,22 @@ def start_block(n, m, seed=123):
     return out
 
 
+# A/B switches: the LIBRARY reads no environment variable; this mirror maps DE_B200_<NAME> onto
+# de_context_set_option for bench.py, the probes and the tests
+ENV_OPTIONS = {"DE_B200_ONE_SWEEP": "one_sweep", "DE_B200_CHEB_EPILOGUE": "cheb_epilogue", "DE_B200_LINCOMB2": "lincomb2",
+               "DE_B200_LOOP_GRAPH": "loop_graph", "DE_B200_FUSED_PUSH": "fused_push",
+               "DE_B200_BRB_PLANE_POINTS": "brb_plane_points"}
+
+
+def _apply_env_options(handle):
+    import os
+
+    for var, name in ENV_OPTIONS.items():
+        val = os.environ.get(var, "")
+        if val != "":
+            check(capi.lib().de_context_set_option(handle, name.encode(), int(val)), handle)
+
+
 class Context:
     """One GPU + stream + workspaces (+ NCCL communicator once init_comm was called)."""
 
@@ -46,6 +62,11 @@ class Context:
         self._h = C.c_void_p()
         check(capi.lib().de_context_create(device, C.c_void_p(stream) if stream else None, C.byref(self._h)))
         self.device = device
+        _apply_env_options(self._h)
+
+    def set_option(self, name, value):
+        """tuning / A-B switch of this context (include/dune_eigensolver_b200.h: de_context_set_option)"""
+        check(capi.lib().de_context_set_option(self._h, name.encode(), int(value)), self._h)
 
     def close(self):
         if self._h:
@@ -240,6 +261,10 @@ class Multi:
         self.ndev = len(d)
         if timeout_s is not None:
             self._check(capi.lib().de_multi_set_timeout(self._h, float(timeout_s)))
+        for r in range(self.ndev):  # the DE_B200_* switches apply to every rank's context
+            h = C.c_void_p()
+            self._check(capi.lib().de_multi_context(self._h, r, C.byref(h)))
+            _apply_env_options(h)
 
     def close(self):
         if self._h:

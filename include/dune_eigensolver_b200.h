@@ -72,6 +72,18 @@ int de_context_launch_count(const de_context *ctx, int64_t *count);
 #define DE_PROF_CATEGORIES 10
 /* enable: 0 = off, 1 = every category, otherwise a bit mask of categories shifted left by one (2 << DE_PROF_SPMM | ...) */
 int de_context_set_profiling(de_context *ctx, int enable);
+/* Tuning / A-B switches of a context. The library itself reads NO environment variable for behaviour; the
+ * Python mirror maps DE_B200_<NAME> onto this call for bench.py and the tests. Every option defaults to the faster, measured
+ * setting; all settings give the same results to rounding. name (value):
+ *   "one_sweep"      (1)  CholQR: one sweep when the first Gram matrix says it is enough, 0 = always the second sweep's test
+ *   "cheb_epilogue"  (1)  LOBPCG: Chebyshev update as an epilogue of the tensor-core SpMM, 0 = SpMM + streaming kernel
+ *   "lincomb2"       (1)  LOBPCG combination / projection on the tensor-core kernel, 0 = first-generation FMA kernels
+ *   "loop_graph"     (1)  StandardLargest: steady-state iterations replayed from a CUDA graph (one GPU), 0 = plain launches
+ *   "fused_push"     (0)  halo rows stored by the block-update kernels instead of halo_push_kernel (measured slower)
+ *   "brb_plane_points" (16384) PROCESS-WIDE: grid planes with more points are swept in y chunks by the BRB tile order; takes
+ *                          effect for matrices created afterwards
+ * Unknown names return DE_ERR_INVALID. */
+int de_context_set_option(de_context *ctx, const char *name, int64_t value);
 int de_context_profile(de_context *ctx, int category, double *total_ms, int64_t *launches, int reset);
 
 /* Multi-GPU (new; the reference is single-threaded): one process per GPU. Rank 0 obtains an

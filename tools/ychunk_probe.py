@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Which y-chunk of the BRB tile order (brb::grid_order) keeps the halo planes of X in the L2? Times the SpMM kernel on one
-matrix for several values of DE_B200_BRB_PLANE_POINTS (the matrix is re-uploaded for each: the order is fixed at build time).
+matrix for several values of the brb_plane_points option (the matrix is re-uploaded for each: the order is fixed at build time).
 
     python tools/ychunk_probe.py --grid 256 --stencil q1 --cols 32
 """
@@ -36,7 +36,7 @@ def main():
         X.upload_rowmajor(np.random.default_rng(m).standard_normal((n, m)))
         Y = E.MultiVector(ctx, n, m)
         for pts in args.points.split(","):
-            os.environ["DE_B200_BRB_PLANE_POINTS"] = pts
+            ctx.set_option("brb_plane_points", int(pts))
             dA = E.Matrix(ctx, A)
             for _ in range(3):
                 E.matmul_sparse_tallskinny_with_dots(Y, dA, X)
