@@ -726,9 +726,9 @@ namespace de_b200
         work[sparent[s]] += work[s];
     }
     const double total_work = std::accumulate(work.begin(), work.end(), 0.0, [](double a, double b) { return std::max(a, b); });
-    // a supernode belongs to the "top" if its subtree holds more than 1 / (4 nthreads) of the work; the maximal subtrees
+    // a supernode belongs to the "top" if its subtree holds more than 1 / (8 nthreads) of the work; the maximal subtrees
     // below the top are the independent tasks
-    const double cut = nthreads > 1 ? total_work / (4.0 * nthreads) : 2.0 * total_work;
+    const double cut = nthreads > 1 ? total_work / (8.0 * nthreads) : 2.0 * total_work;
     std::vector<char> top(nsuper, 0);
     for (I s = 0; s < nsuper; ++s)
       top[s] = work[s] > cut;
