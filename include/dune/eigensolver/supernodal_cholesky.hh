@@ -44,12 +44,36 @@
 #include <numeric>
 #include <stdexcept>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "sparse_lu.hh"
 
 namespace de_b200
 {
+  /** allocator whose default construction leaves the memory as it is: resize() of the factor's value array (29 GB for the
+   *  128^3 pencil) must not zero-fill it on one thread -- the numeric phase writes every entry, in parallel */
+  template <class T>
+  struct default_init_allocator : std::allocator<T>
+  {
+    template <class U>
+    struct rebind
+    {
+      using other = default_init_allocator<U>;
+    };
+    default_init_allocator() = default;
+    template <class U>
+    default_init_allocator(const default_init_allocator<U> &) noexcept {}
+    template <class U, class... Args>
+    void construct(U *p, Args &&...args)
+    {
+      if constexpr (sizeof...(Args) == 0)
+        ::new ((void *)p) U;
+      else
+        ::new ((void *)p) U(std::forward<Args>(args)...);
+    }
+  };
+
   struct SupernodalFactor
   {
     long n = 0, nsuper = 0;
@@ -61,7 +85,7 @@ namespace de_b200
     std::vector<long> rowptr; // [nsuper + 1] offsets into rowidx
     std::vector<int> rowidx;  // rows of supernode s: its own columns first, then the update rows, ascending
     std::vector<long> valptr; // [nsuper + 1] offsets into val
-    std::vector<double> val;  // block of supernode s: rows(s) x cols(s), column-major, leading dimension rows(s);
+    std::vector<double, default_init_allocator<double>> val; // block of supernode s: rows(s) x cols(s), column-major, leading dimension rows(s);
                               // the strict upper triangle of the diagonal block is zero
     std::vector<long> sparent; // supernodal elimination tree (-1: root)
     long rows(long s) const { return rowptr[s + 1] - rowptr[s]; }
@@ -419,6 +443,14 @@ namespace de_b200
     std::vector<I> perm = compute_ordering(n, rowptr, col, ordering);
     const double t_order = since(t_start);
     const auto t_sym = std::chrono::steady_clock::now();
+    auto t_lap = t_sym;
+    auto lap = [&](const char *what) { // DE_TRACE_FACTOR: where the symbolic phase spends its time
+      if (sn_detail::factor_trace().on)
+      {
+        std::fprintf(stderr, "[de factor] symbolic: %-28s %.2f s\n", what, since(t_lap));
+        t_lap = std::chrono::steady_clock::now();
+      }
+    };
 
     // ---- lower part of the permuted matrix by rows: row k holds (column i < k, value), sorted; diagonal apart ------------
     std::vector<I> iperm(n), Bp, Bj;
@@ -519,6 +551,7 @@ namespace de_b200
       etree(parent);
     }
 
+    lap("permute + etree + postorder");
     // ---- column counts (Gilbert / Ng / Peyton): the tree is postordered, so post[k] = k ---------------------------------
     std::vector<I> cc(n, 0);
     {
@@ -577,6 +610,7 @@ namespace de_b200
           cc[parent[j]] += cc[j];
     }
 
+    lap("column counts");
     // ---- supernodes: fundamental, then relaxed amalgamation of a last child into its parent ------------------------------
     std::vector<I> nchild(n, 0);
     for (I j = 0; j < n; ++j)
@@ -637,6 +671,7 @@ namespace de_b200
       sparent[s] = p == -1 ? -1 : snode_of[p];
     }
 
+    lap("supernodes");
     // ---- row structure of every supernode (own columns, then update rows ascending) -------------------------------------
     std::vector<I> rptr(nsuper + 1, 0);
     std::vector<std::vector<int>> upd_rows(nsuper);
@@ -681,6 +716,7 @@ namespace de_b200
         std::sort(R.begin(), R.end());
       }
     }
+    lap("row structure");
     F.nsuper = nsuper;
     F.perm = perm;
     F.sfirst = sfirst;
@@ -709,8 +745,9 @@ namespace de_b200
       std::copy(upd_rows[s].begin(), upd_rows[s].end(), R + ns);
       std::vector<int>().swap(upd_rows[s]);
     }
-    F.val.assign(F.valptr[nsuper], 0.0);
+    F.val.resize(F.valptr[nsuper]); // NOT zero-filled (default_init_allocator): every entry is written by the numeric phase
 
+    lap("index lists + factor storage");
     const double t_symbolic = since(t_sym);
     const auto t_num = std::chrono::steady_clock::now();
     // ---- numeric: subtrees on different threads, the fronts above them with all threads inside the dense kernels ---------
@@ -858,7 +895,10 @@ namespace de_b200
         for (I j = c * cchunk; j < std::min<I>(r, (c + 1) * cchunk); ++j)
         {
           if (j < ns)
+          {
+            std::memset(Lb + j * r, 0, sizeof(double) * (size_t)j); // the strict upper triangle of the pivot block is zero
             std::memcpy(Lb + j + j * r, Fr + j + j * r, sizeof(double) * (size_t)(r - j));
+          }
           else
             std::memcpy(U + (j - ns) + (j - ns) * nu, Fr + j + j * r, sizeof(double) * (size_t)(r - j));
         }
