@@ -319,7 +319,7 @@ namespace de_b200
       return true;
     }
 
-    constexpr long kPanel = 48;  // pivot columns per panel of the blocked factorisation
+    constexpr long kPanel = 96;  // pivot columns per panel of the blocked factorisation
     constexpr long kTile = 192;  // rows / columns per task of a trailing update
 
     /** dense partial Cholesky of a front: Fr = r x r column-major (ld r), lower triangle assembled; the first ns columns are
@@ -395,13 +395,25 @@ namespace de_b200
         const long nb = (nt + kTile - 1) / kTile;
         auto tile = [&](long ti, long tj) {
           const long i0 = ti * kTile, i1 = std::min(nt, i0 + kTile), j0 = tj * kTile, j1 = std::min(nt, j0 + kTile);
+          const long mi = i1 - i0, nj = j1 - j0;
+          // the two panel slices of the tile, packed: in the front they are w columns a whole front column apart (one
+          // page each for a large front), which the k loop of the kernel walks through for every 24 x 4 register tile
+          thread_local std::vector<double> pa, pb;
+          pa.resize((size_t)mi * w);
+          for (long p = 0; p < w; ++p)
+            std::memcpy(pa.data() + p * mi, Pan + i0 + p * r, sizeof(double) * (size_t)mi);
           if (ti != tj)
-            gemm_nt_sub(T + i0 + j0 * r, r, Pan + i0, r, Pan + j0, r, i1 - i0, j1 - j0, w);
+          {
+            pb.resize((size_t)nj * w);
+            for (long p = 0; p < w; ++p)
+              std::memcpy(pb.data() + p * nj, Pan + j0 + p * r, sizeof(double) * (size_t)nj);
+            gemm_nt_sub(T + i0 + j0 * r, r, pa.data(), mi, pb.data(), nj, mi, nj, w);
+          }
           else
             for (long jj = j0; jj < j1; jj += 4) // lower part of a diagonal tile in strips of 4 columns (the few entries
             {                                      // above the diagonal inside a strip are never read)
               const long wj = std::min<long>(4, j1 - jj);
-              gemm_nt_sub(T + jj + jj * r, r, Pan + jj, r, Pan + jj, r, i1 - jj, wj, w);
+              gemm_nt_sub(T + jj + jj * r, r, pa.data() + (jj - i0), mi, pa.data() + (jj - i0), mi, i1 - jj, wj, w);
             }
         };
         const long ntasks = nb * (nb + 1) / 2;
