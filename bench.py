@@ -95,8 +95,8 @@ def parse():
     ap.add_argument("--no-tight", action="store_true", help="skip the tight-tolerance StandardLargest leg")
     ap.add_argument("--c3-grid", type=int, default=80,
                     help="grid of the configs[2] leg (Q1 stiffness + mass pencil, GeneralizedInverse with the factored solve, 64 "
-                         "pairs); the one-time host factorisation grows like grid^6 (80: ~25 s, 96: ~70 s, 128: ~7 min on 16 "
-                         "cores; profiles/ holds a 128^3 run); 0 skips it")
+                         "pairs); the one-time host factorisation grows like grid^6 (80: ~18 s, 128: ~6 min on the 8-core "
+                         "build container, faster on a GPU box's 16 cores; profiles/ holds a 128^3 run); 0 skips it")
     ap.add_argument("--full-reference", action="store_true",
                     help="--impl reference: every replica runs the COMPLETE solve (default: bounded sample, extrapolated)")
     return ap.parse_args()
