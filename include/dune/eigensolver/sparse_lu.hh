@@ -55,8 +55,11 @@ namespace de_b200
     natural = 0,
     nested_dissection = 1, // geometric on detected structured grids with diagonal neighbours, else METIS (else RCM)
     rcm = 2,
-    graph_nested_dissection = 3 // always the graph partitioner (METIS when compiled in, else RCM)
+    graph_nested_dissection = 3, // always the graph partitioner (METIS when compiled in, else RCM)
+    geometric_nested_dissection = 4 // plane separators on a detected structured grid of any size and stencil (else as 1)
   };
+  constexpr long kGeometricFromRows = 50000; // nested_dissection: below this size the graph partitioner is fast enough (and is
+                                             // what the GPU parity tests of the small configurations were verified with)
 
   namespace detail
   {
@@ -257,7 +260,7 @@ namespace de_b200
     std::iota(perm.begin(), perm.end(), 0L);
     if (ord == Ordering::natural || n < 3)
       return perm;
-    if (ord == Ordering::nested_dissection)
+    if (ord == Ordering::geometric_nested_dissection || (ord == Ordering::nested_dissection && n >= kGeometricFromRows))
     {
       // structured grids (every matrix of BASELINE.json): geometric nested dissection in O(n) instead of a graph partitioner
       // (METIS: 31 s for the 128^3 pencil, a fifth of the whole factorisation)
@@ -266,7 +269,8 @@ namespace de_b200
       // finds 30-35 % less fill than planes and keeps the job.
       long nx = 0, ny = 0, nz = 0;
       bool diagonal_neighbours = false;
-      if (detail::detect_structured_grid(n, rowptr, col, nx, ny, nz, diagonal_neighbours) && diagonal_neighbours)
+      if (detail::detect_structured_grid(n, rowptr, col, nx, ny, nz, diagonal_neighbours) &&
+          (diagonal_neighbours || ord == Ordering::geometric_nested_dissection))
       {
         std::vector<long> g;
         g.reserve(n);
@@ -279,7 +283,7 @@ namespace de_b200
     std::vector<int64_t> xadj, adj;
     detail::symmetric_adjacency(n, rowptr, col, xadj, adj);
 #ifdef DE_B200_HAVE_METIS
-    if (ord == Ordering::nested_dissection || ord == Ordering::graph_nested_dissection)
+    if (ord == Ordering::nested_dissection || ord == Ordering::graph_nested_dissection || ord == Ordering::geometric_nested_dissection)
     {
       int64_t nv = n;
       std::vector<int64_t> p(n), ip(n);

@@ -364,7 +364,8 @@ int de_host_sym_gen_eig(int n, const double *GA, const double *GB, double *w, do
 int de_start_block(int64_t n, int m, unsigned seed, double *out_panel8);
 /* one-time host factorisation filling the UMFPACK field contract (stand-in for umfpacktools.hh:46-199 where
  * UMFPACK is unavailable): ordering 0 = natural, 1 = nested dissection (geometric on
- * structured grids with diagonal neighbours, else METIS), 2 = RCM, 3 = always the graph partitioner (METIS) */
+ * structured grids with diagonal neighbours and at least 50 000 rows, else METIS), 2 = RCM, 3 = always the graph partitioner
+ * (METIS), 4 = geometric on any detected structured grid */
 int de_host_factorize(int64_t n, const int64_t *rowptr, const int64_t *col, const double *val, int ordering,
                       int scale_rows, de_host_factor **out);
 int de_host_factor_arrays(const de_host_factor *F, int64_t *n, int64_t *lnz, int64_t *unz, const long **Lp,
